@@ -1,0 +1,312 @@
+// ba_capi.cu -- the extern "C" boundary of libbagpu.so (see include/bagpu.h for the contract).
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include "ba_internal.h"
+
+namespace {
+
+template <class T>
+int dev_alloc(ba_handle* h, T** p, size_t n) {
+  if (*p) return BA_OK;
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
+  return BA_OK;
+}
+
+int fail(ba_handle* h, int code, const char* msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+// uploads x (host) and refreshes the camera records
+int stage_x(ba_handle* h, const double* x) {
+  int rc = dev_alloc(h, &h->d_x, (size_t)h->nvar());
+  if (rc) return rc;
+  BA_CUDA(cudaMemcpyAsync(h->d_x, x, sizeof(double) * (size_t)h->nvar(), cudaMemcpyHostToDevice, h->stream));
+  return BA_OK;
+}
+
+int refresh_cams(ba_handle* h, const double* x_dev) {
+  ba::launch_cam_precompute(x_dev, h->npnts, h->ncams, h->d_camtab, h->stream);
+  BA_CUDA(cudaGetLastError());
+  return BA_OK;
+}
+
+int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, const int64_t* pnt,
+                const double* pt2d, int device, int rank, int nranks, ba_handle** out) {
+  if (!out) return BA_ERR_ARG;
+  *out = nullptr;
+  if (ncams < 0 || npnts < 0 || nobs < 0 || (nobs > 0 && (!cam || !pnt || !pt2d)) || nranks < 1 || rank < 0 ||
+      rank >= nranks || 9 * ncams + 3 * npnts >= (int64_t)1 << 31 || nobs >= (int64_t)1 << 31)
+    return BA_ERR_ARG;
+  ba_handle* h = new (std::nothrow) ba_handle();
+  if (!h) return BA_ERR_ARG;
+  *out = h;  // returned even on failure so that ba_last_error can be read; caller destroys it
+  h->device = device;
+  h->ncams = ncams; h->npnts = npnts; h->nobs = nobs; h->rank = rank; h->nranks = nranks;
+  bool sorted = true;
+  for (int64_t k = 0; k < nobs; ++k) {
+    if (cam[k] < 1 || cam[k] > ncams || pnt[k] < 1 || pnt[k] > npnts)
+      return fail(h, BA_ERR_ARG, "camera/point index out of range (indices are 1-based)");
+    if (k && pnt[k] < pnt[k - 1]) sorted = false;
+  }
+  h->sorted = sorted;
+  h->obs0 = 0; h->obs1 = nobs; h->pnt0 = 0; h->pnt1 = npnts;
+  if (nranks > 1) {
+    std::vector<int64_t> cuts((size_t)nranks + 1);
+    int rc = ba_partition_observations(nobs, pnt, nranks, cuts.data());
+    if (rc) return fail(h, rc, "observation sharding needs point-major order");
+    h->obs0 = cuts[rank]; h->obs1 = cuts[rank + 1];
+    // owned points: those whose observations fall into the range (points without any observation
+    // are attached to the rank that owns the preceding point; rank 0 takes the leading ones)
+    h->pnt0 = (rank == 0) ? 0 : (h->obs0 < nobs ? pnt[h->obs0] - 1 : npnts);
+    h->pnt1 = (rank == nranks - 1) ? npnts : (h->obs1 < nobs ? pnt[h->obs1] - 1 : npnts);
+  }
+  const int64_t nl = h->nobs_l();
+  h->h_cam.resize((size_t)nl);
+  h->h_pnt.resize((size_t)nl);
+  for (int64_t k = 0; k < nl; ++k) {
+    h->h_cam[(size_t)k] = (int32_t)(cam[h->obs0 + k] - 1);
+    h->h_pnt[(size_t)k] = (int32_t)(pnt[h->obs0 + k] - 1);
+  }
+  BA_CUDA(cudaSetDevice(device));
+  BA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  int rc;
+  if ((rc = dev_alloc(h, &h->d_cam, (size_t)nl))) return rc;
+  if ((rc = dev_alloc(h, &h->d_pnt, (size_t)nl))) return rc;
+  if ((rc = dev_alloc(h, &h->d_pt2d, (size_t)nl))) return rc;
+  if ((rc = dev_alloc(h, &h->d_camtab, (size_t)ncams * 24))) return rc;
+  if (nl) {
+    BA_CUDA(cudaMemcpyAsync(h->d_cam, h->h_cam.data(), sizeof(int32_t) * (size_t)nl, cudaMemcpyHostToDevice, h->stream));
+    BA_CUDA(cudaMemcpyAsync(h->d_pnt, h->h_pnt.data(), sizeof(int32_t) * (size_t)nl, cudaMemcpyHostToDevice, h->stream));
+    BA_CUDA(cudaMemcpyAsync(h->d_pt2d, pt2d + 2 * h->obs0, sizeof(double) * 2 * (size_t)nl, cudaMemcpyHostToDevice, h->stream));
+  }
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ba_version(void) { return "bagpu 0.1 (sm_100a, fp64)"; }
+
+const char* ba_last_error(const ba_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int ba_partition_observations(int64_t nobs, const int64_t* pnt, int nranks, int64_t* cuts) {
+  if (nranks < 1 || !cuts || (nobs > 0 && !pnt)) return BA_ERR_ARG;
+  for (int64_t k = 1; k < nobs; ++k)
+    if (pnt[k] < pnt[k - 1]) return BA_ERR_UNSORTED;
+  cuts[0] = 0;
+  for (int r = 1; r < nranks; ++r) {
+    int64_t c = (nobs * r) / nranks;  // balanced by observation count ...
+    if (c < cuts[r - 1]) c = cuts[r - 1];
+    while (c > 0 && c < nobs && pnt[c] == pnt[c - 1]) ++c;  // ... moved up to the next point boundary
+    cuts[r] = c;
+  }
+  cuts[nranks] = nobs;
+  return BA_OK;
+}
+
+int ba_create(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, const int64_t* pnt,
+              const double* pt2d, int device, ba_handle** out) {
+  return create_impl(ncams, npnts, nobs, cam, pnt, pt2d, device, 0, 1, out);
+}
+
+int ba_create_sharded(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, const int64_t* pnt,
+                      const double* pt2d, int device, int rank, int nranks, ba_handle** out) {
+  return create_impl(ncams, npnts, nobs, cam, pnt, pt2d, device, rank, nranks, out);
+}
+
+int ba_destroy(ba_handle* h) {
+  if (!h) return BA_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  ba::lm_release(h);
+  cudaFree(h->d_cam); cudaFree(h->d_pnt); cudaFree(h->d_pt2d); cudaFree(h->d_x); cudaFree(h->d_camtab);
+  cudaFree(h->d_cx); cudaFree(h->d_vals); cudaFree(h->d_v); cudaFree(h->d_w); cudaFree(h->d_rows);
+  cudaFree(h->d_cols);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return BA_OK;
+}
+
+int ba_shard_range(const ba_handle* h, int64_t* obs0, int64_t* obs1, int64_t* pnt0, int64_t* pnt1) {
+  if (!h) return BA_ERR_ARG;
+  if (obs0) *obs0 = h->obs0;
+  if (obs1) *obs1 = h->obs1;
+  if (pnt0) *pnt0 = h->pnt0;
+  if (pnt1) *pnt1 = h->pnt1;
+  return BA_OK;
+}
+
+int ba_set_stream(ba_handle* h, void* s) {
+  if (!h) return BA_ERR_ARG;
+  BA_CUDA(cudaSetDevice(h->device));
+  if (h->stream) BA_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = reinterpret_cast<cudaStream_t>(s);
+  h->own_stream = false;
+  return BA_OK;
+}
+
+int ba_alloc_pinned(uint64_t bytes, void** out) {
+  if (!out) return BA_ERR_ARG;
+  return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? BA_OK : BA_ERR_CUDA;
+}
+
+int ba_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? BA_OK : BA_ERR_CUDA; }
+
+int ba_sync(ba_handle* h) {
+  if (!h) return BA_ERR_ARG;
+  BA_CUDA(cudaSetDevice(h->device));
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+// ---- device-pointer variants ------------------------------------------------------------------
+int ba_residual_dev(ba_handle* h, const double* x, double* cx) {
+  if (!h || !x || !cx) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc = refresh_cams(h, x);
+  if (rc) return rc;
+  ba::launch_eval(h, x, h->d_camtab, cx, nullptr, h->stream);
+  BA_CUDA(cudaGetLastError());
+  return BA_OK;
+}
+
+int ba_jac_coord_dev(ba_handle* h, const double* x, double* vals) {
+  if (!h || !x || !vals) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc = refresh_cams(h, x);
+  if (rc) return rc;
+  ba::launch_eval(h, x, h->d_camtab, nullptr, vals, h->stream);
+  BA_CUDA(cudaGetLastError());
+  return BA_OK;
+}
+
+int ba_residual_jac_dev(ba_handle* h, const double* x, double* cx, double* vals) {
+  if (!h || !x || !cx || !vals) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc = refresh_cams(h, x);
+  if (rc) return rc;
+  ba::launch_eval(h, x, h->d_camtab, cx, vals, h->stream);
+  BA_CUDA(cudaGetLastError());
+  return BA_OK;
+}
+
+int ba_jac_structure_dev(ba_handle* h, int64_t* rows, int64_t* cols) {
+  if (!h || !rows || !cols) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  ba::launch_jac_structure(h, rows, cols, h->stream);
+  BA_CUDA(cudaGetLastError());
+  return BA_OK;
+}
+
+int ba_jprod_dev(ba_handle* h, const double* x, const double* v, double* Jv) {
+  if (!h || !x || !v || !Jv) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc = refresh_cams(h, x);
+  if (rc) return rc;
+  ba::launch_jprod(h, x, h->d_camtab, v, Jv, h->stream);
+  BA_CUDA(cudaGetLastError());
+  return BA_OK;
+}
+
+int ba_jtprod_dev(ba_handle* h, const double* x, const double* v, double* Jtv) {
+  if (!h || !x || !v || !Jtv) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc = refresh_cams(h, x);
+  if (rc) return rc;
+  ba::launch_jtprod(h, x, h->d_camtab, v, Jtv, h->stream);
+  BA_CUDA(cudaGetLastError());
+  if (h->nranks > 1 && h->comm) return ba::allreduce_sum(h, Jtv, (size_t)h->nvar());
+  return BA_OK;
+}
+
+// ---- host-pointer calls (the ones Julia's ccall binds) ----------------------------------------
+int ba_residual(ba_handle* h, const double* x, double* cx) {
+  if (!h || !x || !cx) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = stage_x(h, x))) return rc;
+  if ((rc = dev_alloc(h, &h->d_cx, 2 * (size_t)h->nobs_l()))) return rc;
+  if ((rc = ba_residual_dev(h, h->d_x, h->d_cx))) return rc;
+  BA_CUDA(cudaMemcpyAsync(cx, h->d_cx, sizeof(double) * 2 * (size_t)h->nobs_l(), cudaMemcpyDeviceToHost, h->stream));
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+int ba_jac_coord(ba_handle* h, const double* x, double* vals) {
+  if (!h || !x || !vals) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = stage_x(h, x))) return rc;
+  if ((rc = dev_alloc(h, &h->d_vals, 24 * (size_t)h->nobs_l()))) return rc;
+  if ((rc = ba_jac_coord_dev(h, h->d_x, h->d_vals))) return rc;
+  BA_CUDA(cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * 24 * (size_t)h->nobs_l(), cudaMemcpyDeviceToHost, h->stream));
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+int ba_residual_jac(ba_handle* h, const double* x, double* cx, double* vals) {
+  if (!h || !x || !cx || !vals) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = stage_x(h, x))) return rc;
+  if ((rc = dev_alloc(h, &h->d_cx, 2 * (size_t)h->nobs_l()))) return rc;
+  if ((rc = dev_alloc(h, &h->d_vals, 24 * (size_t)h->nobs_l()))) return rc;
+  if ((rc = ba_residual_jac_dev(h, h->d_x, h->d_cx, h->d_vals))) return rc;
+  BA_CUDA(cudaMemcpyAsync(cx, h->d_cx, sizeof(double) * 2 * (size_t)h->nobs_l(), cudaMemcpyDeviceToHost, h->stream));
+  BA_CUDA(cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * 24 * (size_t)h->nobs_l(), cudaMemcpyDeviceToHost, h->stream));
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+int ba_jac_structure(ba_handle* h, int64_t* rows, int64_t* cols) {
+  if (!h || !rows || !cols) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc;
+  const size_t n = 24 * (size_t)h->nobs_l();
+  if ((rc = dev_alloc(h, &h->d_rows, n))) return rc;
+  if ((rc = dev_alloc(h, &h->d_cols, n))) return rc;
+  if ((rc = ba_jac_structure_dev(h, h->d_rows, h->d_cols))) return rc;
+  BA_CUDA(cudaMemcpyAsync(rows, h->d_rows, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, h->stream));
+  BA_CUDA(cudaMemcpyAsync(cols, h->d_cols, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, h->stream));
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  // the structure is needed once per solve (src/lm.jl:53): do not keep 2 x 192 B/obs resident
+  cudaFree(h->d_rows); cudaFree(h->d_cols);
+  h->d_rows = h->d_cols = nullptr;
+  return BA_OK;
+}
+
+int ba_jprod(ba_handle* h, const double* x, const double* v, double* Jv) {
+  if (!h || !x || !v || !Jv) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = stage_x(h, x))) return rc;
+  if ((rc = dev_alloc(h, &h->d_v, (size_t)h->nvar()))) return rc;
+  if ((rc = dev_alloc(h, &h->d_w, std::max((size_t)h->nvar(), 2 * (size_t)h->nobs_l())))) return rc;
+  BA_CUDA(cudaMemcpyAsync(h->d_v, v, sizeof(double) * (size_t)h->nvar(), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = ba_jprod_dev(h, h->d_x, h->d_v, h->d_w))) return rc;
+  BA_CUDA(cudaMemcpyAsync(Jv, h->d_w, sizeof(double) * 2 * (size_t)h->nobs_l(), cudaMemcpyDeviceToHost, h->stream));
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+int ba_jtprod(ba_handle* h, const double* x, const double* v, double* Jtv) {
+  if (!h || !x || !v || !Jtv) return fail(h, BA_ERR_ARG, "null argument");
+  BA_CUDA(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = stage_x(h, x))) return rc;
+  if ((rc = dev_alloc(h, &h->d_v, (size_t)h->nvar()))) return rc;
+  if ((rc = dev_alloc(h, &h->d_w, std::max((size_t)h->nvar(), 2 * (size_t)h->nobs_l())))) return rc;
+  BA_CUDA(cudaMemcpyAsync(h->d_w, v, sizeof(double) * 2 * (size_t)h->nobs_l(), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = ba_jtprod_dev(h, h->d_x, h->d_w, h->d_v))) return rc;
+  BA_CUDA(cudaMemcpyAsync(Jtv, h->d_v, sizeof(double) * (size_t)h->nvar(), cudaMemcpyDeviceToHost, h->stream));
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+}  // extern "C"

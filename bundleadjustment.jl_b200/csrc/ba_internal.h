@@ -1,0 +1,93 @@
+// ba_internal.h -- handle layout and launcher prototypes shared by the .cu files of libbagpu.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/bagpu.h"
+
+struct ncclComm;
+
+#define BA_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      char b_[512];                                                                            \
+      snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      h->err = b_;                                                                             \
+      return BA_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+// Device-resident state of the LM solver (allocated on first use).
+struct ba_lm_state {
+  // schedules built once per problem on the host
+  int32_t* d_tstart = nullptr;   // point-major warp tasks: obs offsets, ntasks+1
+  int64_t ntasks = 0;
+  int32_t* d_cperm = nullptr;    // observations sorted by camera (local obs ids)
+  int32_t* d_ctask_cam = nullptr;   // camera-major tasks: camera id
+  int32_t* d_ctask_beg = nullptr;   // first position in d_cperm
+  int32_t* d_ctask_end = nullptr;
+  int64_t nctasks = 0;
+  // vectors
+  double* d_x = nullptr;      // current iterate (nvar)
+  double* d_xt = nullptr;     // trial iterate
+  double* d_delta = nullptr;  // step (nvar): points then cameras
+  double* d_cam = nullptr;    // camera records for d_x
+  double* d_camt = nullptr;   // camera records for d_xt
+  double* d_V = nullptr;      // 6 per local point (sym 3x3 of A'A)
+  double* d_gp = nullptr;     // 3 per local point: -A'F
+  double* d_Vinv = nullptr;   // 6 per local point: (V + lambda I)^-1
+  double* d_wp = nullptr;     // 3 per local point: Vinv * gp
+  double* d_camacc = nullptr; // per camera: [U(45) | gc(9) | corr(45) | rhsc(9)] = 108
+  double* d_Minv = nullptr;   // 81 per camera
+  double* d_pcg = nullptr;    // 6 vectors of 9*ncams: b, xc, r, z, p, acc
+  double* d_scal = nullptr;   // device scalars (see ba_lm.cu)
+  double* h_scal = nullptr;   // pinned mirror
+  bool ready = false;
+};
+
+struct ba_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t ncams = 0, npnts = 0, nobs = 0;            // global problem
+  int64_t obs0 = 0, obs1 = 0, pnt0 = 0, pnt1 = 0;    // this rank's shard (0-based, half open)
+  int rank = 0, nranks = 1;
+  bool sorted = false;                               // point-major order
+  int32_t* d_cam = nullptr;   // local obs: 0-based camera id
+  int32_t* d_pnt = nullptr;   // local obs: 0-based GLOBAL point id
+  double2* d_pt2d = nullptr;  // local obs
+  std::vector<int32_t> h_cam, h_pnt;  // host copies kept for schedule construction
+  double* d_x = nullptr;      // staging for host-pointer calls (nvar)
+  double* d_camtab = nullptr; // ncams * 24
+  double* d_cx = nullptr;     // staging: 2*nobs_l
+  double* d_vals = nullptr;   // staging: 24*nobs_l
+  double* d_v = nullptr;      // staging for jprod/jtprod inputs/outputs
+  double* d_w = nullptr;
+  int64_t* d_rows = nullptr;  // staging
+  int64_t* d_cols = nullptr;
+  ba_lm_state lm;
+  ncclComm* comm = nullptr;
+  mutable std::string err;
+  int64_t nvar() const { return 9 * ncams + 3 * npnts; }
+  int64_t nobs_l() const { return obs1 - obs0; }
+  int64_t npnts_l() const { return pnt1 - pnt0; }
+};
+
+namespace ba {
+// ---- ba_eval.cu -----------------------------------------------------------------------------
+void launch_cam_precompute(const double* x, int64_t npnts, int64_t ncams, double* camtab, cudaStream_t s);
+void launch_eval(const ba_handle* h, const double* x, const double* camtab, double* cx, double* vals,
+                 cudaStream_t s);
+void launch_jac_structure(const ba_handle* h, int64_t* rows, int64_t* cols, cudaStream_t s);
+void launch_jprod(const ba_handle* h, const double* x, const double* camtab, const double* v, double* Jv,
+                  cudaStream_t s);
+void launch_jtprod(const ba_handle* h, const double* x, const double* camtab, const double* v, double* Jtv,
+                   cudaStream_t s);
+// ---- ba_lm.cu -------------------------------------------------------------------------------
+int lm_prepare(ba_handle* h);
+void lm_release(ba_handle* h);
+int allreduce_sum(ba_handle* h, double* buf, size_t n);
+}  // namespace ba
