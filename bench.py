@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of BASELINE.json on N B200s (or the CPU reference arm).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (libbagpu.so)
+    python bench.py --impl reference --steps K --warmup W     # CPU restatement of the reference
+
+A *step* is one fused evaluation ``x -> (cx, vals)`` (cons! + jac_coord!, src/BALNLPModels.jl:115-206)
+of the Venice-1778-shaped synthetic problem, observation-sharded over the ranks (no collective on this
+path).  ``value`` = observations of the whole problem / max-over-ranks device time, inputs resident in
+HBM; ``e2e`` = the same through the host-pointer C-ABI call (pinned host buffers, H2D of x and D2H of
+cx/vals inside the timed region).  The LM leg reports full Levenberg-Marquardt iterations per second
+on the same problem (``lm`` object).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+METRIC = "residual+Jacobian Mobs/s"
+UNIT = "Mobs/s"
+
+
+def algorithmic_bytes_per_obs(p) -> float:
+    """2 int32 indices + pt2d 16 + cx 16 + vals 192 + each parameter read once."""
+    return 232.0 + 8.0 * p.nvar / p.nobs
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+            if self.stop_flag.is_set():
+                break
+        self.proc.terminate()
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=2.0)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the restatement of the reference (oracle/ba_oracle.c) on the host cores.  cons! uses all
+    threads (Threads.@threads, src/BALNLPModels.jl:45); jac_coord! is capped at 3 like the reference
+    (src/BALNLPModels.jl:167-168)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import bundleadjustment.jl_b200.synth as synth  # host-only generator
+    from oracle import oracle as O
+    p = synth.make_problem(args.workload)
+    nt = O.max_threads()
+    cx = np.empty(2 * p.nobs)
+    vals = np.empty(24 * p.nobs)
+
+    def step():
+        O.lib().bao_cons(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, cx, p.nobs, p.npnts, nt)
+        O.lib().bao_jac_coord(p.cam_idx, p.pnt_idx, p.x0, vals, p.nobs, p.npnts, min(nt, 3))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = p.nobs / dt / 1e6
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": args.workload, "ncams": p.ncams, "npnts": p.npnts, "nobs": p.nobs},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
+                            "sample": "full %s problem per step; cons! on %d threads, jac_coord! on %d "
+                                      "(reference caps it at 3)" % (args.workload, nt, min(nt, 3))},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(p, workload, budget_s=12.0):
+    from oracle import oracle as O
+    nt = O.max_threads()
+    cx = np.empty(2 * p.nobs)
+    vals = np.empty(24 * p.nobs)
+    O.cons_jac(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.npnts, nt, cx, vals)  # warm-up / page-in
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        O.cons_jac(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.npnts, nt, cx, vals)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 50:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": p.nobs / dt / 1e6, "unit": UNIT, "cores": nt, "kind": "port",
+            "sample": "%d full passes of the %s problem (cons! + jac_coord!, all %d threads for both)"
+                      % (reps, workload, nt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="venice-1778")
+    ap.add_argument("--lm-iters", type=int, default=8, help="LM iterations timed in the lm leg (0 = skip)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import bundleadjustment.jl_b200 as ba
+    L = ba._lib.lib()  # raises if the CUDA library is missing: no fallback
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    p = ba.synth.make_problem(args.workload)
+    m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs, name=p.name,
+                       device=local, rank=rank, nranks=world)
+    h = m.handle
+    nl = m.nobs_local
+    stream = torch.cuda.current_stream()
+    ba._lib.check(L.ba_set_stream(h, C.c_void_p(stream.cuda_stream)), h)
+
+    # ---- device-resident leg ---------------------------------------------------------------------
+    x_d = torch.from_numpy(p.x0).cuda()
+    step_bytes = 26 * 8 * nl
+    ring = max(2, int(np.ceil(3 * 126e6 / max(step_bytes, 1))))  # outputs rotate through > 2x L2 of memory
+    ring = min(ring, 16)
+    cx_d = [torch.empty(2 * nl, dtype=torch.float64, device="cuda") for _ in range(ring)]
+    vals_d = [torch.empty(24 * nl, dtype=torch.float64, device="cuda") for _ in range(ring)]
+
+    def dev_step(i):
+        j = i % ring
+        rc = L.ba_residual_jac_dev(h, C.c_void_p(x_d.data_ptr()), C.c_void_p(cx_d[j].data_ptr()),
+                                   C.c_void_p(vals_d[j].data_ptr()))
+        if rc:
+            ba._lib.check(rc, h)
+
+    for i in range(max(args.warmup, 3)):
+        dev_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        dev_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev = float(t.item())
+
+    # dominant kernel alone (k_eval<cx,vals>): the library brackets that launch with its own CUDA events
+    # on the launching stream; read them step by step (same rotating buffers)
+    ks = []
+    for i in range(args.steps):
+        dev_step(i)
+        f = C.c_float()
+        ba._lib.check(L.ba_last_eval_ms(h, C.byref(f)), h)
+        ks.append(f.value)
+    barrier()
+    k_ms = float(np.mean(ks))
+    clocks = sampler.summary() if rank == 0 else None
+
+    # ---- end-to-end leg through the host-pointer call (what Julia's ccall hits) -------------------------
+    def pinned(nbytes):
+        ptr = C.c_void_p()
+        ba._lib.check(L.ba_alloc_pinned(nbytes, C.byref(ptr)))
+        return ptr
+
+    x_h, cx_h, vals_h = pinned(8 * p.nvar), pinned(16 * max(nl, 1)), pinned(192 * max(nl, 1))
+    C.memmove(x_h, p.x0.ctypes.data, 8 * p.nvar)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ba._lib.check(L.ba_residual_jac(h, x_h, cx_h, vals_h), h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ba._lib.check(L.ba_residual_jac(h, x_h, cx_h, vals_h), h)   # returns with results on the host
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d, d2h = 8 * p.nvar, 208 * nl
+    for ptr in (x_h, cx_h, vals_h):
+        L.ba_free_pinned(ptr)
+
+    # ---- LM leg: full Levenberg-Marquardt iterations per second on the same problem ----------------------
+    lm = None
+    if args.lm_iters > 0:
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (C.c_uint8 * 128)()
+                ba._lib.check(L.ba_comm_unique_id(buf))
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            uid = uid.cuda()
+            dist.broadcast(uid, 0)
+            arr = (C.c_uint8 * 128)(*uid.cpu().tolist())
+            ba._lib.check(L.ba_comm_init(h, arr), h)
+        barrier()
+        t0 = time.perf_counter()
+        st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=args.lm_iters - 1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lm = {"metric": "LM iters/s", "value": st.iter / float(t.item()), "iters": st.iter,
+              "pcg_iters": st.pcg_iters, "objective0": st.rows[0]["f"] if st.rows else None,
+              "objective": st.objective, "status": st.status, "timings_ms": st.timings_ms,
+              "e2e": "x0 host -> solution host through Levenberg_Marquardt()"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bpo = algorithmic_bytes_per_obs(p)
+        # per-launch algorithmic bytes of the dominant kernel on one rank (rank 0's shard)
+        achieved = bpo * nl / (k_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": p.nobs / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "ncams": p.ncams, "npnts": p.npnts, "nobs": p.nobs,
+                       "sharding": "observations, contiguous point ranges, %d rank(s)" % world,
+                       "l2": "per-step footprint %.0f MB, outputs rotate over %d buffers (> L2)" % (
+                           step_bytes / 1e6, ring)},
+            "e2e": {"value": p.nobs / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "ba_residual_jac (host pointers, pinned), per rank"},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "ba::k_eval<true,true>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": k_ms, "bytes_per_obs": bpo, "frac_of_nominal_8TBs": achieved / 8000.0},
+            "clocks": clocks,
+        }
+        if lm:
+            out["lm"] = lm
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(p, args.workload)
+        print(json.dumps(out), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,8 @@ int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, 
   BA_CUDA(cudaSetDevice(device));
   BA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
+  BA_CUDA(cudaEventCreate(&h->ev_eval0));
+  BA_CUDA(cudaEventCreate(&h->ev_eval1));
   int rc;
   if ((rc = dev_alloc(h, &h->d_cam, (size_t)nl))) return rc;
   if ((rc = dev_alloc(h, &h->d_pnt, (size_t)nl))) return rc;
@@ -124,9 +126,12 @@ int ba_destroy(ba_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   ba::lm_release(h);
+  ba::comm_release(h);
   cudaFree(h->d_cam); cudaFree(h->d_pnt); cudaFree(h->d_pt2d); cudaFree(h->d_x); cudaFree(h->d_camtab);
   cudaFree(h->d_cx); cudaFree(h->d_vals); cudaFree(h->d_v); cudaFree(h->d_w); cudaFree(h->d_rows);
   cudaFree(h->d_cols);
+  if (h->ev_eval0) cudaEventDestroy(h->ev_eval0);
+  if (h->ev_eval1) cudaEventDestroy(h->ev_eval1);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return BA_OK;
@@ -162,6 +167,14 @@ int ba_sync(ba_handle* h) {
   if (!h) return BA_ERR_ARG;
   BA_CUDA(cudaSetDevice(h->device));
   BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+int ba_last_eval_ms(ba_handle* h, float* ms) {
+  if (!h || !ms) return BA_ERR_ARG;
+  BA_CUDA(cudaSetDevice(h->device));
+  BA_CUDA(cudaEventSynchronize(h->ev_eval1));
+  BA_CUDA(cudaEventElapsedTime(ms, h->ev_eval0, h->ev_eval1));
   return BA_OK;
 }
 

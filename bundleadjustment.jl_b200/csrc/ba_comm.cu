@@ -1,0 +1,106 @@
+// ba_comm.cu -- NCCL plumbing for the observation-sharded (one process per GPU) mode.
+//
+// The reference has no communication layer at all; this is the only exchange
+// the sharded hot path needs: sum-allreduce of camera-sized buffers and a handful of scalars over
+// NVLink 5 / NVSwitch.  NCCL is bound lazily with dlopen so that libbagpu.so loads (and every
+// single-GPU entry point works) in processes that never touch NCCL; inside a torch process the
+// already-loaded libnccl.so.2 is reused.
+#include <dlfcn.h>
+#include <cstring>
+#include "ba_internal.h"
+
+namespace {
+
+// The few NCCL symbols used, declared locally (stable since NCCL 2.0) so that no NCCL header is
+// needed at build time.
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_get_uid)(nccl_uid*);
+typedef int (*fn_comm_init_rank)(ncclComm**, int, nccl_uid, int);
+typedef int (*fn_comm_destroy)(ncclComm*);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int /*dtype*/, int /*op*/, ncclComm*, cudaStream_t);
+typedef const char* (*fn_errstr)(int);
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+struct nccl_api {
+  void* so = nullptr;
+  fn_get_uid get_uid = nullptr;
+  fn_comm_init_rank init_rank = nullptr;
+  fn_comm_destroy destroy = nullptr;
+  fn_allreduce allreduce = nullptr;
+  fn_errstr errstr = nullptr;
+  bool ok = false;
+};
+
+nccl_api& api() {
+  static nccl_api a;
+  if (a.ok || a.so) return a;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    a.so = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (a.so) break;
+  }
+  if (!a.so) return a;
+  a.get_uid = (fn_get_uid)dlsym(a.so, "ncclGetUniqueId");
+  a.init_rank = (fn_comm_init_rank)dlsym(a.so, "ncclCommInitRank");
+  a.destroy = (fn_comm_destroy)dlsym(a.so, "ncclCommDestroy");
+  a.allreduce = (fn_allreduce)dlsym(a.so, "ncclAllReduce");
+  a.errstr = (fn_errstr)dlsym(a.so, "ncclGetErrorString");
+  a.ok = a.get_uid && a.init_rank && a.destroy && a.allreduce;
+  return a;
+}
+
+}  // namespace
+
+namespace ba {
+
+int allreduce_sum(ba_handle* h, double* buf, size_t n) {
+  if (h->nranks == 1 || n == 0) return BA_OK;
+  if (!h->comm) {
+    h->err = "sharded handle used before ba_comm_init";
+    return BA_ERR_COMM;
+  }
+  const int rc = api().allreduce(buf, buf, n, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+  if (rc != 0) {
+    h->err = std::string("ncclAllReduce: ") + (api().errstr ? api().errstr(rc) : "error");
+    return BA_ERR_COMM;
+  }
+  return BA_OK;
+}
+
+void comm_release(ba_handle* h) {
+  if (h->comm && api().ok) api().destroy(h->comm);
+  h->comm = nullptr;
+}
+
+}  // namespace ba
+
+extern "C" {
+
+int ba_comm_unique_id(uint8_t id128[128]) {
+  if (!id128 || !api().ok) return BA_ERR_COMM;
+  nccl_uid u;
+  if (api().get_uid(&u) != 0) return BA_ERR_COMM;
+  memcpy(id128, u.internal, 128);
+  return BA_OK;
+}
+
+int ba_comm_init(ba_handle* h, const uint8_t id128[128]) {
+  if (!h || !id128) return BA_ERR_ARG;
+  if (h->nranks == 1) return BA_OK;
+  if (!api().ok) {
+    h->err = "libnccl.so.2 not found";
+    return BA_ERR_COMM;
+  }
+  BA_CUDA(cudaSetDevice(h->device));
+  nccl_uid u;
+  memcpy(u.internal, id128, 128);
+  const int rc = api().init_rank(&h->comm, h->nranks, u, h->rank);
+  if (rc != 0) {
+    h->err = std::string("ncclCommInitRank: ") + (api().errstr ? api().errstr(rc) : "error");
+    h->comm = nullptr;
+    return BA_ERR_COMM;
+  }
+  return BA_OK;
+}
+
+}  // extern "C"

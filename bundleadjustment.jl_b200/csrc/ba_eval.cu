@@ -220,12 +220,14 @@ void launch_eval(const ba_handle* h, const double* x, const double* camtab, doub
   if (n == 0) return;
   const int per_block = EVAL_THREADS;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
+  if (h->ev_eval0) cudaEventRecord(h->ev_eval0, s);
   if (cx && vals)
     k_eval<true, true><<<blocks, EVAL_THREADS, 0, s>>>(h->d_cam, h->d_pnt, h->d_pt2d, x, camtab, cx, vals, n);
   else if (vals)
     k_eval<false, true><<<blocks, EVAL_THREADS, 0, s>>>(h->d_cam, h->d_pnt, h->d_pt2d, x, camtab, cx, vals, n);
   else
     k_eval<true, false><<<blocks, EVAL_THREADS, 0, s>>>(h->d_cam, h->d_pnt, h->d_pt2d, x, camtab, cx, vals, n);
+  if (h->ev_eval1) cudaEventRecord(h->ev_eval1, s);
 }
 
 void launch_jac_structure(const ba_handle* h, int64_t* rows, int64_t* cols, cudaStream_t s) {

@@ -68,6 +68,7 @@ struct ba_handle {
   double* d_w = nullptr;
   int64_t* d_rows = nullptr;  // staging
   int64_t* d_cols = nullptr;
+  cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch
   ba_lm_state lm;
   ncclComm* comm = nullptr;
   mutable std::string err;
@@ -89,5 +90,7 @@ void launch_jtprod(const ba_handle* h, const double* x, const double* camtab, co
 // ---- ba_lm.cu -------------------------------------------------------------------------------
 int lm_prepare(ba_handle* h);
 void lm_release(ba_handle* h);
+// ---- ba_comm.cu -----------------------------------------------------------------------------
 int allreduce_sum(ba_handle* h, double* buf, size_t n);
+void comm_release(ba_handle* h);
 }  // namespace ba

@@ -23,6 +23,11 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#define BA_API __attribute__((visibility("default")))
+#else
+#define BA_API
+#endif
 
 typedef struct ba_handle ba_handle;
 
@@ -39,52 +44,55 @@ enum {
 /* Copies indices and pt2d to the device (caller buffers are not retained).  device = CUDA
  * ordinal.  The handle owns a stream and all device storage; free with ba_destroy (from a
  * Julia finalizer). */
-int ba_create(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam_idx_1based,
+BA_API int ba_create(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam_idx_1based,
               const int64_t* pnt_idx_1based, const double* pt2d, int device, ba_handle** out);
 /* Observation-sharded variant for one-process-per-GPU runs: rank r of nranks keeps a contiguous
  * range of observations cut on point boundaries (needs point-major order).  All arrays passed
  * are the FULL problem; outputs of the per-observation calls are the LOCAL slices, whose global
  * ranges ba_shard_range reports (0-based, half-open). */
-int ba_create_sharded(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam_idx_1based,
+BA_API int ba_create_sharded(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam_idx_1based,
                       const int64_t* pnt_idx_1based, const double* pt2d, int device, int rank,
                       int nranks, ba_handle** out);
-int ba_destroy(ba_handle* h);
-int ba_shard_range(const ba_handle* h, int64_t* obs0, int64_t* obs1, int64_t* pnt0, int64_t* pnt1);
+BA_API int ba_destroy(ba_handle* h);
+BA_API int ba_shard_range(const ba_handle* h, int64_t* obs0, int64_t* obs1, int64_t* pnt0, int64_t* pnt1);
 /* Host-side partition used by ba_create_sharded (no GPU needed): cuts[r]..cuts[r+1] is rank r's
  * observation range; cuts has nranks+1 entries.  Returns BA_ERR_UNSORTED if not point-major. */
-int ba_partition_observations(int64_t nobs, const int64_t* pnt_idx_1based, int nranks, int64_t* cuts);
-const char* ba_last_error(const ba_handle* h);
-const char* ba_version(void);
+BA_API int ba_partition_observations(int64_t nobs, const int64_t* pnt_idx_1based, int nranks, int64_t* cuts);
+BA_API const char* ba_last_error(const ba_handle* h);
+BA_API const char* ba_version(void);
 /* Run this handle's work on an existing stream (cudaStream_t passed as void*), e.g. the
  * caller's current stream so that its own CUDA events bracket the kernels. */
-int ba_set_stream(ba_handle* h, void* cuda_stream);
+BA_API int ba_set_stream(ba_handle* h, void* cuda_stream);
 /* Pinned host buffers for callers that want full PCIe rate on the host-pointer calls. */
-int ba_alloc_pinned(uint64_t bytes, void** out);
-int ba_free_pinned(void* p);
+BA_API int ba_alloc_pinned(uint64_t bytes, void** out);
+BA_API int ba_free_pinned(void* p);
 
 /* ---- NLPModels surface ---------------------------------------------------------------------- */
 /* NLPModels.cons!(nlp, x, cx), src/BALNLPModels.jl:115-122 (== residual! of FeasibilityResidual,
  * call sites src/lm.jl:39,252,268).  NaN/Inf are left in cx like the reference. */
-int ba_residual(ba_handle* h, const double* x, double* cx);
+BA_API int ba_residual(ba_handle* h, const double* x, double* cx);
 /* NLPModels.jac_structure!(nlp, rows, cols), src/BALNLPModels.jl:125-158 (src/lm.jl:53). */
-int ba_jac_structure(ba_handle* h, int64_t* rows, int64_t* cols);
+BA_API int ba_jac_structure(ba_handle* h, int64_t* rows, int64_t* cols);
 /* NLPModels.jac_coord!(nlp, x, vals), src/BALNLPModels.jl:161-206 (src/lm.jl:54,341). */
-int ba_jac_coord(ba_handle* h, const double* x, double* vals);
+BA_API int ba_jac_coord(ba_handle* h, const double* x, double* vals);
 /* cons! + jac_coord! in one pass over the observations (the headline metric). */
-int ba_residual_jac(ba_handle* h, const double* x, double* cx, double* vals);
+BA_API int ba_residual_jac(ba_handle* h, const double* x, double* cx, double* vals);
 /* Jv = J(x) v  (2*nobs)  and  Jtv = J(x)' v  (nvar): the products mul_sparse!(…) forms from
  * (rows, cols, vals), src/lma_aux.jl:194-212, call sites src/lm.jl:57,356,370; here matrix-free. */
-int ba_jprod(ba_handle* h, const double* x, const double* v, double* Jv);
-int ba_jtprod(ba_handle* h, const double* x, const double* v, double* Jtv);
+BA_API int ba_jprod(ba_handle* h, const double* x, const double* v, double* Jv);
+BA_API int ba_jtprod(ba_handle* h, const double* x, const double* v, double* Jtv);
 
 /* device-pointer variants (x_dev has the full nvar layout; outputs are local slices) */
-int ba_residual_dev(ba_handle* h, const double* x_dev, double* cx_dev);
-int ba_jac_structure_dev(ba_handle* h, int64_t* rows_dev, int64_t* cols_dev);
-int ba_jac_coord_dev(ba_handle* h, const double* x_dev, double* vals_dev);
-int ba_residual_jac_dev(ba_handle* h, const double* x_dev, double* cx_dev, double* vals_dev);
-int ba_jprod_dev(ba_handle* h, const double* x_dev, const double* v_dev, double* Jv_dev);
-int ba_jtprod_dev(ba_handle* h, const double* x_dev, const double* v_dev, double* Jtv_dev);
-int ba_sync(ba_handle* h);
+BA_API int ba_residual_dev(ba_handle* h, const double* x_dev, double* cx_dev);
+BA_API int ba_jac_structure_dev(ba_handle* h, int64_t* rows_dev, int64_t* cols_dev);
+BA_API int ba_jac_coord_dev(ba_handle* h, const double* x_dev, double* vals_dev);
+BA_API int ba_residual_jac_dev(ba_handle* h, const double* x_dev, double* cx_dev, double* vals_dev);
+BA_API int ba_jprod_dev(ba_handle* h, const double* x_dev, const double* v_dev, double* Jv_dev);
+BA_API int ba_jtprod_dev(ba_handle* h, const double* x_dev, const double* v_dev, double* Jtv_dev);
+BA_API int ba_sync(ba_handle* h);
+/* Device time (CUDA events on the handle's stream) of the most recent per-observation evaluation
+ * kernel alone (k_eval: cons!/jac_coord!/fused), for roofline reporting; waits for that kernel. */
+BA_API int ba_last_eval_ms(ba_handle* h, float* ms);
 
 /* ---- Levenberg-Marquardt, src/lm.jl:15-418 --------------------------------------------------- */
 typedef struct ba_lm_params {
@@ -117,22 +125,22 @@ typedef struct ba_lm_stats {
 
 typedef void (*ba_iter_cb)(const ba_lm_row* row, void* user);
 
-void ba_lm_default_params(ba_lm_params* p);
+BA_API void ba_lm_default_params(ba_lm_params* p);
 /* One damped solve (J'J + lambda I) delta = -J'r at x (what ldl_factorize + ldl_solve! /
  * myqr + solve_qr! deliver, src/lm.jl:138-152,175-229): delta (nvar), dr2 = 1/2 ||J delta + r||^2,
  * optional jtr (nvar, may be NULL) = J'r, obj = 1/2 ||r||^2. */
-int ba_lm_step(ba_handle* h, const double* x, double lambda, double pcg_tol, int32_t pcg_max_iter,
+BA_API int ba_lm_step(ba_handle* h, const double* x, double lambda, double pcg_tol, int32_t pcg_max_iter,
                double* delta, double* dr2, double* obj, double* jtr, int32_t* pcg_iters);
 /* Levenberg_Marquardt(model, facto, perm, normalize, linesearch; x, tolerances...) on device;
  * x_inout: x0 in, solution out (GenericExecutionStats.solution). */
-int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* p, ba_lm_stats* st,
+BA_API int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* p, ba_lm_stats* st,
                 ba_iter_cb cb, void* user);
 
 /* ---- multi-GPU (one process per GPU): NCCL communicator over NVLink/NVSwitch ---------------- */
 /* rank 0 calls ba_comm_unique_id and broadcasts the 128 bytes by any means (torch.distributed,
  * MPI, a file); every rank then calls ba_comm_init on its sharded handle. */
-int ba_comm_unique_id(uint8_t id128[128]);
-int ba_comm_init(ba_handle* h, const uint8_t id128[128]);
+BA_API int ba_comm_unique_id(uint8_t id128[128]);
+BA_API int ba_comm_init(ba_handle* h, const uint8_t id128[128]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,94 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/bagpu.h
+declares (no compute calls without a GPU), host-only entry points, and the Python mirror's
+argument handling."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, small_problem
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bagpu.h")).read()
+    return sorted(set(re.findall(r"^BA_API [\w\s\*]+?\b(ba_\w+)\(", text, re.M)))
+
+
+def test_library_exports_every_declared_symbol(ba):
+    L = ba._lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 28
+    for n in names:
+        assert getattr(L, n) is not None, n
+    assert sorted(ba._lib.SYMBOLS) == names  # the Python binding covers the whole header
+
+
+def test_version_and_default_params(ba):
+    assert b"sm_100a" in ba._lib.lib().ba_version()
+    p = ba.default_params()
+    eps = np.finfo(np.float64).eps
+    assert p.restol == p.ortol == p.rtol == np.cbrt(eps)          # src/lm.jl:21-24
+    assert p.satol == p.srtol == p.oatol == p.atol == np.sqrt(eps)
+    assert (p.nu_d, p.nu_m, p.lam, p.delta_d, p.ite_max) == (3.0, 3.0, 30.0, 2.0, 200)  # :25-26
+
+
+def test_partition_observations_cuts_on_point_boundaries(ba):
+    p = small_problem(ba)
+    L = ba._lib.lib()
+    for nr in (1, 2, 3, 8):
+        cuts = np.empty(nr + 1, dtype=np.int64)
+        rc = L.ba_partition_observations(p.nobs, p.pnt_idx.ctypes.data_as(C.c_void_p), nr,
+                                         cuts.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        assert cuts[0] == 0 and cuts[-1] == p.nobs and np.all(np.diff(cuts) >= 0)
+        for c in cuts[1:-1]:
+            assert c == p.nobs or p.pnt_idx[c] != p.pnt_idx[c - 1]
+        assert np.diff(cuts).max() <= p.nobs / nr + p.ncams  # balanced up to one point's track
+    # not point-major -> BA_ERR_UNSORTED
+    bad = p.pnt_idx[::-1].copy()
+    cuts = np.empty(3, dtype=np.int64)
+    assert L.ba_partition_observations(p.nobs, bad.ctypes.data_as(C.c_void_p), 2,
+                                       cuts.ctypes.data_as(C.c_void_p)) == ba._lib.BA_ERR_UNSORTED
+
+
+def test_name_mangling_like_reference(ba):
+    # src/BALNLPModels.jl:58-68
+    assert ba.name("LadyBug/problem-49-7776-pre.txt.bz2") == "LadyBug-49-7776"
+    assert ba.name("Venice/problem-1778-993923-pre.txt.bz2") == "Venice-1778-993923"
+
+
+def test_create_rejects_bad_indices_without_gpu(ba):
+    # argument validation happens before any CUDA call
+    L = ba._lib.lib()
+    cam = np.array([1, 3], dtype=np.int64)  # 3 > ncams
+    pnt = np.array([1, 1], dtype=np.int64)
+    pt = np.zeros(4)
+    h = C.c_void_p()
+    rc = L.ba_create(2, 1, 2, cam.ctypes.data_as(C.c_void_p), pnt.ctypes.data_as(C.c_void_p),
+                     pt.ctypes.data_as(C.c_void_p), 0, C.byref(h))
+    assert rc == ba._lib.BA_ERR_ARG
+    assert b"out of range" in L.ba_last_error(h)
+    L.ba_destroy(h)
+
+
+def test_synth_problem_shape_and_order(ba):
+    p = small_problem(ba)
+    assert p.cam_idx.min() >= 1 and p.cam_idx.max() == p.ncams and len(np.unique(p.cam_idx)) == p.ncams
+    assert np.all(np.diff(p.pnt_idx) >= 0)                      # point-major
+    same = np.diff(p.pnt_idx) == 0
+    assert np.all(np.diff(p.cam_idx)[same] > 0)                 # cameras ascending and distinct in a point
+    assert np.bincount(p.pnt_idx)[1:].min() >= 2
+    assert p.x0.size == 9 * p.ncams + 3 * p.npnts and p.pt2d.size == 2 * p.nobs
+    q = small_problem(ba)
+    assert np.array_equal(p.pt2d, q.pt2d)                       # deterministic
+
+
+def test_named_shapes_match_baseline_configs(ba):
+    S = ba.synth.SHAPES
+    assert S["ladybug-49"] == (49, 7776, 31843)
+    assert S["trafalgar-257"] == (257, 65132, 225911)
+    assert S["dubrovnik-356"] == (356, 226730, 1255268)
+    assert S["venice-1778"] == (1778, 993923, 5001946)
+    assert S["final-13682"] == (13682, 4456117, 28987644)
