@@ -78,7 +78,7 @@ int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, 
   if ((rc = dev_alloc(h, &h->d_cam, (size_t)nl))) return rc;
   if ((rc = dev_alloc(h, &h->d_pnt, (size_t)nl))) return rc;
   if ((rc = dev_alloc(h, &h->d_pt2d, (size_t)nl))) return rc;
-  if ((rc = dev_alloc(h, &h->d_camtab, (size_t)ncams * 24))) return rc;
+  if ((rc = dev_alloc(h, &h->d_camtab, (size_t)ncams * 16))) return rc;
   if (nl) {
     BA_CUDA(cudaMemcpyAsync(h->d_cam, h->h_cam.data(), sizeof(int32_t) * (size_t)nl, cudaMemcpyHostToDevice, h->stream));
     BA_CUDA(cudaMemcpyAsync(h->d_pnt, h->h_pnt.data(), sizeof(int32_t) * (size_t)nl, cudaMemcpyHostToDevice, h->stream));

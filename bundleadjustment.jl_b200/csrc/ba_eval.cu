@@ -1,6 +1,6 @@
 // ba_eval.cu -- per-observation operator kernels (K1-K4) for sm_100a, FP64.
 //
-//   K1 k_cam_precompute : camera parameters -> 24-double records (once per x)
+//   K1 k_cam_precompute : camera parameters -> 128-byte records (once per x)
 //   K2 k_eval           : cons! and/or jac_coord!   (src/BALNLPModels.jl:115-122, :161-206)
 //   K3 k_jac_structure  : jac_structure!             (src/BALNLPModels.jl:125-158)
 //   K4 k_jprod/k_jtprod : J v and J' v, matrix-free  (semantics of src/lma_aux.jl:194-212)
@@ -10,7 +10,8 @@
 // reused across observations), outputs written with full-sector coalesced streaming stores.  The
 // 24 Jacobian values of one observation are contiguous in the reference layout (192 B), i.e.
 // strided across the lanes of a warp, so each warp transposes its 32x24 tile through a padded
-// shared-memory buffer and writes 6144 contiguous bytes with 16-byte stores.
+// shared-memory buffer and writes 6144 contiguous bytes with 16-byte stores.  The same buffer first
+// stages the warp's 32 camera records, fetched cooperatively as whole 128-byte lines.
 #include "ba_internal.h"
 #include "ba_math.cuh"
 
@@ -36,14 +37,12 @@ __global__ void __launch_bounds__(128) k_cam_precompute(const double* __restrict
 __device__ __forceinline__ void load_cam(const double* __restrict__ camtab, int c, double* cam) {
   const double2* src = reinterpret_cast<const double2*>(camtab + (int64_t)c * CAM_REC);
 #pragma unroll
-  for (int i = 0; i < CAM_REC / 2; ++i) {
+  for (int i = 0; i < 7; ++i) {
     const double2 t = __ldg(src + i);
     cam[2 * i] = t.x;
     cam[2 * i + 1] = t.y;
   }
 }
-
-__device__ __forceinline__ double nan0(double v) { return (v != v) ? 0.0 : v; }
 
 template <bool WCX, bool WVALS>
 __global__ void __launch_bounds__(EVAL_THREADS)
@@ -51,47 +50,51 @@ k_eval(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
        const double2* __restrict__ pt2d, const double* __restrict__ xpts,
        const double* __restrict__ camtab, double* __restrict__ cx, double* __restrict__ vals,
        int64_t nobs) {
-  __shared__ double2 stage[WVALS ? (EVAL_THREADS / 32) * 32 * STAGE_ROW : 1];
+  constexpr int WROW = WVALS ? 32 * STAGE_ROW : 32 * CAM_ROW2;  // double2 per warp
+  __shared__ double2 stage[(EVAL_THREADS / 32) * WROW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t wbase = (blockIdx.x * (int64_t)(EVAL_THREADS / 32) + warp) * 32;
   if (wbase >= nobs) return;
   const int64_t k = wbase + lane;
   const bool valid = k < nobs;
-  ObsBlock o;
+  double2* st = stage + warp * WROW;
+  int c = 0, p = 0;
+  double2 ob = make_double2(0.0, 0.0);
   if (valid) {
-    const int c = __ldcs(cam_idx + k), p = __ldcs(pnt_idx + k);
-    const double2 ob = __ldcs(pt2d + k);
-    double X[3], cam[CAM_REC];
-    const double* xp = xpts + (int64_t)p * 3;
-    X[0] = __ldg(xp);
-    X[1] = __ldg(xp + 1);
-    X[2] = __ldg(xp + 2);
-    load_cam(camtab, c, cam);
-    if (WVALS) {
-      eval_block(X, cam, ob.x, ob.y, o);
-    } else {
-      eval_residual(X, cam, ob.x, ob.y, o.F);
-    }
-    if (WCX) __stcs(reinterpret_cast<double2*>(cx) + k, make_double2(o.F[0], o.F[1]));
+    c = __ldcs(cam_idx + k);
+    p = __ldcs(pnt_idx + k);
+    ob = __ldcs(pt2d + k);
   }
+  double X[3], cam[14];
+  const double* xp = xpts + (int64_t)p * 3;
+  X[0] = __ldg(xp);
+  X[1] = __ldg(xp + 1);
+  X[2] = __ldg(xp + 2);
+  warp_stage_cams(camtab, c, lane, st);
+  read_staged_cam(st, lane, cam);
+  ObsBlock o;
   if (WVALS) {
-    double2* st = stage + warp * (32 * STAGE_ROW);
-    if (valid) {
-      double2* row = st + lane * STAGE_ROW;
-      // reference order: row 1 = [A(3) B(9)], row 2 likewise; per-entry NaN -> 0
-      row[0] = make_double2(nan0(o.A[0]), nan0(o.A[1]));
-      row[1] = make_double2(nan0(o.A[2]), nan0(o.B[0]));
-      row[2] = make_double2(nan0(o.B[1]), nan0(o.B[2]));
-      row[3] = make_double2(nan0(o.B[3]), nan0(o.B[4]));
-      row[4] = make_double2(nan0(o.B[5]), nan0(o.B[6]));
-      row[5] = make_double2(nan0(o.B[7]), nan0(o.B[8]));
-      row[6] = make_double2(nan0(o.A[3]), nan0(o.A[4]));
-      row[7] = make_double2(nan0(o.A[5]), nan0(o.B[9]));
-      row[8] = make_double2(nan0(o.B[10]), nan0(o.B[11]));
-      row[9] = make_double2(nan0(o.B[12]), nan0(o.B[13]));
-      row[10] = make_double2(nan0(o.B[14]), nan0(o.B[15]));
-      row[11] = make_double2(nan0(o.B[16]), nan0(o.B[17]));
-    }
+    eval_block(X, cam, ob.x, ob.y, o);
+  } else {
+    eval_residual(X, cam, ob.x, ob.y, o.F);
+  }
+  if (WCX && valid) __stcs(reinterpret_cast<double2*>(cx) + k, make_double2(o.F[0], o.F[1]));
+  if (WVALS) {
+    __syncwarp();  // every lane has its camera record in registers: the buffer can be reused
+    double2* row = st + lane * STAGE_ROW;
+    // reference order: row 1 = [A(3) B(9)], row 2 likewise; per-entry NaN -> 0
+    row[0] = make_double2(nan0(o.A[0]), nan0(o.A[1]));
+    row[1] = make_double2(nan0(o.A[2]), nan0(o.B[0]));
+    row[2] = make_double2(nan0(o.B[1]), nan0(o.B[2]));
+    row[3] = make_double2(nan0(o.B[3]), nan0(o.B[4]));
+    row[4] = make_double2(nan0(o.B[5]), nan0(o.B[6]));
+    row[5] = make_double2(nan0(o.B[7]), nan0(o.B[8]));
+    row[6] = make_double2(nan0(o.A[3]), nan0(o.A[4]));
+    row[7] = make_double2(nan0(o.A[5]), nan0(o.B[9]));
+    row[8] = make_double2(nan0(o.B[10]), nan0(o.B[11]));
+    row[9] = make_double2(nan0(o.B[12]), nan0(o.B[13]));
+    row[10] = make_double2(nan0(o.B[14]), nan0(o.B[15]));
+    row[11] = make_double2(nan0(o.B[16]), nan0(o.B[17]));
     __syncwarp();
     const int nval = (int)min((int64_t)32, nobs - wbase);
     double2* dst = reinterpret_cast<double2*>(vals) + wbase * 12;
@@ -132,7 +135,7 @@ k_jprod(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx
   if (k >= nobs) return;
   const int c = __ldcs(cam_idx + k), p = __ldcs(pnt_idx + k);
   const double2 ob = __ldcs(pt2d + k);
-  double X[3], cam[CAM_REC];
+  double X[3], cam[14];
   const double* xp = x + (int64_t)p * 3;
   X[0] = __ldg(xp); X[1] = __ldg(xp + 1); X[2] = __ldg(xp + 2);
   load_cam(camtab, c, cam);
@@ -173,7 +176,7 @@ k_jtprod(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_id
     p = __ldcs(pnt_idx + k);
     const double2 ob = __ldcs(pt2d + k);
     const double2 w = __ldcs(v + k);
-    double X[3], cam[CAM_REC];
+    double X[3], cam[14];
     const double* xp = x + (int64_t)p * 3;
     X[0] = __ldg(xp); X[1] = __ldg(xp + 1); X[2] = __ldg(xp + 2);
     load_cam(camtab, c, cam);
@@ -198,8 +201,7 @@ k_jtprod(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_id
       if (lane - d >= seg0) gp[i] += t;
     }
   }
-  const unsigned above = (lane == 31) ? 0u : (hm >> (lane + 1));
-  const bool tail = (above == 0u) || (above & 1u);
+  const bool tail = (lane == 31) || ((hm >> (lane + 1)) & 1u);  // next lane starts a new run
   if (valid && tail) {
     double* jp = Jtv + (int64_t)p * 3;
     atomicAdd(jp, gp[0]);

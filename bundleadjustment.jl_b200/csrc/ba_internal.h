@@ -61,7 +61,7 @@ struct ba_handle {
   double2* d_pt2d = nullptr;  // local obs
   std::vector<int32_t> h_cam, h_pnt;  // host copies kept for schedule construction
   double* d_x = nullptr;      // staging for host-pointer calls (nvar)
-  double* d_camtab = nullptr; // ncams * 24
+  double* d_camtab = nullptr; // ncams * 16 (128-byte records, ba_math.cuh)
   double* d_cx = nullptr;     // staging: 2*nobs_l
   double* d_vals = nullptr;   // staging: 24*nobs_l
   double* d_v = nullptr;      // staging for jprod/jtprod inputs/outputs

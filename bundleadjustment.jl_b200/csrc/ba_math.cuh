@@ -5,57 +5,48 @@
 //   Jacobian  : src/BALNLPModels.jl:161-206 (jac_coord!) with src/JacobianByHand.jl:5-101
 //               denseJ(2x12) = (JP3*JP2)*JP1, columns [X(3) | r(3) | t(3) | k1 k2 f], NaN -> 0.
 //
-// B200-first formulation (not a transcription): everything that depends only on the camera is
-// computed once per camera (K1) into a 24-double record
-//     [ R (9, row-major) | N (9, row-major) | t (3) | k1 k2 f ]
-// where R is the Rodrigues matrix and N = (s/th) I + (1 - s/th) k k^T + ((1-c)/th) [k]x is the
-// left Jacobian of SO(3), so that  dP1/dr = -[R X]x N  (the closed form of
-// src/JacobianByHand.jl:41-57, verified against it to <= 1e-13 relative).  The per-observation
-// work is then ~110 FP64 ops and one reciprocal instead of ~500 flops + sincos + sqrt.
+// B200-first formulation (not a transcription).  Everything that depends only on the camera is
+// computed once per camera (K1) into one 128-byte, 128-byte-aligned record (exactly one L2 line,
+// four sectors):
+//     [ k(3) | c | s | a | g | t(3) | k1 k2 f | 3 pad ]      c = cos th, s = sin th,
+//                                                            a = s/th,  g = (1-c)/th,  k = r/th
+// With R = c I + (1-c) k k^T + s [k]x (Rodrigues) and N = a I + (1-a) k k^T + g [k]x (the left
+// Jacobian of SO(3)) the rotation part of the reference's closed form is
+//     dP1/dr = -[R X]x N          (src/JacobianByHand.jl:41-57; verified to <= 1e-13 relative)
+// and neither matrix is ever formed: R^T v and N^T v are applied as vector formulas.  Per
+// observation this is ~200 FP64 operations and one reciprocal instead of ~500 flops + sincos +
+// sqrt + 6 divisions, which keeps the evaluation pass HBM-bound on B200.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace ba {
 
-constexpr int CAM_REC = 24;  // doubles per precomputed camera record (192 B, sector aligned)
+constexpr int CAM_REC = 16;  // doubles per camera record (128 B)
+enum { CK0 = 0, CK1 = 1, CK2 = 2, CC = 3, CS = 4, CA = 5, CG = 6, CT0 = 7, CT1 = 8, CT2 = 9, CK1D = 10,
+       CK2D = 11, CF = 12 };
 
 // K1: camera parameters c9 = (r, t, k1, k2, f) -> record.  theta == 0 yields NaNs, exactly like
 // the reference, which has no small-angle branch (src/BALNLPModels.jl:19-25).
 __device__ __forceinline__ void cam_precompute(const double* __restrict__ c9, double* __restrict__ rec) {
   const double r0 = c9[0], r1 = c9[1], r2 = c9[2];
   const double th = sqrt((r0 * r0 + r1 * r1) + r2 * r2);
-  const double kx = r0 / th, ky = r1 / th, kz = r2 / th;
   double s, c;
   sincos(th, &s, &c);
-  const double omc = 1.0 - c;
-  // R: the entries of JP1[1:3,1:3] (src/JacobianByHand.jl:38-40,45-47,52-54)
-  rec[0] = c + omc * (kx * kx);
-  rec[1] = -s * kz + (omc * ky) * kx;
-  rec[2] = s * ky + (omc * kz) * kx;
-  rec[3] = s * kz + (omc * ky) * kx;
-  rec[4] = c + omc * (ky * ky);
-  rec[5] = -s * kx + (omc * ky) * kz;
-  rec[6] = -s * ky + (omc * kx) * kz;
-  rec[7] = s * kx + (omc * ky) * kz;
-  rec[8] = c + omc * (kz * kz);
-  // N = a I + b k k^T + g [k]x
-  const double a = s / th, b = 1.0 - a, g = omc / th;
-  rec[9] = a + b * (kx * kx);
-  rec[10] = (b * kx) * ky - g * kz;
-  rec[11] = (b * kx) * kz + g * ky;
-  rec[12] = (b * ky) * kx + g * kz;
-  rec[13] = a + b * (ky * ky);
-  rec[14] = (b * ky) * kz - g * kx;
-  rec[15] = (b * kz) * kx - g * ky;
-  rec[16] = (b * kz) * ky + g * kx;
-  rec[17] = a + b * (kz * kz);
-  rec[18] = c9[3];
-  rec[19] = c9[4];
-  rec[20] = c9[5];
-  rec[21] = c9[6];
-  rec[22] = c9[7];
-  rec[23] = c9[8];
+  rec[CK0] = r0 / th;
+  rec[CK1] = r1 / th;
+  rec[CK2] = r2 / th;
+  rec[CC] = c;
+  rec[CS] = s;
+  rec[CA] = s / th;
+  rec[CG] = (1.0 - c) / th;
+  rec[CT0] = c9[3];
+  rec[CT1] = c9[4];
+  rec[CT2] = c9[5];
+  rec[CK1D] = c9[6];
+  rec[CK2D] = c9[7];
+  rec[CF] = c9[8];
+  rec[13] = rec[14] = rec[15] = 0.0;
 }
 
 // One observation's block.  F is the projection minus the observed pixel (cons!).
@@ -68,26 +59,32 @@ struct ObsBlock {
 __device__ __forceinline__ bool nonfinite(double v) {
   return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000;
 }
+__device__ __forceinline__ double nan0(double v) { return (v != v) ? 0.0 : v; }
 
-// Shared first half of the projection: Y = R X, P1 = Y + t, P2 = -P1.xy / P1.z, distortion.
+// First half of the projection: Y = R X (Rodrigues, same operation order as projection!,
+// src/BALNLPModels.jl:19-27), P1 = Y + t, P2 = -P1.xy / P1.z, distortion (:11-14, :29-30).
 struct Proj {
   double Y0, Y1, Y2, iz, u, v, n2, sg, fs;
 };
 __device__ __forceinline__ void project_core(const double X[3], const double* __restrict__ cam, Proj& q) {
-  q.Y0 = cam[0] * X[0] + cam[1] * X[1] + cam[2] * X[2];
-  q.Y1 = cam[3] * X[0] + cam[4] * X[1] + cam[5] * X[2];
-  q.Y2 = cam[6] * X[0] + cam[7] * X[1] + cam[8] * X[2];
-  const double px = q.Y0 + cam[18], py = q.Y1 + cam[19], pz = q.Y2 + cam[20];
+  const double k0 = cam[CK0], k1 = cam[CK1], k2 = cam[CK2], c = cam[CC], s = cam[CS];
+  const double w0 = k1 * X[2] - k2 * X[1], w1 = k2 * X[0] - k0 * X[2], w2 = k0 * X[1] - k1 * X[0];  // k x X
+  const double d = (k0 * X[0] + k1 * X[1]) + k2 * X[2];
+  const double e = (1.0 - c) * d;
+  q.Y0 = (c * X[0] + s * w0) + e * k0;
+  q.Y1 = (c * X[1] + s * w1) + e * k1;
+  q.Y2 = (c * X[2] + s * w2) + e * k2;
+  const double px = q.Y0 + cam[CT0], py = q.Y1 + cam[CT1], pz = q.Y2 + cam[CT2];
   q.iz = 1.0 / pz;
   q.u = -px * q.iz;
   q.v = -py * q.iz;
   q.n2 = q.u * q.u + q.v * q.v;
-  q.sg = (1.0 + cam[21] * q.n2) + cam[22] * (q.n2 * q.n2);
-  q.fs = cam[23] * q.sg;
+  q.sg = (1.0 + cam[CK1D] * q.n2) + cam[CK2D] * (q.n2 * q.n2);
+  q.fs = cam[CF] * q.sg;
 }
 
-// Residual only (used by the trial-point and cons! kernels); bit-identical to ObsBlock::F of
-// eval_block on finite inputs because both go through project_core.
+// Residual only (trial-point and cons! kernels); bit-identical to ObsBlock::F of eval_block on
+// finite inputs because both go through project_core.
 __device__ __forceinline__ void eval_residual(const double X[3], const double* __restrict__ cam,
                                               double ox, double oy, double F[2]) {
   Proj q;
@@ -101,24 +98,32 @@ __device__ __forceinline__ void eval_residual(const double X[3], const double* _
 // when the fast path produced a non-finite value, so its cost does not matter.
 __device__ __noinline__ void eval_block_dense(const double X[3], const double* __restrict__ cam,
                                               double ox, double oy, ObsBlock& o) {
-  const double Y[3] = {cam[0] * X[0] + cam[1] * X[1] + cam[2] * X[2],
-                       cam[3] * X[0] + cam[4] * X[1] + cam[5] * X[2],
-                       cam[6] * X[0] + cam[7] * X[1] + cam[8] * X[2]};
-  const double p[3] = {Y[0] + cam[18], Y[1] + cam[19], Y[2] + cam[20]};
-  const double k1 = cam[21], k2 = cam[22], f = cam[23];
+  const double kx = cam[CK0], ky = cam[CK1], kz = cam[CK2], c = cam[CC], s = cam[CS];
+  const double a = cam[CA], g = cam[CG], b = 1.0 - a, omc = 1.0 - c;
+  // R: the entries of JP1[1:3,1:3] (src/JacobianByHand.jl:38-40,45-47,52-54); N likewise
+  const double R[9] = {c + omc * (kx * kx),        -s * kz + (omc * ky) * kx, s * ky + (omc * kz) * kx,
+                       s * kz + (omc * ky) * kx,   c + omc * (ky * ky),       -s * kx + (omc * ky) * kz,
+                       -s * ky + (omc * kx) * kz,  s * kx + (omc * ky) * kz,  c + omc * (kz * kz)};
+  const double N[9] = {a + b * (kx * kx),        (b * kx) * ky - g * kz, (b * kx) * kz + g * ky,
+                       (b * ky) * kx + g * kz,   a + b * (ky * ky),      (b * ky) * kz - g * kx,
+                       (b * kz) * kx - g * ky,   (b * kz) * ky + g * kx, a + b * (kz * kz)};
+  const double Y[3] = {R[0] * X[0] + R[1] * X[1] + R[2] * X[2], R[3] * X[0] + R[4] * X[1] + R[5] * X[2],
+                       R[6] * X[0] + R[7] * X[1] + R[8] * X[2]};
+  const double p[3] = {Y[0] + cam[CT0], Y[1] + cam[CT1], Y[2] + cam[CT2]};
+  const double k1 = cam[CK1D], k2 = cam[CK2D], f = cam[CF];
   double JP1[6][12], JP2[5][6], JP3[2][5], T[2][6];
   for (int i = 0; i < 6; ++i)
     for (int j = 0; j < 12; ++j) JP1[i][j] = 0.0;
   for (int i = 0; i < 5; ++i)
     for (int j = 0; j < 6; ++j) JP2[i][j] = 0.0;
   for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) JP1[i][j] = cam[3 * i + j];
+    for (int j = 0; j < 3; ++j) JP1[i][j] = R[3 * i + j];
     JP1[i][6 + i] = 1.0;
     JP1[3 + i][9 + i] = 1.0;
   }
   // dP1/dr = -[Y]x N : column j = N_col_j x Y
   for (int j = 0; j < 3; ++j) {
-    const double n0 = cam[9 + j], n1 = cam[12 + j], n2 = cam[15 + j];
+    const double n0 = N[j], n1 = N[3 + j], n2 = N[6 + j];
     JP1[0][3 + j] = n1 * Y[2] - n2 * Y[1];
     JP1[1][3 + j] = n2 * Y[0] - n0 * Y[2];
     JP1[2][3 + j] = n0 * Y[1] - n1 * Y[0];
@@ -139,23 +144,23 @@ __device__ __noinline__ void eval_block_dense(const double X[3], const double* _
   }
   const double n2 = u * u + v * v, n4 = n2 * n2;
   const double sg = (1.0 + k1 * n2) + k2 * n4;
-  const double a = (2 * k1) * u + k2 * (4 * ((u * u) * u) + (4 * u) * (v * v));
-  const double b = (2 * k1) * v + k2 * (4 * ((v * v) * v) + (4 * v) * (u * u));
-  JP3[0][0] = f * sg + (f * a) * u; JP3[0][1] = (f * b) * u; JP3[0][2] = (f * n2) * u;
-  JP3[0][3] = (f * n4) * u;         JP3[0][4] = sg * u;
-  JP3[1][0] = (f * a) * v;          JP3[1][1] = f * sg + (f * b) * v; JP3[1][2] = (f * n2) * v;
-  JP3[1][3] = (f * n4) * v;         JP3[1][4] = sg * v;
+  const double aa = (2 * k1) * u + k2 * (4 * ((u * u) * u) + (4 * u) * (v * v));
+  const double bb = (2 * k1) * v + k2 * (4 * ((v * v) * v) + (4 * v) * (u * u));
+  JP3[0][0] = f * sg + (f * aa) * u; JP3[0][1] = (f * bb) * u; JP3[0][2] = (f * n2) * u;
+  JP3[0][3] = (f * n4) * u;          JP3[0][4] = sg * u;
+  JP3[1][0] = (f * aa) * v;          JP3[1][1] = f * sg + (f * bb) * v; JP3[1][2] = (f * n2) * v;
+  JP3[1][3] = (f * n4) * v;          JP3[1][4] = sg * v;
   for (int i = 0; i < 2; ++i)
     for (int j = 0; j < 6; ++j) {
-      double s = 0.0;
-      for (int q = 0; q < 5; ++q) s += JP3[i][q] * JP2[q][j];
-      T[i][j] = s;
+      double acc = 0.0;
+      for (int q = 0; q < 5; ++q) acc += JP3[i][q] * JP2[q][j];
+      T[i][j] = acc;
     }
   for (int i = 0; i < 2; ++i)
     for (int j = 0; j < 12; ++j) {
-      double s = 0.0;
-      for (int q = 0; q < 6; ++q) s += T[i][q] * JP1[q][j];
-      const double val = (s != s) ? 0.0 : s;  // per-entry NaN -> 0 (BALNLPModels.jl:201)
+      double acc = 0.0;
+      for (int q = 0; q < 6; ++q) acc += T[i][q] * JP1[q][j];
+      const double val = (acc != acc) ? 0.0 : acc;  // per-entry NaN -> 0 (BALNLPModels.jl:201)
       if (j < 3) o.A[3 * i + j] = val; else o.B[9 * i + (j - 3)] = val;
     }
   // the residual keeps its NaN/Inf (BALNLPModels.jl:120 is commented out)
@@ -166,43 +171,41 @@ __device__ __noinline__ void eval_block_dense(const double X[3], const double* _
   o.F[1] = fs * vv - oy;
 }
 
+// out = M^T v for M = alpha I + beta k k^T + gamma [k]x  (so M^T v = alpha v + beta (k.v) k - gamma k x v)
+__device__ __forceinline__ void apply_T(double alpha, double beta, double gamma, double k0, double k1, double k2,
+                                        double v0, double v1, double v2, double& o0, double& o1, double& o2) {
+  const double d = beta * ((k0 * v0 + k1 * v1) + k2 * v2);
+  o0 = (alpha * v0 + d * k0) - gamma * (k1 * v2 - k2 * v1);
+  o1 = (alpha * v1 + d * k1) - gamma * (k2 * v0 - k0 * v2);
+  o2 = (alpha * v2 + d * k2) - gamma * (k0 * v1 - k1 * v0);
+}
+
 // Fast path: residual + 2x12 Jacobian block from the camera record.
 __device__ __forceinline__ void eval_block(const double X[3], const double* __restrict__ cam,
                                            double ox, double oy, ObsBlock& o) {
-  const double R0 = cam[0], R1 = cam[1], R2 = cam[2], R3 = cam[3], R4 = cam[4], R5 = cam[5],
-               R6 = cam[6], R7 = cam[7], R8 = cam[8];
   Proj q;
   project_core(X, cam, q);
   const double Y0 = q.Y0, Y1 = q.Y1, Y2 = q.Y2, iz = q.iz, u = q.u, v = q.v, n2 = q.n2, sg = q.sg, fs = q.fs;
-  const double k1 = cam[21], k2 = cam[22], f = cam[23];
+  const double kd1 = cam[CK1D], kd2 = cam[CK2D], f = cam[CF];
+  const double k0 = cam[CK0], k1 = cam[CK1], k2 = cam[CK2], c = cam[CC], s = cam[CS], a = cam[CA], g = cam[CG];
   const double n4 = n2 * n2;
   o.F[0] = fs * u - ox;
   o.F[1] = fs * v - oy;
   // JP3 (2x5): d(f*sg*P2)/d(P2x,P2y,k1,k2,f); 4u^3+4uv^2 = 4 u n2
-  const double e = f * (2.0 * k1 + 4.0 * k2 * n2);
+  const double e = f * (2.0 * kd1 + 4.0 * kd2 * n2);
   const double j00 = fs + (e * u) * u, j01 = (e * v) * u, j11 = fs + (e * v) * v;
   const double fn2 = f * n2, fn4 = f * n4;
   // G = JP3[:,0:2] * JP2[0:2,0:3] with JP2 = -iz [1 0 u; 0 1 v]
   const double g00 = -iz * j00, g01 = -iz * j01, g02 = -iz * (j00 * u + j01 * v);
   const double g10 = g01, g11 = -iz * j11, g12 = -iz * (j01 * u + j11 * v);
-  // A = G R
-  o.A[0] = g00 * R0 + g01 * R3 + g02 * R6;
-  o.A[1] = g00 * R1 + g01 * R4 + g02 * R7;
-  o.A[2] = g00 * R2 + g01 * R5 + g02 * R8;
-  o.A[3] = g10 * R0 + g11 * R3 + g12 * R6;
-  o.A[4] = g10 * R1 + g11 * R4 + g12 * R7;
-  o.A[5] = g10 * R2 + g11 * R5 + g12 * R8;
-  // dF/dr = G (-[Y]x N) : row i = (Y x g_i)^T N
-  {
-    const double c0 = Y1 * g02 - Y2 * g01, c1 = Y2 * g00 - Y0 * g02, c2 = Y0 * g01 - Y1 * g00;
-    o.B[0] = c0 * cam[9] + c1 * cam[12] + c2 * cam[15];
-    o.B[1] = c0 * cam[10] + c1 * cam[13] + c2 * cam[16];
-    o.B[2] = c0 * cam[11] + c1 * cam[14] + c2 * cam[17];
-    const double d0 = Y1 * g12 - Y2 * g11, d1 = Y2 * g10 - Y0 * g12, d2 = Y0 * g11 - Y1 * g10;
-    o.B[9] = d0 * cam[9] + d1 * cam[12] + d2 * cam[15];
-    o.B[10] = d0 * cam[10] + d1 * cam[13] + d2 * cam[16];
-    o.B[11] = d0 * cam[11] + d1 * cam[14] + d2 * cam[17];
-  }
+  // A = G R : row i = (R^T g_i)^T
+  apply_T(c, 1.0 - c, s, k0, k1, k2, g00, g01, g02, o.A[0], o.A[1], o.A[2]);
+  apply_T(c, 1.0 - c, s, k0, k1, k2, g10, g11, g12, o.A[3], o.A[4], o.A[5]);
+  // dF/dr = G (-[Y]x N) : row i = (N^T (Y x g_i))^T
+  apply_T(a, 1.0 - a, g, k0, k1, k2, Y1 * g02 - Y2 * g01, Y2 * g00 - Y0 * g02, Y0 * g01 - Y1 * g00,
+          o.B[0], o.B[1], o.B[2]);
+  apply_T(a, 1.0 - a, g, k0, k1, k2, Y1 * g12 - Y2 * g11, Y2 * g10 - Y0 * g12, Y0 * g11 - Y1 * g10,
+          o.B[9], o.B[10], o.B[11]);
   o.B[3] = g00; o.B[4] = g01; o.B[5] = g02;
   o.B[12] = g10; o.B[13] = g11; o.B[14] = g12;
   o.B[6] = fn2 * u; o.B[7] = fn4 * u; o.B[8] = sg * u;
@@ -227,6 +230,32 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v += shfl_xor_d(v, m);
   return v;
+}
+
+// Warp-cooperative gather of the 32 lanes' camera records (128 B each) into shared memory: every
+// load instruction moves four whole records as 4 x 128 contiguous bytes (4 L1 wavefronts instead of
+// 32 for a per-lane strided read), then each lane reads its own record.  Rows are padded to 9
+// double2 (144 B, odd multiple of 16 B) so the per-lane 16-byte reads are bank-conflict free.
+constexpr int CAM_ROW2 = 9;  // double2 per staged camera row
+__device__ __forceinline__ void warp_stage_cams(const double* __restrict__ camtab, int cam_of_lane, int lane,
+                                                double2* __restrict__ rows /* 32 * CAM_ROW2 */) {
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    const int c = __shfl_sync(0xffffffffu, cam_of_lane, r);
+    const double2 t = __ldg(reinterpret_cast<const double2*>(camtab + (int64_t)c * CAM_REC) + ch);
+    rows[r * CAM_ROW2 + ch] = t;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void read_staged_cam(const double2* __restrict__ rows, int lane, double* cam) {
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {  // 13 doubles used: 7 double2
+    const double2 t = rows[lane * CAM_ROW2 + i];
+    cam[2 * i] = t.x;
+    cam[2 * i + 1] = t.y;
+  }
 }
 
 }  // namespace ba
