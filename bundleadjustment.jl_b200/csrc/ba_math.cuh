@@ -218,7 +218,16 @@ __device__ __forceinline__ void eval_block(const double X[3], const double* __re
   for (int i = 0; i < 6; ++i) bad |= nonfinite(o.A[i]);
 #pragma unroll
   for (int i = 0; i < 18; ++i) bad |= nonfinite(o.B[i]);
-  if (bad) eval_block_dense(X, cam, ox, oy, o);
+  if (bad) {
+    // copies keep X / cam / o of the fast path in registers: only these rare-path temporaries have
+    // their address taken (a direct call made every access of `o` a local-memory access)
+    double Xl[3] = {X[0], X[1], X[2]}, cl[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) cl[i] = cam[i];
+    ObsBlock t;
+    eval_block_dense(Xl, cl, ox, oy, t);
+    o = t;
+  }
 }
 
 // ---- small warp helpers ------------------------------------------------------------------

@@ -38,7 +38,7 @@ def test_residual_and_jacobian_match_oracle(ba, oracle, variant):
     assert_rel(m.cons(p.x0), cx_ref, TOL, scale=scale, what="cons!")
     assert_jac_rel(m.jac_coord(p.x0), vals_ref, TOL, what="jac_coord!")
     cx, vals = m.cons_jac_coord_(p.x0)
-    assert np.array_equal(cx, m.cons(p.x0))          # fused and separate kernels: same residual bits
+    assert_rel(cx, m.cons(p.x0), 1e-14, scale=scale)  # fused and separate kernels agree to rounding
     assert_jac_rel(vals, m.jac_coord(p.x0), 1e-14)   # (FMA contraction may differ between instantiations)
     assert m.counters.neval_cons == 3 and m.counters.neval_jac == 3
 
