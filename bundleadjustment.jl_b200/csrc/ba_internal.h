@@ -20,32 +20,48 @@ struct ncclComm;
     }                                                                                          \
   } while (0)
 
-// Device-resident state of the LM solver (allocated on first use).
+// Device-resident state of the LM solver (allocated on first use by ba::lm_prepare).
 struct ba_lm_state {
-  // schedules built once per problem on the host
-  int32_t* d_tstart = nullptr;   // point-major warp tasks: obs offsets, ntasks+1
-  int64_t ntasks = 0;
-  int32_t* d_cperm = nullptr;    // observations sorted by camera (local obs ids)
-  int32_t* d_ctask_cam = nullptr;   // camera-major tasks: camera id
-  int32_t* d_ctask_beg = nullptr;   // first position in d_cperm
-  int32_t* d_ctask_end = nullptr;
-  int64_t nctasks = 0;
-  // vectors
-  double* d_x = nullptr;      // current iterate (nvar)
-  double* d_xt = nullptr;     // trial iterate
-  double* d_delta = nullptr;  // step (nvar): points then cameras
-  double* d_cam = nullptr;    // camera records for d_x
-  double* d_camt = nullptr;   // camera records for d_xt
-  double* d_V = nullptr;      // 6 per local point (sym 3x3 of A'A)
-  double* d_gp = nullptr;     // 3 per local point: -A'F
-  double* d_Vinv = nullptr;   // 6 per local point: (V + lambda I)^-1
-  double* d_wp = nullptr;     // 3 per local point: Vinv * gp
-  double* d_camacc = nullptr; // per camera: [U(45) | gc(9) | corr(45) | rhsc(9)] = 108
-  double* d_Minv = nullptr;   // 81 per camera
-  double* d_pcg = nullptr;    // 6 vectors of 9*ncams: b, xc, r, z, p, acc
-  double* d_scal = nullptr;   // device scalars (see ba_lm.cu)
-  double* h_scal = nullptr;   // pinned mirror
   bool ready = false;
+  // ---- schedules built once per problem on the host -----------------------------------------
+  int32_t* d_tstart = nullptr;   // point-major warp tasks: observation offsets, ntasks + 1
+  int64_t ntasks = 0;
+  int32_t* d_pstart = nullptr;   // first local observation of each local point, npl + 1
+  int32_t* d_cperm = nullptr;    // camera-major position -> local observation id
+  int32_t* d_ctask_beg = nullptr;  // camera-major tasks: [beg, end) positions of one camera
+  int32_t* d_ctask_end = nullptr;
+  int32_t* d_cam_t0 = nullptr;   // first task of each camera, ncams + 1
+  int64_t nctasks = 0;
+  // ---- per observation ------------------------------------------------------------------------
+  double2* d_Jp = nullptr;   // 12 planes x nl, point-major: plane j = (row1[j], row2[j]) of the 2x12 block
+  double2* d_F = nullptr;    // nl residuals
+  double2* d_Bc = nullptr;   // 9 planes x nl, camera-major copy of the camera part
+  double2* d_w = nullptr;    // nl: per-observation 2-vector exchanged between the two passes
+  double* d_T = nullptr;     // 3 planes x nl: A (V + lambda I)^-1 A^T (symmetric 2x2)
+  double2* d_dr = nullptr;   // nl: -(J delta + r), only with linesearch (src/lm.jl:277-279)
+  // ---- per local point ------------------------------------------------------------------------
+  double* d_V = nullptr;     // 6: symmetric A'A
+  double* d_gp = nullptr;    // 3: -A'F
+  double* d_Vinv = nullptr;  // 6: (V + lambda I)^-1
+  double* d_wp = nullptr;    // 3: Vinv gp
+  // ---- per camera -----------------------------------------------------------------------------
+  double* d_taskpart = nullptr;  // nctasks x 54 partial sums
+  double* d_Ug = nullptr;    // ncams x 54: [U (45, symmetric) | gc (9)]
+  double* d_Cr = nullptr;    // ncams x 54: [W Vinv W' diagonal block (45) | W Vinv gp (9)]
+  double* d_H = nullptr;     // ncams x 81: U + lambda I
+  double* d_Minv = nullptr;  // ncams x 81: inverse Schur diagonal block (block-Jacobi preconditioner)
+  double* d_pcg = nullptr;   // 6 vectors of 9 ncams: b, xc, r, z, p, q
+  // ---- iterates -------------------------------------------------------------------------------
+  double* d_x = nullptr;      // current iterate (nvar; only this rank's point slice + cameras are live)
+  double* d_xt = nullptr;     // trial iterate
+  double* d_delta = nullptr;  // step
+  double* d_camt = nullptr;   // camera records of the trial iterate
+  // ---- reductions -----------------------------------------------------------------------------
+  double* d_part = nullptr;   // per-block partial sums (deterministic two-level reductions)
+  int64_t npart = 0;
+  double* d_scal = nullptr;   // device scalars (layout in ba_lm.cu)
+  double* h_scal = nullptr;   // pinned mirror
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct ba_handle {

@@ -1,24 +1,1174 @@
-// ba_lm.cu -- placeholder while the eval path gets its first GPU run; replaced by the real solver.
+// ba_lm.cu -- device-resident Levenberg-Marquardt (K5-K8): block JtJ / Jtr assembly, Schur
+// complement onto the reduced camera system, block-Jacobi PCG, back-substitution, and the LM loop.
+//
+// Reference semantics: src/lm.jl:15-418 (control flow, kept decision for decision) with the damped
+// solve  (J'J + lambda I) delta = -J'r  that src/lm.jl:61-100,138-152,175-229 obtains from
+// ldl_aux.jl / qr_aux.jl factorisations of the augmented matrix (SURVEY.md 3.4 shows every
+// facto x perm x normalize combination solves this same system).
+//
+// With x = [points; cameras] (src/ReadFiles.jl:29-47) and J_k = [A_k | B_k] per observation k=(c,p):
+//     V_p = sum A'A (3x3)   U_c = sum B'B (9x9)   g_p = -sum A'F   g_c = -sum B'F
+//     S = U + lambda I - W (V + lambda I)^-1 W',   W_cp = B_k' A_k,   S dc = g_c - W (V+lI)^-1 g_p
+//     dp = (V + lambda I)^-1 (g_p - W' dc),        dr2 = 1/2 || J delta + r ||^2
+// S is never formed: S v is applied with two passes over the stored J blocks -- a point-major pass
+// (one warp per <=32 observations of whole points: y = B v_c, segmented warp sums per point,
+// u = (V+lI)^-1 sum A'y, w = A u) and a camera-major pass (out_c = (U+lI) v_c - sum B'w).  All
+// sums are two-level and ordered (per-task partials, then a fixed-order gather): results are
+// reproducible run to run and no FP64 atomics are used.  Everything is HBM-bound streaming work;
+// camera-sized vector updates of PCG run in one CTA so that its two dot products need no grid sync.
+#include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstring>
 #include "ba_internal.h"
+#include "ba_math.cuh"
+
 namespace ba {
-int lm_prepare(ba_handle*) { return BA_OK; }
-void lm_release(ba_handle*) {}
+
+constexpr int NV = 54;         // per-camera accumulators: 45 (symmetric 9x9) + 9
+constexpr int PT_THREADS = 128;
+constexpr int RED_THREADS = 1024;
+
+// device scalar slots (doubles)
+enum {
+  S_F2 = 0,   // sum F^2 at the current iterate                 } local partial sums: allreduced
+  S_GP2,      // sum g_p^2                                      } over ranks in sharded mode
+  S_DR2,      // sum (J delta + r)^2                            }
+  S_DP2,      // sum delta_p^2                                  }
+  S_XP2,      // sum (x + delta)_p^2                            }
+  S_TR2,      // sum F^2 at the trial iterate                   }
+  S_NLOCAL = 8,
+  S_GC2 = 8,  // sum g_c^2 (cameras are replicated)
+  S_DC2,      // sum delta_c^2
+  S_XC2,      // sum (x + delta)_c^2
+  S_RZ = 16, S_RZ0, S_PQ, S_DONE, S_ITERS, S_REL, S_ERR,
+  S_COUNT = 32
+};
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < NT / 32; ++i) t += sh[i];
+  return t;
 }
+
+// out[slot0 + j] = sum_b part[b * K + j], one block per j, fixed summation order
+__global__ void __launch_bounds__(RED_THREADS)
+k_reduce_parts(const double* __restrict__ part, int64_t nblocks, int K, double* __restrict__ out, int slot0) {
+  __shared__ double sh[RED_THREADS / 32];
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int64_t b = threadIdx.x; b < nblocks; b += RED_THREADS) s += part[b * K + j];
+  s = block_sum<RED_THREADS>(s, sh);
+  if (threadIdx.x == 0) out[slot0 + j] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5a: evaluate F and the J blocks at x (thread per observation), store them point-major
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT_THREADS)
+k_lm_build(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
+           const double2* __restrict__ pt2d, const double* __restrict__ xpts,
+           const double* __restrict__ camtab, double2* __restrict__ Jp, double2* __restrict__ F,
+           double* __restrict__ part, int64_t nl) {
+  __shared__ double2 stage[(PT_THREADS / 32) * 32 * CAM_ROW2];
+  __shared__ double sh[PT_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t k = blockIdx.x * (int64_t)PT_THREADS + threadIdx.x;
+  const bool valid = k < nl;
+  int c = 0, p = 0;
+  double2 ob = make_double2(0.0, 0.0);
+  if (valid) {
+    c = __ldg(cam_idx + k);
+    p = __ldg(pnt_idx + k);
+    ob = __ldg(pt2d + k);
+  }
+  double X[3], cam[14];
+  const double* xp = xpts + (int64_t)p * 3;
+  X[0] = __ldg(xp);
+  X[1] = __ldg(xp + 1);
+  X[2] = __ldg(xp + 2);
+  double2* st = stage + warp * 32 * CAM_ROW2;
+  warp_stage_cams(camtab, c, lane, st);
+  read_staged_cam(st, lane, cam);
+  ObsBlock o;
+  eval_block(X, cam, ob.x, ob.y, o);
+  double f2 = 0.0;
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Jp[(int64_t)j * nl + k] = make_double2(nan0(o.A[j]), nan0(o.A[3 + j]));
+#pragma unroll
+    for (int j = 0; j < 9; ++j) Jp[(int64_t)(3 + j) * nl + k] = make_double2(nan0(o.B[j]), nan0(o.B[9 + j]));
+    F[k] = make_double2(o.F[0], o.F[1]);
+    f2 = o.F[0] * o.F[0] + o.F[1] * o.F[1];
+  }
+  f2 = block_sum<PT_THREADS>(f2, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = f2;
+}
+
+// trial point: residual norm only
+__global__ void __launch_bounds__(PT_THREADS)
+k_lm_trial(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
+           const double2* __restrict__ pt2d, const double* __restrict__ xpts,
+           const double* __restrict__ camtab, double* __restrict__ part, int64_t nl) {
+  __shared__ double2 stage[(PT_THREADS / 32) * 32 * CAM_ROW2];
+  __shared__ double sh[PT_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t k = blockIdx.x * (int64_t)PT_THREADS + threadIdx.x;
+  const bool valid = k < nl;
+  int c = 0, p = 0;
+  double2 ob = make_double2(0.0, 0.0);
+  if (valid) {
+    c = __ldg(cam_idx + k);
+    p = __ldg(pnt_idx + k);
+    ob = __ldg(pt2d + k);
+  }
+  double X[3], cam[14], Fv[2];
+  const double* xp = xpts + (int64_t)p * 3;
+  X[0] = __ldg(xp);
+  X[1] = __ldg(xp + 1);
+  X[2] = __ldg(xp + 2);
+  double2* st = stage + warp * 32 * CAM_ROW2;
+  warp_stage_cams(camtab, c, lane, st);
+  read_staged_cam(st, lane, cam);
+  eval_residual(X, cam, ob.x, ob.y, Fv);
+  double f2 = valid ? Fv[0] * Fv[0] + Fv[1] * Fv[1] : 0.0;
+  f2 = block_sum<PT_THREADS>(f2, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = f2;
+}
+
+// V_p = sum A'A (6, symmetric: 00 01 02 11 12 22), g_p = -sum A'F; thread per local point
+__global__ void __launch_bounds__(PT_THREADS)
+k_point_assemble(const int32_t* __restrict__ pstart, int64_t npl, int64_t nl, const double2* __restrict__ Jp,
+                 const double2* __restrict__ F, double* __restrict__ V, double* __restrict__ gp,
+                 double* __restrict__ part) {
+  __shared__ double sh[PT_THREADS / 32];
+  const int64_t p = blockIdx.x * (int64_t)PT_THREADS + threadIdx.x;
+  double g2 = 0.0;
+  if (p < npl) {
+    double v00 = 0, v01 = 0, v02 = 0, v11 = 0, v12 = 0, v22 = 0, g0 = 0, g1 = 0, g2v = 0;
+    const int k1 = pstart[p + 1];
+    for (int k = pstart[p]; k < k1; ++k) {
+      const double2 a0 = Jp[k], a1 = Jp[nl + k], a2 = Jp[2 * nl + k], f = F[k];
+      v00 += a0.x * a0.x + a0.y * a0.y;
+      v01 += a0.x * a1.x + a0.y * a1.y;
+      v02 += a0.x * a2.x + a0.y * a2.y;
+      v11 += a1.x * a1.x + a1.y * a1.y;
+      v12 += a1.x * a2.x + a1.y * a2.y;
+      v22 += a2.x * a2.x + a2.y * a2.y;
+      g0 -= a0.x * f.x + a0.y * f.y;
+      g1 -= a1.x * f.x + a1.y * f.y;
+      g2v -= a2.x * f.x + a2.y * f.y;
+    }
+    double* vo = V + p * 6;
+    vo[0] = v00; vo[1] = v01; vo[2] = v02; vo[3] = v11; vo[4] = v12; vo[5] = v22;
+    gp[p * 3] = g0; gp[p * 3 + 1] = g1; gp[p * 3 + 2] = g2v;
+    g2 = (g0 * g0 + g1 * g1) + g2v * g2v;
+  }
+  g2 = block_sum<PT_THREADS>(g2, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = g2;
+}
+
+// (V + lambda I)^-1 (symmetric 3x3 by cofactors) and wp = Vinv gp; thread per local point
+__global__ void __launch_bounds__(PT_THREADS)
+k_point_inv(int64_t npl, double lambda, const double* __restrict__ V, const double* __restrict__ gp,
+            double* __restrict__ Vinv, double* __restrict__ wp) {
+  const int64_t p = blockIdx.x * (int64_t)PT_THREADS + threadIdx.x;
+  if (p >= npl) return;
+  const double* v = V + p * 6;
+  const double a = v[0] + lambda, b = v[1], c = v[2], d = v[3] + lambda, e = v[4], f = v[5] + lambda;
+  const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  const double det = (a * c00 + b * c01) + c * c02;
+  const double id = 1.0 / det;
+  const double i00 = c00 * id, i01 = c01 * id, i02 = c02 * id;
+  const double i11 = (a * f - c * c) * id, i12 = (b * c - a * e) * id, i22 = (a * d - b * b) * id;
+  double* o = Vinv + p * 6;
+  o[0] = i00; o[1] = i01; o[2] = i02; o[3] = i11; o[4] = i12; o[5] = i22;
+  const double g0 = gp[p * 3], g1 = gp[p * 3 + 1], g2 = gp[p * 3 + 2];
+  wp[p * 3] = (i00 * g0 + i01 * g1) + i02 * g2;
+  wp[p * 3 + 1] = (i01 * g0 + i11 * g1) + i12 * g2;
+  wp[p * 3 + 2] = (i02 * g0 + i12 * g1) + i22 * g2;
+}
+
+// per observation: w_k = A_k wp_p (right-hand side) and T_k = A_k Vinv_p A_k' (preconditioner)
+__global__ void __launch_bounds__(PT_THREADS)
+k_point_prep(const int32_t* __restrict__ pnt_idx, int64_t pnt0, int64_t nl, const double2* __restrict__ Jp,
+             const double* __restrict__ Vinv, const double* __restrict__ wp, double2* __restrict__ w,
+             double* __restrict__ T) {
+  const int64_t k = blockIdx.x * (int64_t)PT_THREADS + threadIdx.x;
+  if (k >= nl) return;
+  const int64_t p = __ldg(pnt_idx + k) - pnt0;
+  const double2 a0 = Jp[k], a1 = Jp[nl + k], a2 = Jp[2 * nl + k];
+  const double* vi = Vinv + p * 6;
+  const double i00 = vi[0], i01 = vi[1], i02 = vi[2], i11 = vi[3], i12 = vi[4], i22 = vi[5];
+  const double w0 = wp[p * 3], w1 = wp[p * 3 + 1], w2 = wp[p * 3 + 2];
+  w[k] = make_double2((a0.x * w0 + a1.x * w1) + a2.x * w2, (a0.y * w0 + a1.y * w1) + a2.y * w2);
+  // t1 = Vinv a(row 1), t2 = Vinv a(row 2)
+  const double t10 = (i00 * a0.x + i01 * a1.x) + i02 * a2.x, t11 = (i01 * a0.x + i11 * a1.x) + i12 * a2.x,
+               t12 = (i02 * a0.x + i12 * a1.x) + i22 * a2.x;
+  const double t20 = (i00 * a0.y + i01 * a1.y) + i02 * a2.y, t21 = (i01 * a0.y + i11 * a1.y) + i12 * a2.y,
+               t22 = (i02 * a0.y + i12 * a1.y) + i22 * a2.y;
+  T[k] = (a0.x * t10 + a1.x * t11) + a2.x * t12;
+  T[nl + k] = (a0.x * t20 + a1.x * t21) + a2.x * t22;
+  T[2 * nl + k] = (a0.y * t20 + a1.y * t21) + a2.y * t22;
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera-major passes: one warp per task (a slice of one camera's observations)
+//   MODE 0: gather B, F by observation id, write the camera-major copy Bc, accumulate U and g_c
+//   MODE 1: accumulate B' T B (45) and B' w (9)         (Schur diagonal blocks, right-hand side)
+//   MODE 2: accumulate B' w (9)                         (Schur product)
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(PT_THREADS)
+k_cam_pass(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, int64_t nctasks,
+           const int32_t* __restrict__ cperm, int64_t nl, const double2* __restrict__ Jp,
+           const double2* __restrict__ F, double2* __restrict__ Bc, const double2* __restrict__ w,
+           const double* __restrict__ T, double* __restrict__ taskpart, const double* __restrict__ scal) {
+  if (MODE == 2 && scal[S_DONE] != 0.0) return;
+  constexpr int NACC = (MODE == 2) ? 9 : NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t task = blockIdx.x * (int64_t)(PT_THREADS / 32) + (threadIdx.x >> 5);
+  if (task >= nctasks) return;
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+  const int e = tend[task];
+  for (int pos = tbeg[task] + lane; pos < e; pos += 32) {
+    const int k = __ldg(cperm + pos);
+    double2 B[9];
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        B[j] = Jp[(int64_t)(3 + j) * nl + k];
+        Bc[(int64_t)j * nl + pos] = B[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) B[j] = Bc[(int64_t)j * nl + pos];
+    }
+    if (MODE == 2) {
+      const double2 wk = w[k];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) acc[j] += B[j].x * wk.x + B[j].y * wk.y;
+    } else {
+      double2 v;  // 2-vector contracted into the last 9 accumulators
+      double t00 = 1.0, t01 = 0.0, t11 = 1.0;
+      if (MODE == 0) {
+        const double2 f = F[k];
+        v = make_double2(-f.x, -f.y);
+      } else {
+        v = w[k];
+        t00 = T[k];
+        t01 = T[nl + k];
+        t11 = T[2 * nl + k];
+      }
+      int q = 0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const double ci_x = (MODE == 0) ? B[i].x : t00 * B[i].x + t01 * B[i].y;
+        const double ci_y = (MODE == 0) ? B[i].y : t01 * B[i].x + t11 * B[i].y;
+#pragma unroll
+        for (int j = i; j < 9; ++j) {
+          acc[q] += ci_x * B[j].x + ci_y * B[j].y;
+          ++q;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) acc[45 + j] += B[j].x * v.x + B[j].y * v.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) taskpart[task * NACC + i] = acc[i];
+  }
+}
+
+// out[c * nacc + j] = sum over the camera's tasks (fixed order)
+__global__ void __launch_bounds__(256)
+k_cam_gather(const int32_t* __restrict__ cam_t0, int64_t ncams, int nacc, const double* __restrict__ taskpart,
+             double* __restrict__ out, const double* __restrict__ scal, int check_done) {
+  if (check_done && scal[S_DONE] != 0.0) return;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= ncams * nacc) return;
+  const int64_t c = i / nacc;
+  const int j = (int)(i - c * nacc);
+  double s = 0.0;
+  const int t1 = cam_t0[c + 1];
+  for (int t = cam_t0[c]; t < t1; ++t) s += taskpart[(int64_t)t * nacc + j];
+  out[i] = s;
+}
+
+__device__ __forceinline__ int sym9(int i, int j) {  // i <= j, row-wise upper triangle
+  return i * 9 - (i * (i - 1)) / 2 + (j - i);
+}
+
+// H = U + lambda I, Minv = (H - corr)^-1 by Cholesky, b = g_c - rhs; thread per camera
+__global__ void __launch_bounds__(64)
+k_cam_finish(int64_t ncams, double lambda, const double* __restrict__ Ug, const double* __restrict__ Cr,
+             double* __restrict__ H, double* __restrict__ Minv, double* __restrict__ b, double* __restrict__ scal) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= ncams) return;
+  const double* u = Ug + c * NV;
+  const double* cr = Cr + c * NV;
+  double M[9][9], L[9][9], Li[9][9];
+  for (int i = 0; i < 9; ++i)
+    for (int j = i; j < 9; ++j) {
+      const double h = u[sym9(i, j)] + (i == j ? lambda : 0.0);
+      H[c * 81 + i * 9 + j] = h;
+      H[c * 81 + j * 9 + i] = h;
+      M[i][j] = M[j][i] = h - cr[sym9(i, j)];
+    }
+  bool ok = true;
+  for (int j = 0; j < 9; ++j) {
+    double d = M[j][j];
+    for (int q = 0; q < j; ++q) d -= L[j][q] * L[j][q];
+    if (!(d > 0.0)) ok = false;
+    const double lj = sqrt(d);
+    L[j][j] = lj;
+    for (int i = j + 1; i < 9; ++i) {
+      double s = M[i][j];
+      for (int q = 0; q < j; ++q) s -= L[i][q] * L[j][q];
+      L[i][j] = s / lj;
+    }
+  }
+  if (!ok) scal[S_ERR] = 1.0;
+  // Li = L^-1 (lower)
+  for (int j = 0; j < 9; ++j) {
+    Li[j][j] = 1.0 / L[j][j];
+    for (int i = j + 1; i < 9; ++i) {
+      double s = 0.0;
+      for (int q = j; q < i; ++q) s -= L[i][q] * Li[q][j];
+      Li[i][j] = s / L[i][i];
+    }
+  }
+  for (int i = 0; i < 9; ++i)
+    for (int j = i; j < 9; ++j) {
+      double s = 0.0;
+      for (int q = j; q < 9; ++q) s += Li[q][i] * Li[q][j];
+      Minv[c * 81 + i * 9 + j] = s;
+      Minv[c * 81 + j * 9 + i] = s;
+    }
+  for (int j = 0; j < 9; ++j) b[c * 9 + j] = u[45 + j] - cr[45 + j];
+}
+
+// sum of squares of the g_c part of Ug (single block)
+__global__ void __launch_bounds__(RED_THREADS)
+k_gc_norm(int64_t ncams, const double* __restrict__ Ug, double* __restrict__ scal) {
+  __shared__ double sh[RED_THREADS / 32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < ncams * 9; i += RED_THREADS) {
+    const double g = Ug[(i / 9) * NV + 45 + (i % 9)];
+    s += g * g;
+  }
+  s = block_sum<RED_THREADS>(s, sh);
+  if (threadIdx.x == 0) scal[S_GC2] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// point-major pass of the Schur product (MODE 0) and the back-substitution (MODE 1)
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative gather of the 32 lanes' 9-vectors (72 B each) from a camera-sized vector: each
+// load instruction covers ~3.5 whole records instead of 32 scattered 8-byte words.
+__device__ __forceinline__ void warp_stage_vec9(const double* __restrict__ v, int cam_of_lane, int lane,
+                                                double* __restrict__ rows /* 288 */) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int e = 32 * i + lane;
+    const int r = e / 9;
+    const int c = __shfl_sync(0xffffffffu, cam_of_lane, r);
+    rows[e] = __ldg(v + (int64_t)c * 9 + (e - 9 * r));
+  }
+  __syncwarp();
+}
+
+struct PtLane {
+  double2 A0, A1, A2;
+  double2 y;
+  double t0, t1, t2;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(PT_THREADS)
+k_point_solve(const int32_t* __restrict__ tstart, int64_t ntasks, const int32_t* __restrict__ cam_idx,
+              const int32_t* __restrict__ pnt_idx, int64_t pnt0, int64_t nl, const double2* __restrict__ Jp,
+              const double2* __restrict__ F, const double* __restrict__ vcam, const double* __restrict__ Vinv,
+              const double* __restrict__ gp, double2* __restrict__ w_out, double* __restrict__ delta,
+              double2* __restrict__ dr_out, double* __restrict__ part, const double* __restrict__ scal) {
+  __shared__ double vst[(PT_THREADS / 32) * 288];
+  __shared__ double sh[PT_THREADS / 32];
+  if (MODE == 0 && scal[S_DONE] != 0.0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t task = blockIdx.x * (int64_t)(PT_THREADS / 32) + warp;
+  double* vrow = vst + warp * 288;
+  double acc_dr2 = 0.0;
+
+  // per-observation first half: y = B v_c, t = A' y
+  auto first_half = [&](int64_t k, bool valid, PtLane& L) {
+    int c = 0;
+    double2 B[9];
+    if (valid) {
+      c = __ldg(cam_idx + k);
+      L.A0 = Jp[k];
+      L.A1 = Jp[nl + k];
+      L.A2 = Jp[2 * nl + k];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) B[j] = Jp[(int64_t)(3 + j) * nl + k];
+    } else {
+      L.A0 = L.A1 = L.A2 = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < 9; ++j) B[j] = make_double2(0.0, 0.0);
+    }
+    __syncwarp();
+    warp_stage_vec9(vcam, c, lane, vrow);
+    double yx = 0.0, yy = 0.0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const double vj = vrow[lane * 9 + j];
+      yx += B[j].x * vj;
+      yy += B[j].y * vj;
+    }
+    L.y = make_double2(yx, yy);
+    L.t0 = L.A0.x * yx + L.A0.y * yy;
+    L.t1 = L.A1.x * yx + L.A1.y * yy;
+    L.t2 = L.A2.x * yx + L.A2.y * yy;
+  };
+  // per-observation second half, given the point's summed t
+  auto second_half = [&](int64_t k, int64_t p, const PtLane& L, double T0, double T1, double T2, bool writer) {
+    const double* vi = Vinv + p * 6;
+    const double i00 = vi[0], i01 = vi[1], i02 = vi[2], i11 = vi[3], i12 = vi[4], i22 = vi[5];
+    if (MODE == 0) {
+      const double u0 = (i00 * T0 + i01 * T1) + i02 * T2, u1 = (i01 * T0 + i11 * T1) + i12 * T2,
+                   u2 = (i02 * T0 + i12 * T1) + i22 * T2;
+      w_out[k] = make_double2((L.A0.x * u0 + L.A1.x * u1) + L.A2.x * u2, (L.A0.y * u0 + L.A1.y * u1) + L.A2.y * u2);
+    } else {
+      const double r0 = gp[p * 3] - T0, r1 = gp[p * 3 + 1] - T1, r2 = gp[p * 3 + 2] - T2;
+      const double d0 = (i00 * r0 + i01 * r1) + i02 * r2, d1 = (i01 * r0 + i11 * r1) + i12 * r2,
+                   d2 = (i02 * r0 + i12 * r1) + i22 * r2;
+      const double2 f = F[k];
+      const double ex = ((L.A0.x * d0 + L.A1.x * d1) + L.A2.x * d2) + L.y.x + f.x;
+      const double ey = ((L.A0.y * d0 + L.A1.y * d1) + L.A2.y * d2) + L.y.y + f.y;
+      acc_dr2 += ex * ex + ey * ey;
+      if (dr_out) dr_out[k] = make_double2(-ex, -ey);
+      if (writer) {
+        double* dp = delta + (pnt0 + p) * 3;
+        dp[0] = d0;
+        dp[1] = d1;
+        dp[2] = d2;
+      }
+    }
+  };
+
+  if (task < ntasks) {
+    const int64_t t0 = tstart[task], t1 = tstart[task + 1];
+    if (t1 - t0 <= 32) {
+      // whole points packed into one warp: segmented sums over runs of equal point id
+      const int64_t k = t0 + lane;
+      const bool valid = k < t1;
+      const int p = valid ? (int)(__ldg(pnt_idx + k) - pnt0) : -1;
+      PtLane L;
+      first_half(k, valid, L);
+      const int pprev = __shfl_up_sync(0xffffffffu, p, 1);
+      const bool head = (lane == 0) || (p != pprev);
+      const unsigned hm = __ballot_sync(0xffffffffu, head);
+      const int seg0 = 31 - __clz(hm & (0xffffffffu >> (31 - lane)));
+      double s0 = L.t0, s1 = L.t1, s2 = L.t2;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double a = shfl_up_d(s0, d), b = shfl_up_d(s1, d), c = shfl_up_d(s2, d);
+        if (lane - d >= seg0) {
+          s0 += a;
+          s1 += b;
+          s2 += c;
+        }
+      }
+      const unsigned above = (lane == 31) ? 0u : (hm >> (lane + 1));
+      const int tail = above ? lane + __ffs(above) - 1 : 31;
+      const double T0 = shfl_d(s0, tail), T1 = shfl_d(s1, tail), T2 = shfl_d(s2, tail);
+      if (valid) second_half(k, p, L, T0, T1, T2, lane == tail);
+    } else {
+      // one point with more than 32 observations: sum over chunks, then a second sweep
+      const int64_t p = __ldg(pnt_idx + t0) - pnt0;
+      double T0 = 0.0, T1 = 0.0, T2 = 0.0;
+      for (int64_t base = t0; base < t1; base += 32) {
+        const int64_t k = base + lane;
+        PtLane L;
+        first_half(k, k < t1, L);
+        T0 += warp_sum(L.t0);
+        T1 += warp_sum(L.t1);
+        T2 += warp_sum(L.t2);
+      }
+      for (int64_t base = t0; base < t1; base += 32) {
+        const int64_t k = base + lane;
+        PtLane L;
+        first_half(k, k < t1, L);
+        if (k < t1) second_half(k, p, L, T0, T1, T2, k == t0);
+      }
+    }
+  }
+  if (MODE == 1) {
+    acc_dr2 = block_sum<PT_THREADS>(acc_dr2, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc_dr2;
+  }
+}
+
+// xt = x + delta on this rank's live entries (its point slice and all cameras), with the norms the
+// LM tests need; delta is first divided by `div` (back-tracking, src/lm.jl:266).  part: 4 per block.
+__global__ void __launch_bounds__(256)
+k_step_update(const double* __restrict__ x, double* __restrict__ delta, double* __restrict__ xt, int64_t p_lo,
+              int64_t p_hi, int64_t c_lo, int64_t c_hi, double div, double* __restrict__ part) {
+  __shared__ double sh[256 / 32];
+  const int64_t np = p_hi - p_lo, n = np + (c_hi - c_lo);
+  double dp2 = 0, xp2 = 0, dc2 = 0, xc2 = 0;
+  for (int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const bool is_p = i < np;
+    const int64_t j = is_p ? p_lo + i : c_lo + (i - np);
+    double d = delta[j];
+    if (div != 1.0) {
+      d = d / div;
+      delta[j] = d;
+    }
+    const double v = x[j] + d;
+    xt[j] = v;
+    if (is_p) {
+      dp2 += d * d;
+      xp2 += v * v;
+    } else {
+      dc2 += d * d;
+      xc2 += v * v;
+    }
+  }
+  dp2 = block_sum<256>(dp2, sh);
+  xp2 = block_sum<256>(xp2, sh);
+  dc2 = block_sum<256>(dc2, sh);
+  xc2 = block_sum<256>(xc2, sh);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x * 4] = dp2;
+    part[blockIdx.x * 4 + 1] = xp2;
+    part[blockIdx.x * 4 + 2] = dc2;
+    part[blockIdx.x * 4 + 3] = xc2;
+  }
+}
+
+// back-tracking on the LDL path: dr <- (dr - r) / dd  (src/lm.jl:277-279), with its squared norm
+__global__ void __launch_bounds__(PT_THREADS)
+k_ls_dr(double2* __restrict__ dr, const double2* __restrict__ F, int64_t nl, double dd, double* __restrict__ part) {
+  __shared__ double sh[PT_THREADS / 32];
+  const int64_t k = blockIdx.x * (int64_t)PT_THREADS + threadIdx.x;
+  double s = 0.0;
+  if (k < nl) {
+    const double2 a = dr[k], f = F[k];
+    const double2 n = make_double2((a.x - f.x) / dd, (a.y - f.y) / dd);
+    dr[k] = n;
+    s = n.x * n.x + n.y * n.y;
+  }
+  s = block_sum<PT_THREADS>(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PCG on the reduced camera system: camera-sized vector work in ONE block (two dot products per
+// iteration without grid-wide synchronisation); the heavy S p product is the two passes above.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double row9(const double* __restrict__ M, const double* __restrict__ v, int64_t i) {
+  const int64_t c = i / 9;
+  const double* m = M + c * 81 + (i - c * 9) * 9;
+  const double* x = v + c * 9;
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) s += m[j] * x[j];
+  return s;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_init(int64_t n9, const double* __restrict__ b, const double* __restrict__ Minv, double* __restrict__ xc,
+           double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ scal) {
+  __shared__ double sh[RED_THREADS / 32];
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
+    r[i] = b[i];
+    xc[i] = 0.0;
+  }
+  __syncthreads();
+  double rz = 0.0;
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
+    const double zi = row9(Minv, r, i);
+    z[i] = zi;
+    p[i] = zi;
+    rz += r[i] * zi;
+  }
+  rz = block_sum<RED_THREADS>(rz, sh);
+  if (threadIdx.x == 0) {
+    scal[S_RZ] = rz;
+    scal[S_RZ0] = rz;
+    scal[S_ITERS] = 0.0;
+    scal[S_REL] = 1.0;
+    // zero right-hand side: the zero step is the solution; NaN: let the caller see it
+    scal[S_DONE] = (rz == 0.0) ? 1.0 : ((rz == rz) ? 0.0 : 2.0);
+  }
+}
+
+// q holds sum_k B'w on entry (possibly allreduced); on exit q = S p
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_update(int64_t n9, const double* __restrict__ H, const double* __restrict__ Minv, double* __restrict__ q,
+             double* __restrict__ xc, double* __restrict__ r, double* __restrict__ z, double* __restrict__ p,
+             double* __restrict__ scal, double tol) {
+  __shared__ double sh[RED_THREADS / 32];
+  if (scal[S_DONE] != 0.0) return;
+  const double rz = scal[S_RZ], rz0 = scal[S_RZ0];
+  double pq = 0.0;
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
+    const double qi = row9(H, p, i) - q[i];
+    q[i] = qi;
+    pq += p[i] * qi;
+  }
+  pq = block_sum<RED_THREADS>(pq, sh);
+  if (!(pq > 0.0)) {  // breakdown: S is SPD in exact arithmetic, so this is NaN/Inf or loss of definiteness
+    if (threadIdx.x == 0) {
+      scal[S_DONE] = 2.0;
+      scal[S_PQ] = pq;
+    }
+    return;
+  }
+  const double alpha = rz / pq;
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
+    xc[i] += alpha * p[i];
+    r[i] -= alpha * q[i];
+  }
+  __syncthreads();
+  double rzn = 0.0;
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
+    const double zi = row9(Minv, r, i);
+    z[i] = zi;
+    rzn += r[i] * zi;
+  }
+  rzn = block_sum<RED_THREADS>(rzn, sh);
+  const double beta = rzn / rz;
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) p[i] = z[i] + beta * p[i];
+  if (threadIdx.x == 0) {
+    const double rel = sqrt(rzn / rz0);
+    scal[S_RZ] = rzn;
+    scal[S_PQ] = pq;
+    scal[S_ITERS] += 1.0;
+    scal[S_REL] = rel;
+    if (!(rel > tol)) scal[S_DONE] = (rel == rel) ? 1.0 : 2.0;
+  }
+}
+
+__global__ void k_copy_cam_delta(int64_t n9, const double* __restrict__ xc, double* __restrict__ delta_c) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n9) delta_c[i] = xc[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+template <class T>
+int dmalloc(ba_handle* h, T** p, size_t n) {
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
+  return BA_OK;
+}
+
+inline unsigned nblk(int64_t n, int per) { return (unsigned)std::max<int64_t>((n + per - 1) / per, 1); }
+
+}  // namespace
+
+int lm_prepare(ba_handle* h) {
+  ba_lm_state& S = h->lm;
+  if (S.ready) return BA_OK;
+  if (!h->sorted) {
+    h->err = "the LM entry points need point-major observation order (the order of BAL files)";
+    return BA_ERR_UNSORTED;
+  }
+  BA_CUDA(cudaSetDevice(h->device));
+  const int64_t nl = h->nobs_l(), npl = h->npnts_l(), ncams = h->ncams;
+  // ---- point-major warp tasks: whole points, <= 32 observations; a longer point is a task of its own
+  std::vector<int32_t> tstart, pstart((size_t)npl + 1, 0);
+  {
+    int64_t cur_start = 0, cur_len = 0, a = 0;
+    int64_t next_point = 0;  // local points whose pstart is not set yet
+    while (a < nl) {
+      int64_t b = a + 1;
+      while (b < nl && h->h_pnt[(size_t)b] == h->h_pnt[(size_t)a]) ++b;
+      const int64_t pl = h->h_pnt[(size_t)a] - h->pnt0;
+      for (; next_point <= pl; ++next_point) pstart[(size_t)next_point] = (int32_t)a;
+      const int64_t len = b - a;
+      if (len > 32) {
+        if (cur_len > 0) tstart.push_back((int32_t)cur_start);
+        tstart.push_back((int32_t)a);
+        cur_start = b;
+        cur_len = 0;
+      } else if (cur_len + len > 32) {
+        tstart.push_back((int32_t)cur_start);
+        cur_start = a;
+        cur_len = len;
+      } else {
+        if (cur_len == 0) cur_start = a;
+        cur_len += len;
+      }
+      a = b;
+    }
+    if (cur_len > 0) tstart.push_back((int32_t)cur_start);
+    for (; next_point <= npl; ++next_point) pstart[(size_t)next_point] = (int32_t)nl;
+    S.ntasks = (int64_t)tstart.size();
+    tstart.push_back((int32_t)nl);
+  }
+  // ---- camera-major order (stable counting sort) and tasks
+  std::vector<int32_t> cam_start((size_t)ncams + 1, 0), cperm((size_t)nl), tb, te, cam_t0((size_t)ncams + 1, 0);
+  for (int64_t k = 0; k < nl; ++k) cam_start[(size_t)h->h_cam[(size_t)k] + 1]++;
+  for (int64_t c = 0; c < ncams; ++c) cam_start[(size_t)c + 1] += cam_start[(size_t)c];
+  {
+    std::vector<int32_t> fill(cam_start.begin(), cam_start.end() - 1);
+    for (int64_t k = 0; k < nl; ++k) cperm[(size_t)fill[(size_t)h->h_cam[(size_t)k]]++] = (int32_t)k;
+  }
+  int tsz = 32;  // observations per camera task: enough tasks to fill 148 SMs, at most 256 per warp
+  while (tsz < 256 && nl / tsz > 148 * 64) tsz *= 2;
+  for (int64_t c = 0; c < ncams; ++c) {
+    cam_t0[(size_t)c] = (int32_t)tb.size();
+    for (int32_t b = cam_start[(size_t)c]; b < cam_start[(size_t)c + 1]; b += tsz) {
+      tb.push_back(b);
+      te.push_back(std::min<int32_t>(b + tsz, cam_start[(size_t)c + 1]));
+    }
+  }
+  cam_t0[(size_t)ncams] = (int32_t)tb.size();
+  S.nctasks = (int64_t)tb.size();
+
+  int rc;
+#define ALLOC(ptr, n) if ((rc = dmalloc(h, &(ptr), (size_t)(n)))) return rc
+  ALLOC(S.d_tstart, tstart.size());
+  ALLOC(S.d_pstart, pstart.size());
+  ALLOC(S.d_cperm, nl);
+  ALLOC(S.d_ctask_beg, tb.size());
+  ALLOC(S.d_ctask_end, te.size());
+  ALLOC(S.d_cam_t0, cam_t0.size());
+  ALLOC(S.d_Jp, 12 * nl);
+  ALLOC(S.d_F, nl);
+  ALLOC(S.d_Bc, 9 * nl);
+  ALLOC(S.d_w, nl);
+  ALLOC(S.d_T, 3 * nl);
+  ALLOC(S.d_V, 6 * npl);
+  ALLOC(S.d_gp, 3 * npl);
+  ALLOC(S.d_Vinv, 6 * npl);
+  ALLOC(S.d_wp, 3 * npl);
+  ALLOC(S.d_taskpart, S.nctasks * NV);
+  ALLOC(S.d_Ug, ncams * NV);
+  ALLOC(S.d_Cr, ncams * NV);
+  ALLOC(S.d_H, ncams * 81);
+  ALLOC(S.d_Minv, ncams * 81);
+  ALLOC(S.d_pcg, 6 * 9 * ncams);
+  ALLOC(S.d_x, h->nvar());
+  ALLOC(S.d_xt, h->nvar());
+  ALLOC(S.d_delta, h->nvar());
+  ALLOC(S.d_camt, ncams * CAM_REC);
+  S.npart = 4 * (int64_t)std::max<int64_t>(nblk(std::max(nl, npl), PT_THREADS), 1024);
+  ALLOC(S.d_part, S.npart + 16);  // + scratch for the four step norms
+  ALLOC(S.d_scal, S_COUNT);
+#undef ALLOC
+  BA_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&S.h_scal), S_COUNT * sizeof(double), cudaHostAllocDefault));
+  for (auto& e : S.ev) BA_CUDA(cudaEventCreate(&e));
+  auto up = [&](void* d, const void* s, size_t bytes) {
+    return bytes ? cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
+  };
+  BA_CUDA(up(S.d_tstart, tstart.data(), tstart.size() * 4));
+  BA_CUDA(up(S.d_pstart, pstart.data(), pstart.size() * 4));
+  BA_CUDA(up(S.d_cperm, cperm.data(), cperm.size() * 4));
+  BA_CUDA(up(S.d_ctask_beg, tb.data(), tb.size() * 4));
+  BA_CUDA(up(S.d_ctask_end, te.data(), te.size() * 4));
+  BA_CUDA(up(S.d_cam_t0, cam_t0.data(), cam_t0.size() * 4));
+  BA_CUDA(cudaMemsetAsync(S.d_scal, 0, S_COUNT * sizeof(double), h->stream));
+  BA_CUDA(cudaMemsetAsync(S.d_delta, 0, sizeof(double) * (size_t)h->nvar(), h->stream));
+  BA_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+  S.ready = true;
+  return BA_OK;
+}
+
+void lm_release(ba_handle* h) {
+  ba_lm_state& S = h->lm;
+  void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_Jp, S.d_F, S.d_Bc,
+                  S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
+                  S.d_Minv, S.d_pcg, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
+  for (void* p : ptrs) cudaFree(p);
+  if (S.h_scal) cudaFreeHost(S.h_scal);
+  for (auto& e : S.ev)
+    if (e) cudaEventDestroy(e);
+  S = ba_lm_state();
+}
+
+namespace {
+
+struct Solver {
+  ba_handle* h;
+  ba_lm_state& S;
+  cudaStream_t s;
+  int64_t nl, npl, ncams, n9;
+  double *b, *xc, *r, *z, *p, *q;
+  explicit Solver(ba_handle* hh) : h(hh), S(hh->lm), s(hh->stream) {
+    nl = h->nobs_l(); npl = h->npnts_l(); ncams = h->ncams; n9 = 9 * ncams;
+    b = S.d_pcg; xc = b + n9; r = xc + n9; z = r + n9; p = z + n9; q = p + n9;
+  }
+  int check() {
+    BA_CUDA(cudaGetLastError());
+    return BA_OK;
+  }
+  int reduce_to(int64_t nblocks, int K, int slot0) {
+    k_reduce_parts<<<K, RED_THREADS, 0, s>>>(S.d_part, nblocks, K, S.d_scal, slot0);
+    return check();
+  }
+  // camera-major pass + ordered gather (+ allreduce over ranks) into out (ncams x nacc)
+  template <int MODE>
+  int cam_pass(double* out, int check_done) {
+    constexpr int nacc = (MODE == 2) ? 9 : NV;
+    if (S.nctasks)
+      k_cam_pass<MODE><<<nblk(S.nctasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
+          S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_cperm, nl, S.d_Jp, S.d_F, S.d_Bc, S.d_w, S.d_T,
+          S.d_taskpart, S.d_scal);
+    k_cam_gather<<<nblk(ncams * nacc, 256), 256, 0, s>>>(S.d_cam_t0, ncams, nacc, S.d_taskpart, out, S.d_scal,
+                                                       check_done);
+    int rc = check();
+    if (rc) return rc;
+    return allreduce_sum(h, out, (size_t)(ncams * nacc));
+  }
+  // F, J blocks, V, g_p, U, g_c at x; leaves sum F^2, sum g_p^2 (allreduced) and sum g_c^2 in the scalars
+  int build(const double* x) {
+    launch_cam_precompute(x, h->npnts, ncams, h->d_camtab, s);
+    const unsigned nb = nblk(nl, PT_THREADS), npb = nblk(npl, PT_THREADS);
+    k_lm_build<<<nb, PT_THREADS, 0, s>>>(h->d_cam, h->d_pnt, h->d_pt2d, x, h->d_camtab, S.d_Jp, S.d_F, S.d_part, nl);
+    int rc = reduce_to(nb, 1, S_F2);
+    if (rc) return rc;
+    k_point_assemble<<<npb, PT_THREADS, 0, s>>>(S.d_pstart, npl, nl, S.d_Jp, S.d_F, S.d_V, S.d_gp, S.d_part);
+    if ((rc = reduce_to(npb, 1, S_GP2))) return rc;
+    if ((rc = cam_pass<0>(S.d_Ug, 0))) return rc;
+    k_gc_norm<<<1, RED_THREADS, 0, s>>>(ncams, S.d_Ug, S.d_scal);
+    if ((rc = check())) return rc;
+    return allreduce_sum(h, S.d_scal + S_F2, 2);
+  }
+  // everything that depends on lambda: Vinv, Schur diagonal blocks -> Minv, right-hand side b, H
+  int factor(double lambda) {
+    k_point_inv<<<nblk(npl, PT_THREADS), PT_THREADS, 0, s>>>(npl, lambda, S.d_V, S.d_gp, S.d_Vinv, S.d_wp);
+    k_point_prep<<<nblk(nl, PT_THREADS), PT_THREADS, 0, s>>>(h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_Vinv, S.d_wp, S.d_w, S.d_T);
+    int rc = check();
+    if (rc) return rc;
+    if ((rc = cam_pass<1>(S.d_Cr, 0))) return rc;
+    k_cam_finish<<<nblk(ncams, 64), 64, 0, s>>>(ncams, lambda, S.d_Ug, S.d_Cr, S.d_H, S.d_Minv, b, S.d_scal);
+    return check();
+  }
+  int read_scalars() {
+    BA_CUDA(cudaMemcpyAsync(S.h_scal, S.d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+    return BA_OK;
+  }
+  // block-Jacobi PCG on S dc = b; result in xc.  Convergence is decided on the device (S_DONE);
+  // the host only polls every `poll` iterations, later launches of a finished solve exit at once.
+  int pcg(double tol, int maxit, int* iters) {
+    k_pcg_init<<<1, RED_THREADS, 0, s>>>(n9, b, S.d_Minv, xc, r, z, p, S.d_scal);
+    int rc = check();
+    if (rc) return rc;
+    const int poll = 8;
+    int launched = 0;
+    for (;;) {
+      const int chunk = std::min(poll, maxit - launched);
+      for (int i = 0; i < chunk; ++i) {
+        if (S.ntasks)
+          k_point_solve<0><<<nblk(S.ntasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
+              S.d_tstart, S.ntasks, h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_F, p, S.d_Vinv, S.d_gp, S.d_w,
+              nullptr, nullptr, S.d_part, S.d_scal);
+        if ((rc = cam_pass<2>(q, 1))) return rc;
+        k_pcg_update<<<1, RED_THREADS, 0, s>>>(n9, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
+      }
+      launched += chunk;
+      if ((rc = check())) return rc;
+      if ((rc = read_scalars())) return rc;
+      if (S.h_scal[S_DONE] != 0.0 || launched >= maxit) break;
+    }
+    *iters = (int)S.h_scal[S_ITERS];
+    if (S.h_scal[S_DONE] == 2.0) {
+      h->err = "PCG breakdown (non-finite or non-positive curvature in the reduced camera system)";
+      return BA_ERR_NUMERIC;
+    }
+    return BA_OK;
+  }
+  // delta from xc: camera part copied, point part by back-substitution; sum (J delta + r)^2 -> S_DR2
+  int backsub(bool keep_dr) {
+    if (keep_dr && !S.d_dr) {
+      int rc = dmalloc(h, &S.d_dr, (size_t)nl);
+      if (rc) return rc;
+    }
+    k_copy_cam_delta<<<nblk(n9, 256), 256, 0, s>>>(n9, xc, S.d_delta + 3 * h->npnts);
+    const unsigned nb = nblk(S.ntasks, PT_THREADS / 32);
+    k_point_solve<1><<<nb, PT_THREADS, 0, s>>>(S.d_tstart, S.ntasks, h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_F,
+                                              xc, S.d_Vinv, S.d_gp, nullptr, S.d_delta, keep_dr ? S.d_dr : nullptr,
+                                              S.d_part, S.d_scal);
+    return reduce_to(nb, 1, S_DR2);
+  }
+  // xt = x + delta / div, norms, residual norm at xt; then every local sum is allreduced and read back
+  int trial(double div) {
+    const int64_t n = 3 * npl + n9;
+    const unsigned nb = (unsigned)std::min<int64_t>(nblk(n, 256), 1024);
+    k_step_update<<<nb, 256, 0, s>>>(S.d_x, S.d_delta, S.d_xt, 3 * h->pnt0, 3 * h->pnt1, 3 * h->npnts, h->nvar(), div,
+                                     S.d_part);
+    k_reduce_parts<<<4, RED_THREADS, 0, s>>>(S.d_part, nb, 4, S.d_part + S.npart, 0);
+    // scatter the four sums to their slots: dp2, xp2 local; dc2, xc2 replicated
+    BA_CUDA(cudaMemcpyAsync(S.d_scal + S_DP2, S.d_part + S.npart, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    BA_CUDA(cudaMemcpyAsync(S.d_scal + S_DC2, S.d_part + S.npart + 2, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    launch_cam_precompute(S.d_xt, h->npnts, ncams, S.d_camt, s);
+    const unsigned nbo = nblk(nl, PT_THREADS);
+    k_lm_trial<<<nbo, PT_THREADS, 0, s>>>(h->d_cam, h->d_pnt, h->d_pt2d, S.d_xt, S.d_camt, S.d_part, nl);
+    int rc = reduce_to(nbo, 1, S_TR2);
+    if (rc) return rc;
+    if ((rc = allreduce_sum(h, S.d_scal + S_DR2, 4))) return rc;  // DR2, DP2, XP2, TR2 are contiguous
+    return read_scalars();
+  }
+  int ls_dr(double dd) {
+    const unsigned nb = nblk(nl, PT_THREADS);
+    k_ls_dr<<<nb, PT_THREADS, 0, s>>>(S.d_dr, S.d_F, nl, dd, S.d_part);
+    return reduce_to(nb, 1, S_DR2);
+  }
+  // full-length host copy of a device vector laid out like x: point slices are summed over ranks
+  int gather_full(double* dvec, double* host) {
+    if (h->nranks > 1) {
+      // zero what this rank does not own (other ranks' points; cameras except on rank 0), then sum
+      if (h->pnt0 > 0) BA_CUDA(cudaMemsetAsync(dvec, 0, sizeof(double) * 3 * (size_t)h->pnt0, s));
+      if (h->pnt1 < h->npnts)
+        BA_CUDA(cudaMemsetAsync(dvec + 3 * h->pnt1, 0, sizeof(double) * 3 * (size_t)(h->npnts - h->pnt1), s));
+      if (h->rank != 0) BA_CUDA(cudaMemsetAsync(dvec + 3 * h->npnts, 0, sizeof(double) * (size_t)n9, s));
+      int rc = allreduce_sum(h, dvec, (size_t)h->nvar());
+      if (rc) return rc;
+    }
+    BA_CUDA(cudaMemcpyAsync(host, dvec, sizeof(double) * (size_t)h->nvar(), cudaMemcpyDeviceToHost, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+    return BA_OK;
+  }
+};
+
+inline double sq_to_half_norm2(double sumsq) {  // norm(v)^2 / 2 the way the reference forms it
+  const double n = sqrt(sumsq);
+  return n * n / 2;
+}
+
+}  // namespace
+}  // namespace ba
+
 extern "C" {
+
 void ba_lm_default_params(ba_lm_params* p) {
+  if (!p) return;
   const double eps = 2.220446049250313e-16;
-  p->restol = p->ortol = p->rtol = cbrt(eps);
+  p->restol = p->ortol = p->rtol = cbrt(eps);  // eps^(1/3), src/lm.jl:21-24
   p->satol = p->srtol = p->oatol = p->atol = sqrt(eps);
-  p->nu_d = 3; p->nu_m = 3; p->lambda = 30; p->delta_d = 2;
-  p->ite_max = 200; p->linesearch = 0; p->pcg_max_iter = 500; p->pcg_tol = 1e-13;
+  p->nu_d = 3; p->nu_m = 3; p->lambda = 30; p->delta_d = 2;  // src/lm.jl:25
+  p->ite_max = 200;                                             // src/lm.jl:26
+  p->linesearch = 0;
+  p->pcg_max_iter = 1000;
+  p->pcg_tol = 1e-13;
 }
-int ba_lm_step(ba_handle* h, const double*, double, double, int32_t, double*, double*, double*, double*, int32_t*) {
-  if (h) h->err = "ba_lm_step: not built yet";
-  return BA_ERR_ARG;
+
+int ba_lm_step(ba_handle* h, const double* x, double lambda, double pcg_tol, int32_t pcg_max_iter, double* delta,
+               double* dr2, double* obj, double* jtr, int32_t* pcg_iters) {
+  if (!h || !x || !delta) {
+    if (h) h->err = "null argument";
+    return BA_ERR_ARG;
+  }
+  int rc = ba::lm_prepare(h);
+  if (rc) return rc;
+  BA_CUDA(cudaSetDevice(h->device));
+  ba::Solver sv(h);
+  ba_lm_state& S = h->lm;
+  BA_CUDA(cudaMemcpyAsync(S.d_x, x, sizeof(double) * (size_t)h->nvar(), cudaMemcpyHostToDevice, h->stream));
+  BA_CUDA(cudaMemsetAsync(S.d_scal, 0, ba::S_COUNT * sizeof(double), h->stream));
+  if ((rc = sv.build(S.d_x))) return rc;
+  if ((rc = sv.factor(lambda))) return rc;
+  int it = 0;
+  rc = sv.pcg(pcg_tol, pcg_max_iter, &it);
+  if (pcg_iters) *pcg_iters = it;
+  if (rc) return rc;
+  if ((rc = sv.backsub(false))) return rc;
+  if ((rc = ba::allreduce_sum(h, S.d_scal + ba::S_DR2, 1))) return rc;
+  if ((rc = sv.read_scalars())) return rc;
+  if (S.h_scal[ba::S_ERR] != 0.0) {
+    h->err = "Schur diagonal block not positive definite";
+    return BA_ERR_NUMERIC;
+  }
+  if (dr2) *dr2 = ba::sq_to_half_norm2(S.h_scal[ba::S_DR2]);
+  if (obj) *obj = ba::sq_to_half_norm2(S.h_scal[ba::S_F2]);
+  if (jtr) {  // J'r = -[g_p; g_c]
+    std::vector<double> gp((size_t)(3 * sv.npl)), ug((size_t)(sv.ncams * ba::NV));
+    BA_CUDA(cudaMemcpyAsync(gp.data(), S.d_gp, gp.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    BA_CUDA(cudaMemcpyAsync(ug.data(), S.d_Ug, ug.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    BA_CUDA(cudaStreamSynchronize(h->stream));
+    // other ranks' point entries are not available here: left zero (documented in bagpu.h)
+    std::fill(jtr, jtr + h->nvar(), 0.0);
+    for (int64_t i = 0; i < 3 * sv.npl; ++i) jtr[3 * h->pnt0 + i] = -gp[(size_t)i];
+    for (int64_t c = 0; c < sv.ncams; ++c)
+      for (int j = 0; j < 9; ++j) jtr[3 * h->npnts + 9 * c + j] = -ug[(size_t)(c * ba::NV + 45 + j)];
+  }
+  return sv.gather_full(S.d_delta, delta);
 }
-int ba_lm_solve(ba_handle* h, double*, const ba_lm_params*, ba_lm_stats*, ba_iter_cb, void*) {
-  if (h) h->err = "ba_lm_solve: not built yet";
-  return BA_ERR_ARG;
+
+int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm_stats* st, ba_iter_cb cb,
+                void* user) {
+  using namespace ba;
+  if (!h || !x_inout) {
+    if (h) h->err = "null argument";
+    return BA_ERR_ARG;
+  }
+  ba_lm_params prm;
+  if (prm_in) prm = *prm_in; else ba_lm_default_params(&prm);
+  int rc = lm_prepare(h);
+  if (rc) return rc;
+  BA_CUDA(cudaSetDevice(h->device));
+  Solver sv(h);
+  ba_lm_state& S = h->lm;
+  const auto wall0 = std::chrono::steady_clock::now();
+  double t_eval = 0, t_asm = 0, t_pcg = 0, t_back = 0;
+  int64_t pcg_total = 0;
+  auto rec = [&](int i) { cudaEventRecord(S.ev[i], h->stream); };
+  auto lap = [&](int a, int b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, S.ev[a], S.ev[b]);
+    return (double)ms;
+  };
+
+  BA_CUDA(cudaMemcpyAsync(S.d_x, x_inout, sizeof(double) * (size_t)h->nvar(), cudaMemcpyHostToDevice, h->stream));
+  BA_CUDA(cudaMemsetAsync(S.d_scal, 0, S_COUNT * sizeof(double), h->stream));
+  int64_t iter = 0;
+  // src/lm.jl:39-59
+  rec(0);
+  if ((rc = sv.build(S.d_x))) return rc;
+  rec(1);
+  if ((rc = sv.read_scalars())) return rc;
+  t_eval += lap(0, 1);
+  double norm_r = sqrt(S.h_scal[S_F2]);
+  double obj = norm_r * norm_r / 2;
+  double norm_Jtr = sqrt(S.h_scal[S_GP2] + S.h_scal[S_GC2]);
+  double lambda = std::max(prm.lambda, 1e10 / norm_Jtr);
+  double norm_delta = 0, dr2 = 0;
+  const double eps_first_order = prm.atol + prm.rtol * norm_Jtr;  // :107
+  double old_obj = obj;
+  bool small_step = false, first_order = norm_Jtr < eps_first_order, small_residual = norm_r < prm.restol;
+  bool small_obj_change = false, tired = iter > prm.ite_max, fail = false, fail2 = false;
+  bool need_factor = true;
+
+  while (!(small_step || first_order || small_residual || small_obj_change || tired || fail || fail2)) {
+    iter += 1;
+    // damped solve (stands in for ldl_factorize + ldl_solve!, src/lm.jl:175-180,227-229)
+    rec(0);
+    if (need_factor) {
+      if ((rc = sv.factor(lambda))) return rc;
+      need_factor = false;
+    }
+    rec(1);
+    int pit = 0;
+    rc = sv.pcg(prm.pcg_tol, prm.pcg_max_iter, &pit);
+    pcg_total += pit;
+    if (rc == BA_ERR_NUMERIC || S.h_scal[S_ERR] != 0.0) {  // like SQDException / NaN step: status exception
+      fail2 = true;
+      continue;
+    }
+    if (rc) return rc;
+    rec(2);
+    if ((rc = sv.backsub(prm.linesearch != 0))) return rc;
+    rec(3);
+    // src/lm.jl:251-254
+    if ((rc = sv.trial(1.0))) return rc;
+    rec(4);
+    BA_CUDA(cudaEventSynchronize(S.ev[4]));
+    t_asm += lap(0, 1); t_pcg += lap(1, 2); t_back += lap(2, 3); t_eval += lap(3, 4);
+    dr2 = sq_to_half_norm2(S.h_scal[S_DR2]);
+    double norm_rsuiv = sqrt(S.h_scal[S_TR2]);
+    double obj_suiv = norm_rsuiv * norm_rsuiv / 2;
+    // :257-260
+    double pred = obj - dr2, ared = obj - obj_suiv;
+    bool step_accepted = ared >= 1e-4 * pred;
+    bool acc_str = step_accepted && dr2 <= obj;
+    int ntimes = 0;
+    // :264-295
+    if (prm.linesearch) {
+      while (!step_accepted && ntimes < 4) {
+        if ((rc = sv.ls_dr(prm.delta_d))) return rc;
+        if ((rc = sv.trial(prm.delta_d))) return rc;
+        norm_rsuiv = sqrt(S.h_scal[S_TR2]);
+        obj_suiv = norm_rsuiv * norm_rsuiv / 2;
+        dr2 = sq_to_half_norm2(S.h_scal[S_DR2]);
+        pred = obj - dr2; ared = obj - obj_suiv;
+        step_accepted = ared >= 1e-4 * pred;
+        acc_str = step_accepted && dr2 <= obj;
+        ntimes += 1;
+      }
+    }
+    // :297-302
+    norm_delta = sqrt(S.h_scal[S_DP2] + S.h_scal[S_DC2]);
+    if (std::isnan(norm_delta)) {
+      fail2 = true;
+      continue;
+    }
+    // :304
+    if (cb) {
+      ba_lm_row row;
+      row.iter = iter; row.f = obj; row.df = old_obj - obj; row.dfeas = norm_Jtr; row.lambda = lambda;
+      row.delta_norm = norm_delta; row.rho = ared / pred; row.accepted = step_accepted; row.acc_str = acc_str;
+      row.pcg_iters = pit; row.ntimes = ntimes;
+      cb(&row, user);
+    }
+    if (!step_accepted) {
+      // :306-325
+      lambda = std::max(lambda, 1 / norm_delta) * pow(prm.nu_m, (double)(ntimes + 1));
+      need_factor = true;
+    } else {
+      // :328-338
+      if (ntimes > 0) lambda /= pow(prm.nu_d, (double)(ntimes - 1));
+      else lambda /= prm.nu_d;
+      if (ared >= 0.9 * pred) lambda /= prm.nu_d;
+      lambda = std::max(1.0e-8, lambda);
+      std::swap(S.d_x, S.d_xt);
+      const double norm_x = sqrt(S.h_scal[S_XP2] + S.h_scal[S_XC2]);
+      // :341-371: Jacobian, residual, J'r at the new x
+      rec(0);
+      if ((rc = sv.build(S.d_x))) return rc;
+      rec(1);
+      if ((rc = sv.read_scalars())) return rc;
+      t_eval += lap(0, 1);
+      old_obj = obj;
+      norm_r = norm_rsuiv;
+      obj = obj_suiv;
+      need_factor = true;
+      // :374-379
+      norm_Jtr = sqrt(S.h_scal[S_GP2] + S.h_scal[S_GC2]);
+      small_step = norm_delta < prm.satol + prm.srtol * norm_x;
+      first_order = norm_Jtr < eps_first_order;
+      small_residual = norm_r < prm.restol;
+      small_obj_change = old_obj - obj < prm.oatol + prm.ortol * old_obj;
+    }
+    tired = iter > prm.ite_max;  // :382 (elapsed_time is never updated inside the loop)
+  }
+  int status = 0;  // :391-405
+  if (small_step) status = 1;
+  else if (first_order) status = 2;
+  else if (small_residual) status = 3;
+  else if (small_obj_change) status = 4;
+  else if (fail) status = 5;
+  else if (fail2) status = 6;
+  else if (tired) status = 7;
+  if ((rc = sv.gather_full(S.d_x, x_inout))) return rc;
+  if (st) {
+    st->status = status; st->pad = 0; st->iter = iter; st->objective = obj; st->dual_feas = norm_Jtr;
+    st->lambda_final = lambda;
+    st->elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    st->pcg_iters_total = pcg_total;
+    st->t_eval_ms = t_eval; st->t_assemble_ms = t_asm; st->t_pcg_ms = t_pcg; st->t_backsub_ms = t_back;
+  }
+  return BA_OK;
 }
-}
+
+}  // extern "C"

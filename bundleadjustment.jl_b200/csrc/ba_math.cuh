@@ -96,7 +96,7 @@ __device__ __forceinline__ void eval_residual(const double X[3], const double* _
 // Faithful dense path: reproduces the reference's NaN/Inf propagation through the dense
 // products (JP3*JP2)*JP1 including their structural zeros (src/BALNLPModels.jl:197).  Only taken
 // when the fast path produced a non-finite value, so its cost does not matter.
-__device__ __noinline__ void eval_block_dense(const double X[3], const double* __restrict__ cam,
+static __device__ __noinline__ void eval_block_dense(const double X[3], const double* __restrict__ cam,
                                               double ox, double oy, ObsBlock& o) {
   const double kx = cam[CK0], ky = cam[CK1], kz = cam[CK2], c = cam[CC], s = cam[CS];
   const double a = cam[CA], g = cam[CG], b = 1.0 - a, omc = 1.0 - c;
