@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="venice-1778")
     ap.add_argument("--lm-iters", type=int, default=8, help="LM iterations timed in the lm leg (0 = skip)")
+    ap.add_argument("--pcg-max-iter", type=int, default=None, help="cap PCG iterations per solve (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -258,7 +259,8 @@ def main():
             ba._lib.check(L.ba_comm_init(h, arr), h)
         barrier()
         t0 = time.perf_counter()
-        st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=args.lm_iters - 1)
+        st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=args.lm_iters - 1,
+                                    pcg_max_iter=args.pcg_max_iter)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")

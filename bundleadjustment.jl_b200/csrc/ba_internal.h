@@ -31,7 +31,11 @@ struct ba_lm_state {
   int32_t* d_ctask_beg = nullptr;  // camera-major tasks: [beg, end) positions of one camera
   int32_t* d_ctask_end = nullptr;
   int32_t* d_cam_t0 = nullptr;   // first task of each camera, ncams + 1
+  int32_t* d_ctask_cam = nullptr;  // camera of each task
+  int32_t* d_cam_cnt = nullptr;  // per camera: tasks finished in the current pass (ordered two-level sums)
   int64_t nctasks = 0;
+  int32_t* d_empty_cams = nullptr;  // cameras without observations on this rank
+  int64_t nempty = 0;
   // ---- per observation ------------------------------------------------------------------------
   double2* d_Jp = nullptr;   // 12 planes x nl, point-major: plane j = (row1[j], row2[j]) of the 2x12 block
   double2* d_F = nullptr;    // nl residuals

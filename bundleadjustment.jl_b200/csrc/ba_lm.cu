@@ -21,7 +21,10 @@
 #include <cmath>
 #include <cstring>
 #include "ba_internal.h"
+#include <cooperative_groups.h>
 #include "ba_math.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ba {
 
@@ -231,9 +234,11 @@ k_point_prep(const int32_t* __restrict__ pnt_idx, int64_t pnt0, int64_t nl, cons
 template <int MODE>
 __global__ void __launch_bounds__(PT_THREADS)
 k_cam_pass(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, int64_t nctasks,
+           const int32_t* __restrict__ task_cam, const int32_t* __restrict__ cam_t0, int32_t* __restrict__ cam_cnt,
            const int32_t* __restrict__ cperm, int64_t nl, const double2* __restrict__ Jp,
            const double2* __restrict__ F, double2* __restrict__ Bc, const double2* __restrict__ w,
-           const double* __restrict__ T, double* __restrict__ taskpart, const double* __restrict__ scal) {
+           const double* __restrict__ T, double* taskpart, double* __restrict__ out,
+           const double* __restrict__ scal) {
   if (MODE == 2 && scal[S_DONE] != 0.0) return;
   constexpr int NACC = (MODE == 2) ? 9 : NV;
   const int lane = threadIdx.x & 31;
@@ -289,25 +294,40 @@ k_cam_pass(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, i
   }
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = warp_sum(acc[i]);
+  // ordered two-level sum without a second kernel: the task that finishes last for its camera adds the
+  // camera's task partials in task order (threadfence reduction; partials are read past L1)
+  const int c = task_cam[task];
+  const int tb0 = cam_t0[c], nt = cam_t0[c + 1] - tb0;
+  if (nt == 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) out[(int64_t)c * NACC + i] = acc[i];
+    }
+    return;
+  }
+  int last = 0;
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < NACC; ++i) taskpart[task * NACC + i] = acc[i];
+    __threadfence();
+    last = (atomicAdd(cam_cnt + c, 1) == nt - 1);
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {
+    __threadfence();
+    for (int j = lane; j < NACC; j += 32) {
+      double s = 0.0;
+      for (int t = 0; t < nt; ++t) s += __ldcg(taskpart + (int64_t)(tb0 + t) * NACC + j);
+      out[(int64_t)c * NACC + j] = s;
+    }
+    if (lane == 0) cam_cnt[c] = 0;  // ready for the next pass (kernel boundaries order this)
   }
 }
 
-// out[c * nacc + j] = sum over the camera's tasks (fixed order)
-__global__ void __launch_bounds__(256)
-k_cam_gather(const int32_t* __restrict__ cam_t0, int64_t ncams, int nacc, const double* __restrict__ taskpart,
-             double* __restrict__ out, const double* __restrict__ scal, int check_done) {
-  if (check_done && scal[S_DONE] != 0.0) return;
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= ncams * nacc) return;
-  const int64_t c = i / nacc;
-  const int j = (int)(i - c * nacc);
-  double s = 0.0;
-  const int t1 = cam_t0[c + 1];
-  for (int t = cam_t0[c]; t < t1; ++t) s += taskpart[(int64_t)t * nacc + j];
-  out[i] = s;
+// cameras without observations on this rank: their sums are zero
+__global__ void k_zero_cams(const int32_t* __restrict__ cams, int n, int nacc, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * nacc) out[(int64_t)cams[i / nacc] * nacc + (i % nacc)] = 0.0;
 }
 
 __device__ __forceinline__ int sym9(int i, int j) {  // i <= j, row-wise upper triangle
@@ -394,13 +414,62 @@ __device__ __forceinline__ void warp_stage_vec9(const double* __restrict__ v, in
 }
 
 struct PtLane {
-  double2 A0, A1, A2;
+  double2 A0, A1, A2;  // point part of the block (columns 0..2)
+  double2 B[9];        // camera part
+  double vi[6];        // (V_p + lambda I)^-1, prefetched
+  double g[3];         // g_p (back-substitution only)
+  double2 f;           // residual (back-substitution only)
   double2 y;
   double t0, t1, t2;
 };
 
+// Issue every global load of one observation up front (block planes, the point's inverse, and for the
+// back-substitution g_p and F): the only dependent chain left is index -> address.
 template <int MODE>
-__global__ void __launch_bounds__(PT_THREADS)
+__device__ __forceinline__ void pt_load(PtLane& L, bool valid, int64_t k, int64_t p, int64_t nl,
+                                        const double2* __restrict__ Jp, const double2* __restrict__ F,
+                                        const double* __restrict__ Vinv, const double* __restrict__ gp) {
+  if (valid) {
+    L.A0 = __ldcs(Jp + k);
+    L.A1 = __ldcs(Jp + nl + k);
+    L.A2 = __ldcs(Jp + 2 * nl + k);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) L.B[j] = __ldcs(Jp + (int64_t)(3 + j) * nl + k);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) L.vi[i] = __ldg(Vinv + p * 6 + i);
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) L.g[i] = __ldg(gp + p * 3 + i);
+      L.f = __ldg(F + k);
+    }
+  } else {
+    L.A0 = L.A1 = L.A2 = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) L.B[j] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) L.vi[i] = 0.0;
+    L.g[0] = L.g[1] = L.g[2] = 0.0;
+    L.f = make_double2(0.0, 0.0);
+  }
+}
+
+// y = B v_c (v staged in shared memory), t = A' y
+__device__ __forceinline__ void pt_first(PtLane& L, const double* __restrict__ vrow, int lane) {
+  double yx = 0.0, yy = 0.0;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const double vj = vrow[lane * 9 + j];
+    yx += L.B[j].x * vj;
+    yy += L.B[j].y * vj;
+  }
+  L.y = make_double2(yx, yy);
+  L.t0 = L.A0.x * yx + L.A0.y * yy;
+  L.t1 = L.A1.x * yx + L.A1.y * yy;
+  L.t2 = L.A2.x * yx + L.A2.y * yy;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PT_THREADS, 5)
 k_point_solve(const int32_t* __restrict__ tstart, int64_t ntasks, const int32_t* __restrict__ cam_idx,
               const int32_t* __restrict__ pnt_idx, int64_t pnt0, int64_t nl, const double2* __restrict__ Jp,
               const double2* __restrict__ F, const double* __restrict__ vcam, const double* __restrict__ Vinv,
@@ -414,51 +483,19 @@ k_point_solve(const int32_t* __restrict__ tstart, int64_t ntasks, const int32_t*
   double* vrow = vst + warp * 288;
   double acc_dr2 = 0.0;
 
-  // per-observation first half: y = B v_c, t = A' y
-  auto first_half = [&](int64_t k, bool valid, PtLane& L) {
-    int c = 0;
-    double2 B[9];
-    if (valid) {
-      c = __ldg(cam_idx + k);
-      L.A0 = Jp[k];
-      L.A1 = Jp[nl + k];
-      L.A2 = Jp[2 * nl + k];
-#pragma unroll
-      for (int j = 0; j < 9; ++j) B[j] = Jp[(int64_t)(3 + j) * nl + k];
-    } else {
-      L.A0 = L.A1 = L.A2 = make_double2(0.0, 0.0);
-#pragma unroll
-      for (int j = 0; j < 9; ++j) B[j] = make_double2(0.0, 0.0);
-    }
-    __syncwarp();
-    warp_stage_vec9(vcam, c, lane, vrow);
-    double yx = 0.0, yy = 0.0;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const double vj = vrow[lane * 9 + j];
-      yx += B[j].x * vj;
-      yy += B[j].y * vj;
-    }
-    L.y = make_double2(yx, yy);
-    L.t0 = L.A0.x * yx + L.A0.y * yy;
-    L.t1 = L.A1.x * yx + L.A1.y * yy;
-    L.t2 = L.A2.x * yx + L.A2.y * yy;
-  };
   // per-observation second half, given the point's summed t
   auto second_half = [&](int64_t k, int64_t p, const PtLane& L, double T0, double T1, double T2, bool writer) {
-    const double* vi = Vinv + p * 6;
-    const double i00 = vi[0], i01 = vi[1], i02 = vi[2], i11 = vi[3], i12 = vi[4], i22 = vi[5];
+    const double i00 = L.vi[0], i01 = L.vi[1], i02 = L.vi[2], i11 = L.vi[3], i12 = L.vi[4], i22 = L.vi[5];
     if (MODE == 0) {
       const double u0 = (i00 * T0 + i01 * T1) + i02 * T2, u1 = (i01 * T0 + i11 * T1) + i12 * T2,
                    u2 = (i02 * T0 + i12 * T1) + i22 * T2;
       w_out[k] = make_double2((L.A0.x * u0 + L.A1.x * u1) + L.A2.x * u2, (L.A0.y * u0 + L.A1.y * u1) + L.A2.y * u2);
     } else {
-      const double r0 = gp[p * 3] - T0, r1 = gp[p * 3 + 1] - T1, r2 = gp[p * 3 + 2] - T2;
+      const double r0 = L.g[0] - T0, r1 = L.g[1] - T1, r2 = L.g[2] - T2;
       const double d0 = (i00 * r0 + i01 * r1) + i02 * r2, d1 = (i01 * r0 + i11 * r1) + i12 * r2,
                    d2 = (i02 * r0 + i12 * r1) + i22 * r2;
-      const double2 f = F[k];
-      const double ex = ((L.A0.x * d0 + L.A1.x * d1) + L.A2.x * d2) + L.y.x + f.x;
-      const double ey = ((L.A0.y * d0 + L.A1.y * d1) + L.A2.y * d2) + L.y.y + f.y;
+      const double ex = ((L.A0.x * d0 + L.A1.x * d1) + L.A2.x * d2) + L.y.x + L.f.x;
+      const double ey = ((L.A0.y * d0 + L.A1.y * d1) + L.A2.y * d2) + L.y.y + L.f.y;
       acc_dr2 += ex * ex + ey * ey;
       if (dr_out) dr_out[k] = make_double2(-ex, -ey);
       if (writer) {
@@ -476,9 +513,15 @@ k_point_solve(const int32_t* __restrict__ tstart, int64_t ntasks, const int32_t*
       // whole points packed into one warp: segmented sums over runs of equal point id
       const int64_t k = t0 + lane;
       const bool valid = k < t1;
-      const int p = valid ? (int)(__ldg(pnt_idx + k) - pnt0) : -1;
+      int c = 0, p = -1;
+      if (valid) {
+        c = __ldg(cam_idx + k);
+        p = (int)(__ldg(pnt_idx + k) - pnt0);
+      }
       PtLane L;
-      first_half(k, valid, L);
+      pt_load<MODE>(L, valid, k, p, nl, Jp, F, Vinv, gp);
+      warp_stage_vec9(vcam, c, lane, vrow);
+      pt_first(L, vrow, lane);
       const int pprev = __shfl_up_sync(0xffffffffu, p, 1);
       const bool head = (lane == 0) || (p != pprev);
       const unsigned hm = __ballot_sync(0xffffffffu, head);
@@ -486,11 +529,11 @@ k_point_solve(const int32_t* __restrict__ tstart, int64_t ntasks, const int32_t*
       double s0 = L.t0, s1 = L.t1, s2 = L.t2;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const double a = shfl_up_d(s0, d), b = shfl_up_d(s1, d), c = shfl_up_d(s2, d);
+        const double a = shfl_up_d(s0, d), b = shfl_up_d(s1, d), cc = shfl_up_d(s2, d);
         if (lane - d >= seg0) {
           s0 += a;
           s1 += b;
-          s2 += c;
+          s2 += cc;
         }
       }
       const unsigned above = (lane == 31) ? 0u : (hm >> (lane + 1));
@@ -501,19 +544,24 @@ k_point_solve(const int32_t* __restrict__ tstart, int64_t ntasks, const int32_t*
       // one point with more than 32 observations: sum over chunks, then a second sweep
       const int64_t p = __ldg(pnt_idx + t0) - pnt0;
       double T0 = 0.0, T1 = 0.0, T2 = 0.0;
-      for (int64_t base = t0; base < t1; base += 32) {
-        const int64_t k = base + lane;
-        PtLane L;
-        first_half(k, k < t1, L);
-        T0 += warp_sum(L.t0);
-        T1 += warp_sum(L.t1);
-        T2 += warp_sum(L.t2);
-      }
-      for (int64_t base = t0; base < t1; base += 32) {
-        const int64_t k = base + lane;
-        PtLane L;
-        first_half(k, k < t1, L);
-        if (k < t1) second_half(k, p, L, T0, T1, T2, k == t0);
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t base = t0; base < t1; base += 32) {
+          const int64_t k = base + lane;
+          const bool valid = k < t1;
+          const int c = valid ? __ldg(cam_idx + k) : 0;
+          PtLane L;
+          pt_load<MODE>(L, valid, k, p, nl, Jp, F, Vinv, gp);
+          __syncwarp();
+          warp_stage_vec9(vcam, c, lane, vrow);
+          pt_first(L, vrow, lane);
+          if (pass == 0) {
+            T0 += warp_sum(L.t0);
+            T1 += warp_sum(L.t1);
+            T2 += warp_sum(L.t2);
+          } else if (valid) {
+            second_half(k, p, L, T0, T1, T2, k == t0);
+          }
+        }
       }
     }
   }
@@ -578,84 +626,109 @@ k_ls_dr(double2* __restrict__ dr, const double2* __restrict__ F, int64_t nl, dou
 }
 
 // ---------------------------------------------------------------------------------------------
-// PCG on the reduced camera system: camera-sized vector work in ONE block (two dot products per
-// iteration without grid-wide synchronisation); the heavy S p product is the two passes above.
+// PCG on the reduced camera system: the camera-sized vector work of one iteration runs as ONE
+// thread-block cluster (8 CTAs on 8 SMs of one GPC).  The two dot products of the iteration are
+// block sums combined through distributed shared memory between cluster barriers, in rank order,
+// so no grid-wide synchronisation, no atomics and no host round trip are needed and the result is
+// reproducible.  Cameras are dealt to CTAs in contiguous ranges: the 9 rows of a camera live in
+// one CTA, so the r -> z = Minv r dependency needs only __syncthreads.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double row9(const double* __restrict__ M, const double* __restrict__ v, int64_t i) {
+constexpr int PCG_CTAS = 8;
+constexpr int PCG_THREADS = 512;
+
+__device__ __forceinline__ double row9(const double* __restrict__ M, const double* v, int64_t i) {
   const int64_t c = i / 9;
   const double* m = M + c * 81 + (i - c * 9) * 9;
   const double* x = v + c * 9;
   double s = 0.0;
 #pragma unroll
-  for (int j = 0; j < 9; ++j) s += m[j] * x[j];
+  for (int j = 0; j < 9; ++j) s += __ldg(m + j) * x[j];
   return s;
 }
 
-__global__ void __launch_bounds__(RED_THREADS)
-k_pcg_init(int64_t n9, const double* __restrict__ b, const double* __restrict__ Minv, double* __restrict__ xc,
-           double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ scal) {
-  __shared__ double sh[RED_THREADS / 32];
-  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
-    r[i] = b[i];
-    xc[i] = 0.0;
-  }
-  __syncthreads();
-  double rz = 0.0;
-  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
-    const double zi = row9(Minv, r, i);
-    z[i] = zi;
-    p[i] = zi;
-    rz += r[i] * zi;
-  }
-  rz = block_sum<RED_THREADS>(rz, sh);
-  if (threadIdx.x == 0) {
-    scal[S_RZ] = rz;
-    scal[S_RZ0] = rz;
-    scal[S_ITERS] = 0.0;
-    scal[S_REL] = 1.0;
-    // zero right-hand side: the zero step is the solution; NaN: let the caller see it
-    scal[S_DONE] = (rz == 0.0) ? 1.0 : ((rz == rz) ? 0.0 : 2.0);
-  }
+// sum over the cluster of one value per CTA, every CTA obtains the same total (rank order)
+__device__ __forceinline__ double cluster_sum(cg::cluster_group& cluster, double v, double* sh, double* slot) {
+  v = block_sum<PCG_THREADS>(v, sh);
+  if (threadIdx.x == 0) *slot = v;
+  cluster.sync();
+  double t = 0.0;
+#pragma unroll
+  for (int r = 0; r < PCG_CTAS; ++r) t += *cluster.map_shared_rank(slot, r);
+  return t;
 }
 
-// q holds sum_k B'w on entry (possibly allreduced); on exit q = S p
-__global__ void __launch_bounds__(RED_THREADS)
-k_pcg_update(int64_t n9, const double* __restrict__ H, const double* __restrict__ Minv, double* __restrict__ q,
-             double* __restrict__ xc, double* __restrict__ r, double* __restrict__ z, double* __restrict__ p,
-             double* __restrict__ scal, double tol) {
-  __shared__ double sh[RED_THREADS / 32];
-  if (scal[S_DONE] != 0.0) return;
+// INIT: r = b, xc = 0, z = Minv r, p = z, rz0 = r.z.   Otherwise one PCG iteration: on entry q holds
+// sum_k B'w (allreduced over ranks in sharded mode); q = (U + lambda I) p - q = S p; alpha, xc, r, z, beta, p.
+template <bool INIT>
+__global__ void __cluster_dims__(PCG_CTAS, 1, 1) __launch_bounds__(PCG_THREADS)
+k_pcg_cluster(int64_t ncams, const double* __restrict__ b, const double* __restrict__ H,
+              const double* __restrict__ Minv, double* q, double* xc, double* r, double* z, double* p,
+              double* scal, double tol) {
+  __shared__ double sh[PCG_THREADS / 32];
+  __shared__ double slots[2];
+  cg::cluster_group cluster = cg::this_cluster();
+  if (!INIT && scal[S_DONE] != 0.0) return;  // uniform over the cluster: written by an earlier kernel
+  const int rank = (int)cluster.block_rank();
+  const int64_t per = (ncams + PCG_CTAS - 1) / PCG_CTAS;
+  const int64_t i0 = min((long long)(rank * per), (long long)ncams) * 9,
+                i1 = min((long long)((rank + 1) * per), (long long)ncams) * 9;
+  if (INIT) {
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
+      r[i] = b[i];
+      xc[i] = 0.0;
+    }
+    __syncthreads();
+    double rz = 0.0;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
+      const double zi = row9(Minv, r, i);
+      z[i] = zi;
+      p[i] = zi;
+      rz += r[i] * zi;
+    }
+    rz = cluster_sum(cluster, rz, sh, &slots[0]);
+    if (rank == 0 && threadIdx.x == 0) {
+      scal[S_RZ] = rz;
+      scal[S_RZ0] = rz;
+      scal[S_ITERS] = 0.0;
+      scal[S_REL] = 1.0;
+      // zero right-hand side: the zero step is the solution; NaN: let the caller see it
+      scal[S_DONE] = (rz == 0.0) ? 1.0 : ((rz == rz) ? 0.0 : 2.0);
+    }
+    cluster.sync();  // nobody leaves while its shared memory may still be read
+    return;
+  }
   const double rz = scal[S_RZ], rz0 = scal[S_RZ0];
   double pq = 0.0;
-  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
     const double qi = row9(H, p, i) - q[i];
     q[i] = qi;
     pq += p[i] * qi;
   }
-  pq = block_sum<RED_THREADS>(pq, sh);
-  if (!(pq > 0.0)) {  // breakdown: S is SPD in exact arithmetic, so this is NaN/Inf or loss of definiteness
-    if (threadIdx.x == 0) {
+  pq = cluster_sum(cluster, pq, sh, &slots[0]);
+  if (!(pq > 0.0)) {  // breakdown: S is SPD in exact arithmetic, so this is NaN/Inf or lost definiteness
+    if (rank == 0 && threadIdx.x == 0) {
       scal[S_DONE] = 2.0;
       scal[S_PQ] = pq;
     }
+    cluster.sync();
     return;
   }
   const double alpha = rz / pq;
-  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
     xc[i] += alpha * p[i];
     r[i] -= alpha * q[i];
   }
   __syncthreads();
   double rzn = 0.0;
-  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
     const double zi = row9(Minv, r, i);
     z[i] = zi;
     rzn += r[i] * zi;
   }
-  rzn = block_sum<RED_THREADS>(rzn, sh);
+  rzn = cluster_sum(cluster, rzn, sh, &slots[1]);
   const double beta = rzn / rz;
-  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) p[i] = z[i] + beta * p[i];
-  if (threadIdx.x == 0) {
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) p[i] = z[i] + beta * p[i];
+  if (rank == 0 && threadIdx.x == 0) {
     const double rel = sqrt(rzn / rz0);
     scal[S_RZ] = rzn;
     scal[S_PQ] = pq;
@@ -663,6 +736,7 @@ k_pcg_update(int64_t n9, const double* __restrict__ H, const double* __restrict_
     scal[S_REL] = rel;
     if (!(rel > tol)) scal[S_DONE] = (rel == rel) ? 1.0 : 2.0;
   }
+  cluster.sync();
 }
 
 __global__ void k_copy_cam_delta(int64_t n9, const double* __restrict__ xc, double* __restrict__ delta_c) {
@@ -726,7 +800,7 @@ int lm_prepare(ba_handle* h) {
     tstart.push_back((int32_t)nl);
   }
   // ---- camera-major order (stable counting sort) and tasks
-  std::vector<int32_t> cam_start((size_t)ncams + 1, 0), cperm((size_t)nl), tb, te, cam_t0((size_t)ncams + 1, 0);
+  std::vector<int32_t> cam_start((size_t)ncams + 1, 0), cperm((size_t)nl), tb, te, tc, cam_t0((size_t)ncams + 1, 0);
   for (int64_t k = 0; k < nl; ++k) cam_start[(size_t)h->h_cam[(size_t)k] + 1]++;
   for (int64_t c = 0; c < ncams; ++c) cam_start[(size_t)c + 1] += cam_start[(size_t)c];
   {
@@ -739,10 +813,15 @@ int lm_prepare(ba_handle* h) {
     cam_t0[(size_t)c] = (int32_t)tb.size();
     for (int32_t b = cam_start[(size_t)c]; b < cam_start[(size_t)c + 1]; b += tsz) {
       tb.push_back(b);
+      tc.push_back((int32_t)c);
       te.push_back(std::min<int32_t>(b + tsz, cam_start[(size_t)c + 1]));
     }
   }
   cam_t0[(size_t)ncams] = (int32_t)tb.size();
+  std::vector<int32_t> empty_cams;
+  for (int64_t c = 0; c < ncams; ++c)
+    if (cam_start[(size_t)c] == cam_start[(size_t)c + 1]) empty_cams.push_back((int32_t)c);
+  S.nempty = (int64_t)empty_cams.size();
   S.nctasks = (int64_t)tb.size();
 
   int rc;
@@ -753,6 +832,9 @@ int lm_prepare(ba_handle* h) {
   ALLOC(S.d_ctask_beg, tb.size());
   ALLOC(S.d_ctask_end, te.size());
   ALLOC(S.d_cam_t0, cam_t0.size());
+  ALLOC(S.d_ctask_cam, tc.size());
+  ALLOC(S.d_cam_cnt, ncams);
+  ALLOC(S.d_empty_cams, empty_cams.size());
   ALLOC(S.d_Jp, 12 * nl);
   ALLOC(S.d_F, nl);
   ALLOC(S.d_Bc, 9 * nl);
@@ -787,6 +869,9 @@ int lm_prepare(ba_handle* h) {
   BA_CUDA(up(S.d_ctask_beg, tb.data(), tb.size() * 4));
   BA_CUDA(up(S.d_ctask_end, te.data(), te.size() * 4));
   BA_CUDA(up(S.d_cam_t0, cam_t0.data(), cam_t0.size() * 4));
+  BA_CUDA(up(S.d_ctask_cam, tc.data(), tc.size() * 4));
+  BA_CUDA(up(S.d_empty_cams, empty_cams.data(), empty_cams.size() * 4));
+  BA_CUDA(cudaMemsetAsync(S.d_cam_cnt, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(ncams, 1), h->stream));
   BA_CUDA(cudaMemsetAsync(S.d_scal, 0, S_COUNT * sizeof(double), h->stream));
   BA_CUDA(cudaMemsetAsync(S.d_delta, 0, sizeof(double) * (size_t)h->nvar(), h->stream));
   BA_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
@@ -796,7 +881,7 @@ int lm_prepare(ba_handle* h) {
 
 void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
-  void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_Jp, S.d_F, S.d_Bc,
+  void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_Bc,
                   S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
                   S.d_Minv, S.d_pcg, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
   for (void* p : ptrs) cudaFree(p);
@@ -832,10 +917,10 @@ struct Solver {
     constexpr int nacc = (MODE == 2) ? 9 : NV;
     if (S.nctasks)
       k_cam_pass<MODE><<<nblk(S.nctasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
-          S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_cperm, nl, S.d_Jp, S.d_F, S.d_Bc, S.d_w, S.d_T,
-          S.d_taskpart, S.d_scal);
-    k_cam_gather<<<nblk(ncams * nacc, 256), 256, 0, s>>>(S.d_cam_t0, ncams, nacc, S.d_taskpart, out, S.d_scal,
-                                                       check_done);
+          S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_ctask_cam, S.d_cam_t0, S.d_cam_cnt, S.d_cperm, nl, S.d_Jp,
+          S.d_F, S.d_Bc, S.d_w, S.d_T, S.d_taskpart, out, S.d_scal);
+    (void)check_done;
+    if (S.nempty) k_zero_cams<<<nblk((int64_t)S.nempty * nacc, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, nacc, out);
     int rc = check();
     if (rc) return rc;
     return allreduce_sum(h, out, (size_t)(ncams * nacc));
@@ -872,7 +957,7 @@ struct Solver {
   // block-Jacobi PCG on S dc = b; result in xc.  Convergence is decided on the device (S_DONE);
   // the host only polls every `poll` iterations, later launches of a finished solve exit at once.
   int pcg(double tol, int maxit, int* iters) {
-    k_pcg_init<<<1, RED_THREADS, 0, s>>>(n9, b, S.d_Minv, xc, r, z, p, S.d_scal);
+    k_pcg_cluster<true><<<PCG_CTAS, PCG_THREADS, 0, s>>>(ncams, b, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
     int rc = check();
     if (rc) return rc;
     const int poll = 8;
@@ -885,7 +970,7 @@ struct Solver {
               S.d_tstart, S.ntasks, h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_F, p, S.d_Vinv, S.d_gp, S.d_w,
               nullptr, nullptr, S.d_part, S.d_scal);
         if ((rc = cam_pass<2>(q, 1))) return rc;
-        k_pcg_update<<<1, RED_THREADS, 0, s>>>(n9, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
+        k_pcg_cluster<false><<<PCG_CTAS, PCG_THREADS, 0, s>>>(ncams, b, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
       }
       launched += chunk;
       if ((rc = check())) return rc;
