@@ -39,7 +39,8 @@ struct ba_lm_state {
   // ---- per observation ------------------------------------------------------------------------
   double2* d_Jp = nullptr;   // 12 planes x nl, point-major: plane j = (row1[j], row2[j]) of the 2x12 block
   double2* d_F = nullptr;    // nl residuals
-  double2* d_Bc = nullptr;   // 9 planes x nl, camera-major copy of the camera part
+  int32_t* d_pntc = nullptr; // nl: point id of the observation at each camera-major position
+  double2* d_x4 = nullptr;   // 2 x npnts: points of the current iterate padded to 32 bytes
   double2* d_w = nullptr;    // nl: per-observation 2-vector exchanged between the two passes
   double* d_T = nullptr;     // 3 planes x nl: A (V + lambda I)^-1 A^T (symmetric 2x2)
   double2* d_dr = nullptr;   // nl: -(J delta + r), only with linesearch (src/lm.jl:277-279)

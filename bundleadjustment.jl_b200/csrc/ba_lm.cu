@@ -10,15 +10,19 @@
 //     V_p = sum A'A (3x3)   U_c = sum B'B (9x9)   g_p = -sum A'F   g_c = -sum B'F
 //     S = U + lambda I - W (V + lambda I)^-1 W',   W_cp = B_k' A_k,   S dc = g_c - W (V+lI)^-1 g_p
 //     dp = (V + lambda I)^-1 (g_p - W' dc),        dr2 = 1/2 || J delta + r ||^2
-// S is never formed: S v is applied with two passes over the stored J blocks -- a point-major pass
-// (one warp per <=32 observations of whole points: y = B v_c, segmented warp sums per point,
-// u = (V+lI)^-1 sum A'y, w = A u) and a camera-major pass (out_c = (U+lI) v_c - sum B'w).  All
-// sums are two-level and ordered (per-task partials, then a fixed-order gather): results are
-// reproducible run to run and no FP64 atomics are used.  Everything is HBM-bound streaming work;
-// camera-sized vector updates of PCG run in one CTA so that its two dot products need no grid sync.
+// S is never formed: S v is applied with two passes -- a point-major pass over the stored J blocks (one
+// warp per <=32 observations of whole points: y = B v_c, segmented warp sums per point,
+// u = (V+lI)^-1 sum A'y, w = A u; 192 B/obs streamed, coalesced) and a camera-major pass that RECOMPUTES
+// the camera part of each block instead of keeping a second, camera-ordered copy of it
+// (out_c = (U+lI) v_c - sum B'w; the camera record is warp-uniform, points are gathered as one 32-byte
+// sector each; measured faster on B200 than streaming 144 B/obs, profiles/r01_pcg_*).  All sums are two-level and
+// ordered (per-task partials, then a fixed-order gather by the last task of a camera): results are
+// reproducible run to run and no FP64 atomics are used.  The camera-sized vector updates of PCG run
+// in one thread-block cluster so that its two dot products need no grid-wide synchronisation.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "ba_internal.h"
 #include <cooperative_groups.h>
@@ -76,7 +80,8 @@ k_reduce_parts(const double* __restrict__ part, int64_t nblocks, int K, double* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5a: evaluate F and the J blocks at x (thread per observation), store them point-major
+// K5a: evaluate F and the J blocks at x (thread per observation), store them point-major (12 planes of
+// (row1,row2) pairs); the camera-major passes recompute the camera part instead of reading a second copy
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PT_THREADS)
 k_lm_build(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
@@ -88,31 +93,33 @@ k_lm_build(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t k = blockIdx.x * (int64_t)PT_THREADS + threadIdx.x;
   const bool valid = k < nl;
-  int c = 0, p = 0;
-  double2 ob = make_double2(0.0, 0.0);
-  if (valid) {
-    c = __ldg(cam_idx + k);
-    p = __ldg(pnt_idx + k);
-    ob = __ldg(pt2d + k);
-  }
-  double X[3], cam[14];
-  const double* xp = xpts + (int64_t)p * 3;
-  X[0] = __ldg(xp);
-  X[1] = __ldg(xp + 1);
-  X[2] = __ldg(xp + 2);
-  double2* st = stage + warp * 32 * CAM_ROW2;
-  warp_stage_cams(camtab, c, lane, st);
-  read_staged_cam(st, lane, cam);
-  ObsBlock o;
-  eval_block(X, cam, ob.x, ob.y, o);
   double f2 = 0.0;
-  if (valid) {
+  if (k - lane < nl) {  // warps wholly past the end only take part in the block sum
+    int c = 0, p = 0;
+    double2 ob = make_double2(0.0, 0.0);
+    if (valid) {
+      c = __ldg(cam_idx + k);
+      p = __ldg(pnt_idx + k);
+      ob = __ldg(pt2d + k);
+    }
+    double X[3], cam[14];
+    const double* xp = xpts + (int64_t)p * 3;
+    X[0] = __ldg(xp);
+    X[1] = __ldg(xp + 1);
+    X[2] = __ldg(xp + 2);
+    double2* st = stage + warp * 32 * CAM_ROW2;
+    warp_stage_cams(camtab, c, lane, st);
+    read_staged_cam(st, lane, cam);
+    ObsBlock o;
+    eval_block(X, cam, ob.x, ob.y, o);
+    if (valid) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) Jp[(int64_t)j * nl + k] = make_double2(nan0(o.A[j]), nan0(o.A[3 + j]));
+      for (int j = 0; j < 3; ++j) Jp[(int64_t)j * nl + k] = make_double2(nan0(o.A[j]), nan0(o.A[3 + j]));
 #pragma unroll
-    for (int j = 0; j < 9; ++j) Jp[(int64_t)(3 + j) * nl + k] = make_double2(nan0(o.B[j]), nan0(o.B[9 + j]));
-    F[k] = make_double2(o.F[0], o.F[1]);
-    f2 = o.F[0] * o.F[0] + o.F[1] * o.F[1];
+      for (int j = 0; j < 9; ++j) Jp[(int64_t)(3 + j) * nl + k] = make_double2(nan0(o.B[j]), nan0(o.B[9 + j]));
+      F[k] = make_double2(o.F[0], o.F[1]);
+      f2 = o.F[0] * o.F[0] + o.F[1] * o.F[1];
+    }
   }
   f2 = block_sum<PT_THREADS>(f2, sh);
   if (threadIdx.x == 0) part[blockIdx.x] = f2;
@@ -128,23 +135,26 @@ k_lm_trial(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t k = blockIdx.x * (int64_t)PT_THREADS + threadIdx.x;
   const bool valid = k < nl;
-  int c = 0, p = 0;
-  double2 ob = make_double2(0.0, 0.0);
-  if (valid) {
-    c = __ldg(cam_idx + k);
-    p = __ldg(pnt_idx + k);
-    ob = __ldg(pt2d + k);
+  double f2 = 0.0;
+  if (k - lane < nl) {  // warps wholly past the end only take part in the block sum
+    int c = 0, p = 0;
+    double2 ob = make_double2(0.0, 0.0);
+    if (valid) {
+      c = __ldg(cam_idx + k);
+      p = __ldg(pnt_idx + k);
+      ob = __ldg(pt2d + k);
+    }
+    double X[3], cam[14], Fv[2];
+    const double* xp = xpts + (int64_t)p * 3;
+    X[0] = __ldg(xp);
+    X[1] = __ldg(xp + 1);
+    X[2] = __ldg(xp + 2);
+    double2* st = stage + warp * 32 * CAM_ROW2;
+    warp_stage_cams(camtab, c, lane, st);
+    read_staged_cam(st, lane, cam);
+    eval_residual(X, cam, ob.x, ob.y, Fv);
+    if (valid) f2 = Fv[0] * Fv[0] + Fv[1] * Fv[1];
   }
-  double X[3], cam[14], Fv[2];
-  const double* xp = xpts + (int64_t)p * 3;
-  X[0] = __ldg(xp);
-  X[1] = __ldg(xp + 1);
-  X[2] = __ldg(xp + 2);
-  double2* st = stage + warp * 32 * CAM_ROW2;
-  warp_stage_cams(camtab, c, lane, st);
-  read_staged_cam(st, lane, cam);
-  eval_residual(X, cam, ob.x, ob.y, Fv);
-  double f2 = valid ? Fv[0] * Fv[0] + Fv[1] * Fv[1] : 0.0;
   f2 = block_sum<PT_THREADS>(f2, sh);
   if (threadIdx.x == 0) part[blockIdx.x] = f2;
 }
@@ -227,7 +237,8 @@ k_point_prep(const int32_t* __restrict__ pnt_idx, int64_t pnt0, int64_t nl, cons
 
 // ---------------------------------------------------------------------------------------------
 // camera-major passes: one warp per task (a slice of one camera's observations)
-//   MODE 0: gather B, F by observation id, write the camera-major copy Bc, accumulate U and g_c
+// The camera record is warp-uniform; each lane recomputes the camera part B of its observation's block.
+//   MODE 0: accumulate U = B'B (45) and g_c = -B'F (9)
 //   MODE 1: accumulate B' T B (45) and B' w (9)         (Schur diagonal blocks, right-hand side)
 //   MODE 2: accumulate B' w (9)                         (Schur product)
 // ---------------------------------------------------------------------------------------------
@@ -235,48 +246,57 @@ template <int MODE>
 __global__ void __launch_bounds__(PT_THREADS)
 k_cam_pass(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, int64_t nctasks,
            const int32_t* __restrict__ task_cam, const int32_t* __restrict__ cam_t0, int32_t* __restrict__ cam_cnt,
-           const int32_t* __restrict__ cperm, int64_t nl, const double2* __restrict__ Jp,
-           const double2* __restrict__ F, double2* __restrict__ Bc, const double2* __restrict__ w,
-           const double* __restrict__ T, double* taskpart, double* __restrict__ out,
+           const int32_t* __restrict__ cperm, const int32_t* __restrict__ pntc, int64_t nl,
+           const double* __restrict__ camtab, const double2* __restrict__ x4, const double2* __restrict__ F,
+           const double2* __restrict__ w, const double* __restrict__ T, double* taskpart, double* __restrict__ out,
            const double* __restrict__ scal) {
   if (MODE == 2 && scal[S_DONE] != 0.0) return;
   constexpr int NACC = (MODE == 2) ? 9 : NV;
   const int lane = threadIdx.x & 31;
   const int64_t task = blockIdx.x * (int64_t)(PT_THREADS / 32) + (threadIdx.x >> 5);
   if (task >= nctasks) return;
+  const int c = task_cam[task];
+  double cam[14];
+  {
+    const double2* src = reinterpret_cast<const double2*>(camtab + (int64_t)c * CAM_REC);  // warp-uniform
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const double2 t = __ldg(src + i);
+      cam[2 * i] = t.x;
+      cam[2 * i + 1] = t.y;
+    }
+  }
   double acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
   const int e = tend[task];
   for (int pos = tbeg[task] + lane; pos < e; pos += 32) {
     const int k = __ldg(cperm + pos);
-    double2 B[9];
+    const int p = __ldg(pntc + pos);
+    const double2 xa = __ldg(x4 + 2 * (int64_t)p), xb = __ldg(x4 + 2 * (int64_t)p + 1);  // one 32-byte sector
+    double2 wk = make_double2(0.0, 0.0);
+    double t00 = 1.0, t01 = 0.0, t11 = 1.0;
     if (MODE == 0) {
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        B[j] = Jp[(int64_t)(3 + j) * nl + k];
-        Bc[(int64_t)j * nl + pos] = B[j];
-      }
+      const double2 f = F[k];
+      wk = make_double2(-f.x, -f.y);
     } else {
-#pragma unroll
-      for (int j = 0; j < 9; ++j) B[j] = Bc[(int64_t)j * nl + pos];
-    }
-    if (MODE == 2) {
-      const double2 wk = w[k];
-#pragma unroll
-      for (int j = 0; j < 9; ++j) acc[j] += B[j].x * wk.x + B[j].y * wk.y;
-    } else {
-      double2 v;  // 2-vector contracted into the last 9 accumulators
-      double t00 = 1.0, t01 = 0.0, t11 = 1.0;
-      if (MODE == 0) {
-        const double2 f = F[k];
-        v = make_double2(-f.x, -f.y);
-      } else {
-        v = w[k];
+      wk = w[k];
+      if (MODE == 1) {
         t00 = T[k];
         t01 = T[nl + k];
         t11 = T[2 * nl + k];
       }
+    }
+    const double X[3] = {xa.x, xa.y, xb.x};
+    ObsBlock o;
+    eval_block(X, cam, 0.0, 0.0, o);
+    double2 B[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) B[j] = make_double2(nan0(o.B[j]), nan0(o.B[9 + j]));
+    if (MODE == 2) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) acc[j] += B[j].x * wk.x + B[j].y * wk.y;
+    } else {
       int q = 0;
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
@@ -289,14 +309,13 @@ k_cam_pass(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, i
         }
       }
 #pragma unroll
-      for (int j = 0; j < 9; ++j) acc[45 + j] += B[j].x * v.x + B[j].y * v.y;
+      for (int j = 0; j < 9; ++j) acc[45 + j] += B[j].x * wk.x + B[j].y * wk.y;
     }
   }
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = warp_sum(acc[i]);
   // ordered two-level sum without a second kernel: the task that finishes last for its camera adds the
   // camera's task partials in task order (threadfence reduction; partials are read past L1)
-  const int c = task_cam[task];
   const int tb0 = cam_t0[c], nt = cam_t0[c + 1] - tb0;
   if (nt == 1) {
     if (lane == 0) {
@@ -322,6 +341,15 @@ k_cam_pass(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, i
     }
     if (lane == 0) cam_cnt[c] = 0;  // ready for the next pass (kernel boundaries order this)
   }
+}
+
+// x4[p] = (X_p, 0): one 32-byte sector per point for the random gathers of the camera-major passes
+__global__ void __launch_bounds__(256)
+k_pad_points(const double* __restrict__ x, int64_t p_lo, int64_t p_hi, double2* __restrict__ x4) {
+  const int64_t p = p_lo + blockIdx.x * (int64_t)256 + threadIdx.x;
+  if (p >= p_hi) return;
+  x4[2 * p] = make_double2(x[3 * p], x[3 * p + 1]);
+  x4[2 * p + 1] = make_double2(x[3 * p + 2], 0.0);
 }
 
 // cameras without observations on this rank: their sums are zero
@@ -837,7 +865,8 @@ int lm_prepare(ba_handle* h) {
   ALLOC(S.d_empty_cams, empty_cams.size());
   ALLOC(S.d_Jp, 12 * nl);
   ALLOC(S.d_F, nl);
-  ALLOC(S.d_Bc, 9 * nl);
+  ALLOC(S.d_pntc, nl);
+  ALLOC(S.d_x4, 2 * h->npnts);
   ALLOC(S.d_w, nl);
   ALLOC(S.d_T, 3 * nl);
   ALLOC(S.d_V, 6 * npl);
@@ -866,6 +895,9 @@ int lm_prepare(ba_handle* h) {
   BA_CUDA(up(S.d_tstart, tstart.data(), tstart.size() * 4));
   BA_CUDA(up(S.d_pstart, pstart.data(), pstart.size() * 4));
   BA_CUDA(up(S.d_cperm, cperm.data(), cperm.size() * 4));
+  std::vector<int32_t> pntc((size_t)nl);
+  for (int64_t i = 0; i < nl; ++i) pntc[(size_t)i] = h->h_pnt[(size_t)cperm[(size_t)i]];
+  BA_CUDA(up(S.d_pntc, pntc.data(), pntc.size() * 4));
   BA_CUDA(up(S.d_ctask_beg, tb.data(), tb.size() * 4));
   BA_CUDA(up(S.d_ctask_end, te.data(), te.size() * 4));
   BA_CUDA(up(S.d_cam_t0, cam_t0.data(), cam_t0.size() * 4));
@@ -881,7 +913,7 @@ int lm_prepare(ba_handle* h) {
 
 void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
-  void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_Bc,
+  void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,
                   S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
                   S.d_Minv, S.d_pcg, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
   for (void* p : ptrs) cudaFree(p);
@@ -903,22 +935,36 @@ struct Solver {
     nl = h->nobs_l(); npl = h->npnts_l(); ncams = h->ncams; n9 = 9 * ncams;
     b = S.d_pcg; xc = b + n9; r = xc + n9; z = r + n9; p = z + n9; q = p + n9;
   }
-  int check() {
-    BA_CUDA(cudaGetLastError());
+  // BAGPU_DEBUG_SYNC=1: synchronise before every check so that a faulting kernel is reported at the
+  // check that follows its launch (file:line in ba_last_error) instead of at the next host sync
+  int check_at(int line) {
+    static const bool dbg = getenv("BAGPU_DEBUG_SYNC") != nullptr;
+    cudaError_t e = dbg ? cudaStreamSynchronize(s) : cudaSuccess;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      char b_[256];
+      snprintf(b_, sizeof b_, "ba_lm.cu:%d: %s", line, cudaGetErrorString(e));
+      h->err = b_;
+      return BA_ERR_CUDA;
+    }
     return BA_OK;
   }
-  int reduce_to(int64_t nblocks, int K, int slot0) {
+#define check() check_at(__LINE__)
+  int reduce_to_at(int line, int64_t nblocks, int K, int slot0) {
+    int rc = check_at(line);  // the kernel that produced the partials
+    if (rc) return rc;
     k_reduce_parts<<<K, RED_THREADS, 0, s>>>(S.d_part, nblocks, K, S.d_scal, slot0);
-    return check();
+    return check_at(line);
   }
+#define reduce_to(...) reduce_to_at(__LINE__, __VA_ARGS__)
   // camera-major pass + ordered gather (+ allreduce over ranks) into out (ncams x nacc)
   template <int MODE>
   int cam_pass(double* out, int check_done) {
     constexpr int nacc = (MODE == 2) ? 9 : NV;
     if (S.nctasks)
       k_cam_pass<MODE><<<nblk(S.nctasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
-          S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_ctask_cam, S.d_cam_t0, S.d_cam_cnt, S.d_cperm, nl, S.d_Jp,
-          S.d_F, S.d_Bc, S.d_w, S.d_T, S.d_taskpart, out, S.d_scal);
+          S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_ctask_cam, S.d_cam_t0, S.d_cam_cnt, S.d_cperm, S.d_pntc, nl,
+          h->d_camtab, S.d_x4, S.d_F, S.d_w, S.d_T, S.d_taskpart, out, S.d_scal);
     (void)check_done;
     if (S.nempty) k_zero_cams<<<nblk((int64_t)S.nempty * nacc, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, nacc, out);
     int rc = check();
@@ -929,6 +975,10 @@ struct Solver {
   int build(const double* x) {
     launch_cam_precompute(x, h->npnts, ncams, h->d_camtab, s);
     const unsigned nb = nblk(nl, PT_THREADS), npb = nblk(npl, PT_THREADS);
+    int rc0 = check();
+    if (rc0) return rc0;
+    k_pad_points<<<nblk(npl, 256), 256, 0, s>>>(x, h->pnt0, h->pnt1, S.d_x4);
+    if ((rc0 = check())) return rc0;
     k_lm_build<<<nb, PT_THREADS, 0, s>>>(h->d_cam, h->d_pnt, h->d_pt2d, x, h->d_camtab, S.d_Jp, S.d_F, S.d_part, nl);
     int rc = reduce_to(nb, 1, S_F2);
     if (rc) return rc;
@@ -942,9 +992,10 @@ struct Solver {
   // everything that depends on lambda: Vinv, Schur diagonal blocks -> Minv, right-hand side b, H
   int factor(double lambda) {
     k_point_inv<<<nblk(npl, PT_THREADS), PT_THREADS, 0, s>>>(npl, lambda, S.d_V, S.d_gp, S.d_Vinv, S.d_wp);
-    k_point_prep<<<nblk(nl, PT_THREADS), PT_THREADS, 0, s>>>(h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_Vinv, S.d_wp, S.d_w, S.d_T);
     int rc = check();
     if (rc) return rc;
+    k_point_prep<<<nblk(nl, PT_THREADS), PT_THREADS, 0, s>>>(h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_Vinv, S.d_wp, S.d_w, S.d_T);
+    if ((rc = check())) return rc;
     if ((rc = cam_pass<1>(S.d_Cr, 0))) return rc;
     k_cam_finish<<<nblk(ncams, 64), 64, 0, s>>>(ncams, lambda, S.d_Ug, S.d_Cr, S.d_H, S.d_Minv, b, S.d_scal);
     return check();
@@ -969,6 +1020,7 @@ struct Solver {
           k_point_solve<0><<<nblk(S.ntasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
               S.d_tstart, S.ntasks, h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_F, p, S.d_Vinv, S.d_gp, S.d_w,
               nullptr, nullptr, S.d_part, S.d_scal);
+        if ((rc = check())) return rc;
         if ((rc = cam_pass<2>(q, 1))) return rc;
         k_pcg_cluster<false><<<PCG_CTAS, PCG_THREADS, 0, s>>>(ncams, b, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
       }

@@ -96,8 +96,17 @@ __device__ __forceinline__ void eval_residual(const double X[3], const double* _
 // Faithful dense path: reproduces the reference's NaN/Inf propagation through the dense
 // products (JP3*JP2)*JP1 including their structural zeros (src/BALNLPModels.jl:197).  Only taken
 // when the fast path produced a non-finite value, so its cost does not matter.
-static __device__ __noinline__ void eval_block_dense(const double X[3], const double* __restrict__ cam,
-                                              double ox, double oy, ObsBlock& o) {
+// Arguments and result travel by value (param space): no generic pointers into a caller's stack.
+struct DenseIn {
+  double X[3];
+  double cam[13];
+  double ox, oy;
+};
+static __device__ __noinline__ ObsBlock eval_block_dense(const DenseIn in) {
+  const double* X = in.X;
+  const double* cam = in.cam;
+  const double ox = in.ox, oy = in.oy;
+  ObsBlock o;
   const double kx = cam[CK0], ky = cam[CK1], kz = cam[CK2], c = cam[CC], s = cam[CS];
   const double a = cam[CA], g = cam[CG], b = 1.0 - a, omc = 1.0 - c;
   // R: the entries of JP1[1:3,1:3] (src/JacobianByHand.jl:38-40,45-47,52-54); N likewise
@@ -169,6 +178,7 @@ static __device__ __noinline__ void eval_block_dense(const double X[3], const do
   const double fs = f * ((1.0 + k1 * m2) + k2 * (m2 * m2));
   o.F[0] = fs * uu - ox;
   o.F[1] = fs * vv - oy;
+  return o;
 }
 
 // out = M^T v for M = alpha I + beta k k^T + gamma [k]x  (so M^T v = alpha v + beta (k.v) k - gamma k x v)
@@ -219,14 +229,13 @@ __device__ __forceinline__ void eval_block(const double X[3], const double* __re
 #pragma unroll
   for (int i = 0; i < 18; ++i) bad |= nonfinite(o.B[i]);
   if (bad) {
-    // copies keep X / cam / o of the fast path in registers: only these rare-path temporaries have
-    // their address taken (a direct call made every access of `o` a local-memory access)
-    double Xl[3] = {X[0], X[1], X[2]}, cl[13];
+    DenseIn in;
+    in.X[0] = X[0]; in.X[1] = X[1]; in.X[2] = X[2];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) cl[i] = cam[i];
-    ObsBlock t;
-    eval_block_dense(Xl, cl, ox, oy, t);
-    o = t;
+    for (int i = 0; i < 13; ++i) in.cam[i] = cam[i];
+    in.ox = ox;
+    in.oy = oy;
+    o = eval_block_dense(in);
   }
 }
 
