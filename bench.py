@@ -188,12 +188,12 @@ def main():
         if rc:
             ba._lib.check(rc, h)
 
-    for i in range(max(args.warmup, 3)):
-        dev_step(i)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(max(args.warmup, 3)):
+        dev_step(i)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -217,7 +217,6 @@ def main():
         ks.append(f.value)
     barrier()
     k_ms = float(np.mean(ks))
-    clocks = sampler.summary() if rank == 0 else None
 
     # ---- end-to-end leg through the host-pointer call (what Julia's ccall hits) -------------------------
     def pinned(nbytes):
@@ -247,16 +246,7 @@ def main():
     # ---- LM leg: full Levenberg-Marquardt iterations per second on the same problem ----------------------
     lm = None
     if args.lm_iters > 0:
-        if world > 1:
-            uid = torch.zeros(128, dtype=torch.uint8)
-            if rank == 0:
-                buf = (C.c_uint8 * 128)()
-                ba._lib.check(L.ba_comm_unique_id(buf))
-                uid = torch.tensor(list(buf), dtype=torch.uint8)
-            uid = uid.cuda()
-            dist.broadcast(uid, 0)
-            arr = (C.c_uint8 * 128)(*uid.cpu().tolist())
-            ba._lib.check(L.ba_comm_init(h, arr), h)
+        ba.init_comm(m)
         barrier()
         t0 = time.perf_counter()
         st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=args.lm_iters - 1,
@@ -272,6 +262,7 @@ def main():
               "e2e": "x0 host -> solution host through Levenberg_Marquardt()"}
 
     if rank == 0:
+        clocks = sampler.summary()  # sampled every 100 ms from warm-up to the end of the last leg
         peak, peak_src = measured_peak()
         bpo = algorithmic_bytes_per_obs(p)
         # per-launch algorithmic bytes of the dominant kernel on one rank (rank 0's shard)

@@ -10,6 +10,7 @@ from ._lib import BAError
 from .model import BALNLPModel, FeasibilityResidual, NLPModelMeta, Counters, name
 from .lm import Levenberg_Marquardt, GenericExecutionStats, default_params, lm_step
 from . import synth
+from .dist import init_comm
 
 __all__ = ["BALNLPModel", "FeasibilityResidual", "NLPModelMeta", "Counters", "name", "Levenberg_Marquardt",
-           "GenericExecutionStats", "default_params", "lm_step", "BAError", "synth"]
+           "GenericExecutionStats", "default_params", "lm_step", "BAError", "synth", "init_comm"]

@@ -1,0 +1,30 @@
+"""One-process-per-GPU plumbing: torch.distributed carries the NCCL unique id of libbagpu's own
+communicator (ba_comm_unique_id / ba_comm_init); the data path never goes through torch."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib
+
+
+def init_comm(model, group=None):
+    """Create the NCCL communicator of a sharded BALNLPModel.  Needs an initialised torch.distributed
+    process group (any backend) whose ranks match model.rank / model.nranks."""
+    import torch
+    import torch.distributed as dist
+    if model.nranks == 1:
+        return
+    if not dist.is_initialized():
+        raise RuntimeError("init_comm needs torch.distributed to be initialised")
+    if dist.get_world_size(group) != model.nranks or dist.get_rank(group) != model.rank:
+        raise ValueError("process group does not match the model's rank/nranks")
+    L = _lib.lib()
+    buf = (C.c_uint8 * 128)()
+    if model.rank == 0:
+        _lib.check(L.ba_comm_unique_id(buf))
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda(model.device)
+    dist.broadcast(t, 0, group=group)
+    arr = (C.c_uint8 * 128)(*t.cpu().tolist())
+    _lib.check(L.ba_comm_init(model.handle, arr), model.handle)
