@@ -188,3 +188,19 @@ def test_venice_shape_properties(ba, oracle):
     vc = v[3 * p.npnts:].reshape(-1, 9)[p.cam_idx - 1]
     Jv2 = np.einsum("kij,kj->ki", V[:, :, :3], vp) + np.einsum("kij,kj->ki", V[:, :, 3:], vc)
     assert_rel(Jv, Jv2.ravel(), TOL, what="jprod vs vals")
+
+
+def test_model_from_bal_file(ba, oracle, tmp_path):
+    # BALNLPModel(filename) (src/BALNLPModels.jl:91-106) through the BAL reader (src/ReadFiles.jl:9-53)
+    from bundleadjustment.jl_b200 import balio
+    p = small_problem(ba)
+    d = tmp_path / "Synth"
+    d.mkdir()
+    f = d / ("problem-%d-%d-pre.txt.bz2" % (p.ncams, p.npnts))
+    balio.write_problem(str(f), p)
+    m = ba.BALNLPModel.from_file(str(f))
+    assert m.meta.name == "Synth-%d-%d" % (p.ncams, p.npnts)            # name(), src/BALNLPModels.jl:58-68
+    assert (m.meta.nvar, m.meta.ncon, m.meta.nnzj) == (p.nvar, 2 * p.nobs, 24 * p.nobs)
+    assert np.array_equal(m.meta.x0, p.x0)
+    assert_rel(m.cons(m.meta.x0), oracle.cons(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.npnts), TOL,
+               scale=np.abs(p.pt2d).max())
