@@ -126,9 +126,14 @@ def cpu_baseline(p, workload, budget_s=12.0):
         if time.perf_counter() - t0 > budget_s or reps >= 50:
             break
     dt = (time.perf_counter() - t0) / reps
+    n1 = min(p.nobs, 1_000_000)  # single-thread figure on a 1M-observation prefix of the same problem
+    t1 = time.perf_counter()
+    O.cons_jac(p.cam_idx[:n1], p.pnt_idx[:n1], p.pt2d[:2 * n1], p.x0, p.npnts, 1, cx[:2 * n1], vals[:24 * n1])
+    dt1 = time.perf_counter() - t1
     return {"value": p.nobs / dt / 1e6, "unit": UNIT, "cores": nt, "kind": "port",
             "sample": "%d full passes of the %s problem (cons! + jac_coord!, all %d threads for both)"
-                      % (reps, workload, nt)}
+                      % (reps, workload, nt),
+            "single_thread_value": n1 / dt1 / 1e6}
 
 
 def main():
@@ -170,7 +175,10 @@ def main():
                        device=local, rank=rank, nranks=world)
     h = m.handle
     nl = m.nobs_local
-    stream = torch.cuda.current_stream()
+    # a side stream (the legacy default stream cannot be captured into the CUDA graph the PCG loop uses);
+    # every torch.cuda.Event below is recorded on it, and the library launches on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ba._lib.check(L.ba_set_stream(h, C.c_void_p(stream.cuda_stream)), h)
 
     # ---- device-resident leg ---------------------------------------------------------------------
@@ -217,6 +225,20 @@ def main():
         ks.append(f.value)
     barrier()
     k_ms = float(np.mean(ks))
+
+    # ---- jac_structure! once (src/lm.jl:53 calls it once per solve): write-only 384 B per observation -----------
+    rows_d = torch.empty(24 * nl, dtype=torch.int64, device="cuda")
+    cols_d = torch.empty(24 * nl, dtype=torch.int64, device="cuda")
+    ba._lib.check(L.ba_jac_structure_dev(h, C.c_void_p(rows_d.data_ptr()), C.c_void_p(cols_d.data_ptr())), h)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(5):
+        ba._lib.check(L.ba_jac_structure_dev(h, C.c_void_p(rows_d.data_ptr()), C.c_void_p(cols_d.data_ptr())), h)
+    s1.record()
+    barrier()
+    js_ms = s0.elapsed_time(s1) / 5
+    del rows_d, cols_d
 
     # ---- end-to-end leg through the host-pointer call (what Julia's ccall hits) -------------------------
     def pinned(nbytes):
@@ -283,6 +305,8 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "kernel_ms": k_ms, "bytes_per_obs": bpo, "frac_of_nominal_8TBs": achieved / 8000.0},
             "clocks": clocks,
+            "jac_structure": {"ms": js_ms, "GB/s": 392.0 * nl / (js_ms * 1e-3) / 1e9,
+                              "bytes_per_obs": 392, "note": "rank 0 shard; 2 x 24 Int64 written + 8 B of indices read"},
         }
         if lm:
             out["lm"] = lm

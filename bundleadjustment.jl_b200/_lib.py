@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbagpu.so")
+LIB_PATH = os.environ.get("BAGPU_LIB", os.path.join(HERE, "libbagpu.so"))  # BAGPU_LIB: A/B builds
 
 BA_OK, BA_ERR_ARG, BA_ERR_CUDA, BA_ERR_UNSORTED, BA_ERR_COMM, BA_ERR_NUMERIC = range(6)
 _CODE = {1: "bad argument", 2: "CUDA failure", 3: "observations not point-major", 4: "NCCL failure",

@@ -11,10 +11,10 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libbagpu.so")
+LIB = os.path.join(HERE, os.environ.get("BAGPU_LIB_NAME", "libbagpu.so"))  # override: A/B builds
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "--fmad=true", "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-Xptxas", "-v", "-shared"]
+         "--fmad=true"] + os.environ.get("BAGPU_EXTRA_NVCC", "").split() + [ "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-Xptxas", "-v", "-shared"]
 
 
 def sources():

@@ -153,6 +153,9 @@ int ba_set_stream(ba_handle* h, void* s) {
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   h->stream = reinterpret_cast<cudaStream_t>(s);
   h->own_stream = false;
+  if (h->lm.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(h->lm.pcg_graph));
+  h->lm.pcg_graph = nullptr;  // captured on the old stream's work; re-captured on first use
+  h->lm.pcg_graph_off = false;
   return BA_OK;
 }
 

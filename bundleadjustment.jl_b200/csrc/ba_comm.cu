@@ -100,7 +100,16 @@ int ba_comm_init(ba_handle* h, const uint8_t id128[128]) {
     h->comm = nullptr;
     return BA_ERR_COMM;
   }
-  return BA_OK;
+  // NCCL sets its channels up lazily inside the first collective (hundreds of ms): pay that here, not in
+  // the first LM iteration
+  double* warm = nullptr;
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&warm), 1024 * sizeof(double)));
+  BA_CUDA(cudaMemsetAsync(warm, 0, 1024 * sizeof(double), h->stream));
+  int wrc = ba::allreduce_sum(h, warm, 1024);
+  if (!wrc) wrc = ba::allreduce_sum(h, warm, 8);
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(warm);
+  return wrc;
 }
 
 }  // extern "C"

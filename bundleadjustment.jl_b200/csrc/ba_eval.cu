@@ -17,6 +17,9 @@
 
 namespace ba {
 
+#ifndef EVAL_MINBLOCKS
+#define EVAL_MINBLOCKS 5  // resident blocks per SM the register allocation targets (A/B-tested)
+#endif
 constexpr int EVAL_THREADS = 128;           // 4 warps
 constexpr int STAGE_ROW = 13;               // double2 per staged observation (12 + 1 pad: odd stride,
                                             // conflict-free 16-byte shared stores and loads)
@@ -45,7 +48,7 @@ __device__ __forceinline__ void load_cam(const double* __restrict__ camtab, int 
 }
 
 template <bool WCX, bool WVALS>
-__global__ void __launch_bounds__(EVAL_THREADS)
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MINBLOCKS)
 k_eval(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
        const double2* __restrict__ pt2d, const double* __restrict__ xpts,
        const double* __restrict__ camtab, double* __restrict__ cx, double* __restrict__ vals,

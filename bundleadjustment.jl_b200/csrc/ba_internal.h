@@ -66,6 +66,9 @@ struct ba_lm_state {
   int64_t npart = 0;
   double* d_scal = nullptr;   // device scalars (layout in ba_lm.cu)
   double* h_scal = nullptr;   // pinned mirror
+  void* pcg_graph = nullptr;  // cudaGraphExec_t: PCG_POLL iterations captured once (ba_lm.cu)
+  double pcg_graph_tol = 0.0;
+  bool pcg_graph_off = false;  // capture not possible on this stream
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

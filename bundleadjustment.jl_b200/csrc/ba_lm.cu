@@ -918,6 +918,7 @@ void lm_release(ba_handle* h) {
                   S.d_Minv, S.d_pcg, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
   for (void* p : ptrs) cudaFree(p);
   if (S.h_scal) cudaFreeHost(S.h_scal);
+  if (S.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph));
   for (auto& e : S.ev)
     if (e) cudaEventDestroy(e);
   S = ba_lm_state();
@@ -1005,24 +1006,61 @@ struct Solver {
     BA_CUDA(cudaStreamSynchronize(s));
     return BA_OK;
   }
-  // block-Jacobi PCG on S dc = b; result in xc.  Convergence is decided on the device (S_DONE);
-  // the host only polls every `poll` iterations, later launches of a finished solve exit at once.
+  // one PCG iteration: point-major pass, camera-major pass (+ allreduce over ranks), cluster update
+  int pcg_iteration(double tol, bool checks) {
+    int rc;
+    if (S.ntasks)
+      k_point_solve<0><<<nblk(S.ntasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
+          S.d_tstart, S.ntasks, h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_F, p, S.d_Vinv, S.d_gp, S.d_w,
+          nullptr, nullptr, S.d_part, S.d_scal);
+    if (checks && (rc = check())) return rc;
+    if (S.nctasks)
+      k_cam_pass<2><<<nblk(S.nctasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
+          S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_ctask_cam, S.d_cam_t0, S.d_cam_cnt, S.d_cperm, S.d_pntc, nl,
+          h->d_camtab, S.d_x4, S.d_F, S.d_w, S.d_T, S.d_taskpart, q, S.d_scal);
+    if (S.nempty) k_zero_cams<<<nblk((int64_t)S.nempty * 9, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, 9, q);
+    if (checks && (rc = check())) return rc;
+    if ((rc = allreduce_sum(h, q, (size_t)n9))) return rc;
+    k_pcg_cluster<false><<<PCG_CTAS, PCG_THREADS, 0, s>>>(ncams, b, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
+    return checks ? check() : BA_OK;
+  }
+  // block-Jacobi PCG on S dc = b; result in xc.  Convergence is decided on the device (S_DONE): the host
+  // only polls every PCG_POLL iterations, and those iterations are ONE CUDA-graph launch (the 3 kernels
+  // and the NCCL allreduce of each iteration captured once per handle); launches of a finished solve exit
+  // at once.  BAGPU_NO_GRAPH=1 or BAGPU_DEBUG_SYNC=1 fall back to plain launches.
   int pcg(double tol, int maxit, int* iters) {
+    constexpr int PCG_POLL = 8;
+    static const bool no_graph = getenv("BAGPU_NO_GRAPH") != nullptr || getenv("BAGPU_DEBUG_SYNC") != nullptr;
     k_pcg_cluster<true><<<PCG_CTAS, PCG_THREADS, 0, s>>>(ncams, b, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
     int rc = check();
     if (rc) return rc;
-    const int poll = 8;
+    if (!no_graph && !S.pcg_graph_off && (!S.pcg_graph || S.pcg_graph_tol != tol)) {
+      if (S.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph));
+      S.pcg_graph = nullptr;
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();      // e.g. the handle runs on the legacy default stream, which cannot be captured
+        S.pcg_graph_off = true;  // plain launches from now on
+      } else {
+        for (int i = 0; i < PCG_POLL && !rc; ++i) rc = pcg_iteration(tol, false);
+        const cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc) return rc;
+        BA_CUDA(e);
+        cudaGraphExec_t ge = nullptr;
+        BA_CUDA(cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+        S.pcg_graph = ge;
+        S.pcg_graph_tol = tol;
+      }
+    }
     int launched = 0;
     for (;;) {
-      const int chunk = std::min(poll, maxit - launched);
-      for (int i = 0; i < chunk; ++i) {
-        if (S.ntasks)
-          k_point_solve<0><<<nblk(S.ntasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
-              S.d_tstart, S.ntasks, h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_F, p, S.d_Vinv, S.d_gp, S.d_w,
-              nullptr, nullptr, S.d_part, S.d_scal);
-        if ((rc = check())) return rc;
-        if ((rc = cam_pass<2>(q, 1))) return rc;
-        k_pcg_cluster<false><<<PCG_CTAS, PCG_THREADS, 0, s>>>(ncams, b, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
+      const int chunk = std::min(PCG_POLL, maxit - launched);
+      if (chunk == PCG_POLL && S.pcg_graph) {
+        BA_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph), s));
+      } else {
+        for (int i = 0; i < chunk; ++i)
+          if ((rc = pcg_iteration(tol, true))) return rc;
       }
       launched += chunk;
       if ((rc = check())) return rc;
