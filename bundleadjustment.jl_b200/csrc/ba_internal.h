@@ -56,6 +56,7 @@ struct ba_lm_state {
   double* d_H = nullptr;     // ncams x 81: U + lambda I
   double* d_Minv = nullptr;  // ncams x 81: inverse Schur diagonal block (block-Jacobi preconditioner)
   double* d_pcg = nullptr;   // 6 vectors of 9 ncams: b, xc, r, z, p, q
+  double* d_pcgpart = nullptr;  // per-CTA partials of the two PCG dot products
   // ---- iterates -------------------------------------------------------------------------------
   double* d_x = nullptr;      // current iterate (nvar; only this rank's point slice + cameras are live)
   double* d_xt = nullptr;     // trial iterate

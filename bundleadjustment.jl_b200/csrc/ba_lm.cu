@@ -17,18 +17,16 @@
 // (out_c = (U+lI) v_c - sum B'w; the camera record is warp-uniform, points are gathered as one 32-byte
 // sector each; measured faster on B200 than streaming 144 B/obs, profiles/r01_pcg_*).  All sums are two-level and
 // ordered (per-task partials, then a fixed-order gather by the last task of a camera): results are
-// reproducible run to run and no FP64 atomics are used.  The camera-sized vector updates of PCG run
-// in one thread-block cluster so that its two dot products need no grid-wide synchronisation.
+// reproducible run to run and no FP64 atomics are used.  The camera-sized vector updates of PCG are
+// three small multi-CTA kernels; its dot products are per-CTA partials summed in fixed order.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include "ba_internal.h"
-#include <cooperative_groups.h>
 #include "ba_math.cuh"
 
-namespace cg = cooperative_groups;
 
 namespace ba {
 
@@ -48,7 +46,7 @@ enum {
   S_GC2 = 8,  // sum g_c^2 (cameras are replicated)
   S_DC2,      // sum delta_c^2
   S_XC2,      // sum (x + delta)_c^2
-  S_RZ = 16, S_RZ0, S_PQ, S_DONE, S_ITERS, S_REL, S_ERR,
+  S_RZ = 16, S_RZ0, S_PQ, S_DONE, S_ITERS, S_REL, S_ERR, S_RZN,
   S_COUNT = 32
 };
 
@@ -654,15 +652,17 @@ k_ls_dr(double2* __restrict__ dr, const double2* __restrict__ F, int64_t nl, dou
 }
 
 // ---------------------------------------------------------------------------------------------
-// PCG on the reduced camera system: the camera-sized vector work of one iteration runs as ONE
-// thread-block cluster (8 CTAs on 8 SMs of one GPC).  The two dot products of the iteration are
-// block sums combined through distributed shared memory between cluster barriers, in rank order,
-// so no grid-wide synchronisation, no atomics and no host round trip are needed and the result is
-// reproducible.  Cameras are dealt to CTAs in contiguous ranges: the 9 rows of a camera live in
-// one CTA, so the r -> z = Minv r dependency needs only __syncthreads.
+// PCG on the reduced camera system: camera-sized vector work.  One iteration needs two global dot
+// products (p.Sp and r.z) with vector updates between them; they run as three small multi-CTA
+// kernels whose dot products are per-CTA partials summed in fixed order by every CTA of the next
+// kernel (reproducible, no atomics, no host round trip; alpha, beta and the convergence flag live on
+// the device).  A CTA owns whole cameras (28 cameras = 252 rows), so z = Minv r needs only
+// __syncthreads.  [A single 8-CTA thread-block cluster with DSMEM reductions did the same work in
+// 27 us on Venice (latency-bound: 4 dependent passes over 2.3 MB from 8 SMs) and does not scale to
+// 13682 cameras; this version spreads the matrix reads over all SMs: profiles/r01_pcg_vector_*.]
 // ---------------------------------------------------------------------------------------------
-constexpr int PCG_CTAS = 8;
-constexpr int PCG_THREADS = 512;
+constexpr int VEC_THREADS = 256;
+constexpr int VEC_ROWS = 252;  // 28 cameras x 9 rows per CTA
 
 __device__ __forceinline__ double row9(const double* __restrict__ M, const double* v, int64_t i) {
   const int64_t c = i / 9;
@@ -674,97 +674,112 @@ __device__ __forceinline__ double row9(const double* __restrict__ M, const doubl
   return s;
 }
 
-// sum over the cluster of one value per CTA, every CTA obtains the same total (rank order)
-__device__ __forceinline__ double cluster_sum(cg::cluster_group& cluster, double v, double* sh, double* slot) {
-  v = block_sum<PCG_THREADS>(v, sh);
-  if (threadIdx.x == 0) *slot = v;
-  cluster.sync();
-  double t = 0.0;
-#pragma unroll
-  for (int r = 0; r < PCG_CTAS; ++r) t += *cluster.map_shared_rank(slot, r);
-  return t;
+// the same total in every thread of every CTA: partials are added in index order
+__device__ __forceinline__ double sum_partials(const double* part, int n, double* sh) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += VEC_THREADS) s += part[i];
+  return block_sum<VEC_THREADS>(s, sh);
 }
 
-// INIT: r = b, xc = 0, z = Minv r, p = z, rz0 = r.z.   Otherwise one PCG iteration: on entry q holds
-// sum_k B'w (allreduced over ranks in sharded mode); q = (U + lambda I) p - q = S p; alpha, xc, r, z, beta, p.
+// K7c: on entry q holds sum_k B'w (allreduced over ranks in sharded mode); q = (U + lambda I) p - q = S p,
+// per-CTA partials of p.q.  Also publishes the r.z of the previous iteration as the current one.
+__global__ void __launch_bounds__(VEC_THREADS)
+k_pcg_q(int64_t n9, const double* __restrict__ H, const double* p, double* q, double* __restrict__ part_pq,
+        double* scal) {
+  __shared__ double sh[VEC_THREADS / 32];
+  if (scal[S_DONE] != 0.0) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_RZ] = scal[S_RZN];
+  const int64_t i = blockIdx.x * (int64_t)VEC_ROWS + threadIdx.x;
+  double pq = 0.0;
+  if (threadIdx.x < VEC_ROWS && i < n9) {
+    const double qi = row9(H, p, i) - q[i];
+    q[i] = qi;
+    pq = p[i] * qi;
+  }
+  pq = block_sum<VEC_THREADS>(pq, sh);
+  if (threadIdx.x == 0) part_pq[blockIdx.x] = pq;
+}
+
+// K7d: alpha = r.z / p.q; xc += alpha p; r -= alpha q; z = Minv r; per-CTA partials of r.z.
+// INIT: r = b, xc = 0 instead of the update.
 template <bool INIT>
-__global__ void __cluster_dims__(PCG_CTAS, 1, 1) __launch_bounds__(PCG_THREADS)
-k_pcg_cluster(int64_t ncams, const double* __restrict__ b, const double* __restrict__ H,
-              const double* __restrict__ Minv, double* q, double* xc, double* r, double* z, double* p,
-              double* scal, double tol) {
-  __shared__ double sh[PCG_THREADS / 32];
-  __shared__ double slots[2];
-  cg::cluster_group cluster = cg::this_cluster();
-  if (!INIT && scal[S_DONE] != 0.0) return;  // uniform over the cluster: written by an earlier kernel
-  const int rank = (int)cluster.block_rank();
-  const int64_t per = (ncams + PCG_CTAS - 1) / PCG_CTAS;
-  const int64_t i0 = min((long long)(rank * per), (long long)ncams) * 9,
-                i1 = min((long long)((rank + 1) * per), (long long)ncams) * 9;
+__global__ void __launch_bounds__(VEC_THREADS)
+k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __restrict__ Minv, const double* p,
+         const double* q, double* xc, double* r, double* z, const double* part_pq, double* __restrict__ part_rz,
+         const double* scal) {
+  __shared__ double sh[VEC_THREADS / 32];
+  const int64_t i = blockIdx.x * (int64_t)VEC_ROWS + threadIdx.x;
+  const bool live = threadIdx.x < VEC_ROWS && i < n9;
   if (INIT) {
-    for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
+    if (live) {
       r[i] = b[i];
       xc[i] = 0.0;
     }
-    __syncthreads();
-    double rz = 0.0;
-    for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
-      const double zi = row9(Minv, r, i);
-      z[i] = zi;
-      p[i] = zi;
-      rz += r[i] * zi;
+  } else {
+    if (scal[S_DONE] != 0.0) return;
+    const double pq = sum_partials(part_pq, nparts, sh);
+    if (!(pq > 0.0)) return;  // breakdown: flagged by k_pcg_p
+    const double alpha = scal[S_RZ] / pq;
+    if (live) {
+      xc[i] += alpha * p[i];
+      r[i] -= alpha * q[i];
     }
-    rz = cluster_sum(cluster, rz, sh, &slots[0]);
-    if (rank == 0 && threadIdx.x == 0) {
-      scal[S_RZ] = rz;
+  }
+  __syncthreads();
+  double rz = 0.0;
+  if (live) {
+    const double zi = row9(Minv, r, i);
+    z[i] = zi;
+    rz = r[i] * zi;
+  }
+  rz = block_sum<VEC_THREADS>(rz, sh);
+  if (threadIdx.x == 0) part_rz[blockIdx.x] = rz;
+}
+
+// K7e: beta = r.z(new) / r.z(old); p = z + beta p; iteration count and convergence flag.
+// INIT: p = z, r0.z0.
+template <bool INIT>
+__global__ void __launch_bounds__(VEC_THREADS)
+k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_pq, const double* part_rz,
+        double* scal, double tol) {
+  __shared__ double sh[VEC_THREADS / 32];
+  const int64_t i = blockIdx.x * (int64_t)VEC_ROWS + threadIdx.x;
+  const bool live = threadIdx.x < VEC_ROWS && i < n9;
+  const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+  if (INIT) {
+    const double rz = sum_partials(part_rz, nparts, sh);
+    if (live) p[i] = z[i];
+    if (lead) {
+      scal[S_RZN] = rz;
       scal[S_RZ0] = rz;
       scal[S_ITERS] = 0.0;
       scal[S_REL] = 1.0;
       // zero right-hand side: the zero step is the solution; NaN: let the caller see it
       scal[S_DONE] = (rz == 0.0) ? 1.0 : ((rz == rz) ? 0.0 : 2.0);
     }
-    cluster.sync();  // nobody leaves while its shared memory may still be read
     return;
   }
-  const double rz = scal[S_RZ], rz0 = scal[S_RZ0];
-  double pq = 0.0;
-  for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
-    const double qi = row9(H, p, i) - q[i];
-    q[i] = qi;
-    pq += p[i] * qi;
-  }
-  pq = cluster_sum(cluster, pq, sh, &slots[0]);
+  if (scal[S_DONE] != 0.0) return;  // (a CTA that starts after the lead thread flagged convergence may skip
+                                    //  its slice of p: p is dead once the solve is done)
+  const double pq = sum_partials(part_pq, nparts, sh);
   if (!(pq > 0.0)) {  // breakdown: S is SPD in exact arithmetic, so this is NaN/Inf or lost definiteness
-    if (rank == 0 && threadIdx.x == 0) {
+    if (lead) {
       scal[S_DONE] = 2.0;
       scal[S_PQ] = pq;
     }
-    cluster.sync();
     return;
   }
-  const double alpha = rz / pq;
-  for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
-    xc[i] += alpha * p[i];
-    r[i] -= alpha * q[i];
-  }
-  __syncthreads();
-  double rzn = 0.0;
-  for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) {
-    const double zi = row9(Minv, r, i);
-    z[i] = zi;
-    rzn += r[i] * zi;
-  }
-  rzn = cluster_sum(cluster, rzn, sh, &slots[1]);
-  const double beta = rzn / rz;
-  for (int64_t i = i0 + threadIdx.x; i < i1; i += PCG_THREADS) p[i] = z[i] + beta * p[i];
-  if (rank == 0 && threadIdx.x == 0) {
-    const double rel = sqrt(rzn / rz0);
-    scal[S_RZ] = rzn;
+  const double rzn = sum_partials(part_rz, nparts, sh);
+  const double beta = rzn / scal[S_RZ];
+  if (live) p[i] = z[i] + beta * p[i];
+  if (lead) {
+    const double rel = sqrt(rzn / scal[S_RZ0]);
+    scal[S_RZN] = rzn;
     scal[S_PQ] = pq;
     scal[S_ITERS] += 1.0;
     scal[S_REL] = rel;
     if (!(rel > tol)) scal[S_DONE] = (rel == rel) ? 1.0 : 2.0;
   }
-  cluster.sync();
 }
 
 __global__ void k_copy_cam_delta(int64_t n9, const double* __restrict__ xc, double* __restrict__ delta_c) {
@@ -879,6 +894,7 @@ int lm_prepare(ba_handle* h) {
   ALLOC(S.d_H, ncams * 81);
   ALLOC(S.d_Minv, ncams * 81);
   ALLOC(S.d_pcg, 6 * 9 * ncams);
+  ALLOC(S.d_pcgpart, 2 * (int64_t)nblk(9 * ncams, VEC_ROWS));
   ALLOC(S.d_x, h->nvar());
   ALLOC(S.d_xt, h->nvar());
   ALLOC(S.d_delta, h->nvar());
@@ -915,7 +931,7 @@ void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,
                   S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
-                  S.d_Minv, S.d_pcg, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
+                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
   for (void* p : ptrs) cudaFree(p);
   if (S.h_scal) cudaFreeHost(S.h_scal);
   if (S.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph));
@@ -1021,7 +1037,12 @@ struct Solver {
     if (S.nempty) k_zero_cams<<<nblk((int64_t)S.nempty * 9, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, 9, q);
     if (checks && (rc = check())) return rc;
     if ((rc = allreduce_sum(h, q, (size_t)n9))) return rc;
-    k_pcg_cluster<false><<<PCG_CTAS, PCG_THREADS, 0, s>>>(ncams, b, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
+    const int nvb = (int)nblk(n9, VEC_ROWS);
+    double* ppq = S.d_pcgpart;
+    double* prz = S.d_pcgpart + nvb;
+    k_pcg_q<<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, ppq, S.d_scal);
+    k_pcg_xr<false><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, b, S.d_Minv, p, q, xc, r, z, ppq, prz, S.d_scal);
+    k_pcg_p<false><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol);
     return checks ? check() : BA_OK;
   }
   // block-Jacobi PCG on S dc = b; result in xc.  Convergence is decided on the device (S_DONE): the host
@@ -1031,7 +1052,13 @@ struct Solver {
   int pcg(double tol, int maxit, int* iters) {
     constexpr int PCG_POLL = 8;
     static const bool no_graph = getenv("BAGPU_NO_GRAPH") != nullptr || getenv("BAGPU_DEBUG_SYNC") != nullptr;
-    k_pcg_cluster<true><<<PCG_CTAS, PCG_THREADS, 0, s>>>(ncams, b, S.d_H, S.d_Minv, q, xc, r, z, p, S.d_scal, tol);
+    {
+      const int nvb = (int)nblk(n9, VEC_ROWS);
+      double* ppq = S.d_pcgpart;
+      double* prz = S.d_pcgpart + nvb;
+      k_pcg_xr<true><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, b, S.d_Minv, p, q, xc, r, z, ppq, prz, S.d_scal);
+      k_pcg_p<true><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol);
+    }
     int rc = check();
     if (rc) return rc;
     if (!no_graph && !S.pcg_graph_off && (!S.pcg_graph || S.pcg_graph_tol != tol)) {
