@@ -35,6 +35,19 @@ def algorithmic_bytes_per_obs(p) -> float:
     return 232.0 + 8.0 * p.nvar / p.nobs
 
 
+def measured_traffic(workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+    (profiles/k_eval_traffic.json); only valid for the configuration it was captured on."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k_eval_traffic.json")) as f:
+            t = json.load(f)
+        if t["workload"] == workload and t["n_gpus"] == world:
+            return t["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -218,12 +231,14 @@ def main():
     # dominant kernel alone (k_eval<cx,vals>): the library brackets that launch with its own CUDA events
     # on the launching stream; read them step by step (same rotating buffers)
     ks = []
+    ba._lib.check(L.ba_set_profiling(h, 1), h)
     for i in range(args.steps):
         dev_step(i)
         f = C.c_float()
         ba._lib.check(L.ba_last_eval_ms(h, C.byref(f)), h)
         ks.append(f.value)
     barrier()
+    ba._lib.check(L.ba_set_profiling(h, 0), h)
     k_ms = float(np.mean(ks))
 
     # ---- jac_structure! once (src/lm.jl:53 calls it once per solve): write-only 384 B per observation -----------
@@ -302,7 +317,9 @@ def main():
                     "api": "ba_residual_jac (host pointers, pinned), per rank"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "ba::k_eval<true,true>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, world),
+                         "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bpo * nl,
                          "kernel_ms": k_ms, "bytes_per_obs": bpo, "frac_of_nominal_8TBs": achieved / 8000.0},
             "clocks": clocks,
             "jac_structure": {"ms": js_ms, "GB/s": 392.0 * nl / (js_ms * 1e-3) / 1e9,

@@ -173,8 +173,18 @@ int ba_sync(ba_handle* h) {
   return BA_OK;
 }
 
+int ba_set_profiling(ba_handle* h, int on) {
+  if (!h) return BA_ERR_ARG;
+  h->profile = on != 0;
+  return BA_OK;
+}
+
 int ba_last_eval_ms(ba_handle* h, float* ms) {
   if (!h || !ms) return BA_ERR_ARG;
+  if (!h->profile) {
+    h->err = "ba_last_eval_ms: call ba_set_profiling(h, 1) before the evaluation";
+    return BA_ERR_ARG;
+  }
   BA_CUDA(cudaSetDevice(h->device));
   BA_CUDA(cudaEventSynchronize(h->ev_eval1));
   BA_CUDA(cudaEventElapsedTime(ms, h->ev_eval0, h->ev_eval1));

@@ -93,7 +93,8 @@ struct ba_handle {
   double* d_w = nullptr;
   int64_t* d_rows = nullptr;  // staging
   int64_t* d_cols = nullptr;
-  cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch
+  cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (profiling only)
+  bool profile = false;
   ba_lm_state lm;
   ncclComm* comm = nullptr;
   mutable std::string err;

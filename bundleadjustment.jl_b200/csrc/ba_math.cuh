@@ -255,14 +255,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 // 32 for a per-lane strided read), then each lane reads its own record.  Rows are padded to 9
 // double2 (144 B, odd multiple of 16 B) so the per-lane 16-byte reads are bank-conflict free.
 constexpr int CAM_ROW2 = 9;  // double2 per staged camera row
-__device__ __forceinline__ void warp_stage_cams(const double* __restrict__ camtab, int cam_of_lane, int lane,
+// COHERENT: read the records with ld.global.cg instead of the non-coherent path.  Needed when the kernel
+// runs as a programmatic dependent launch of the kernel that wrote them (k_eval after k_cam_precompute):
+// ld.global.nc may be hoisted above griddepcontrol.wait, because the compiler takes nc data to be constant
+// for the whole kernel.
+template <bool COHERENT = false>
+__device__ __forceinline__ void warp_stage_cams(const double* camtab, int cam_of_lane, int lane,
                                                 double2* __restrict__ rows /* 32 * CAM_ROW2 */) {
   const int sub = lane >> 3, ch = lane & 7;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + sub;
     const int c = __shfl_sync(0xffffffffu, cam_of_lane, r);
-    const double2 t = __ldg(reinterpret_cast<const double2*>(camtab + (int64_t)c * CAM_REC) + ch);
+    const double2* src = reinterpret_cast<const double2*>(camtab + (int64_t)c * CAM_REC) + ch;
+    const double2 t = COHERENT ? __ldcg(src) : __ldg(src);
     rows[r * CAM_ROW2 + ch] = t;
   }
   __syncwarp();

@@ -90,8 +90,11 @@ BA_API int ba_residual_jac_dev(ba_handle* h, const double* x_dev, double* cx_dev
 BA_API int ba_jprod_dev(ba_handle* h, const double* x_dev, const double* v_dev, double* Jv_dev);
 BA_API int ba_jtprod_dev(ba_handle* h, const double* x_dev, const double* v_dev, double* Jtv_dev);
 BA_API int ba_sync(ba_handle* h);
-/* Device time (CUDA events on the handle's stream) of the most recent per-observation evaluation
- * kernel alone (k_eval: cons!/jac_coord!/fused), for roofline reporting; waits for that kernel. */
+/* Profiling: with it on, the per-observation evaluation kernel (k_eval: cons!/jac_coord!/fused) is
+ * bracketed by CUDA events on the handle's stream and ba_last_eval_ms returns its device time alone
+ * (waits for that kernel); for roofline reporting.  Off by default: the events would sit between the
+ * camera-precompute kernel and its programmatic dependent launch. */
+BA_API int ba_set_profiling(ba_handle* h, int on);
 BA_API int ba_last_eval_ms(ba_handle* h, float* ms);
 
 /* ---- Levenberg-Marquardt, src/lm.jl:15-418 --------------------------------------------------- */

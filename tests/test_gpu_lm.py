@@ -196,3 +196,54 @@ def test_trafalgar_shape_full_solve(ba):
     assert abs(0.5 * float(r @ r) - st.objective) <= 1e-9 * st.objective
     g = m.jtprod_(st.solution, r)
     assert abs(np.linalg.norm(g) - st.dual_feas) <= 1e-6 * st.dual_feas
+
+
+def test_dubrovnik_shape_lm_iterations(ba, oracle):
+    # BASELINE.json configs[2]: Dubrovnik problem-356-226730 shape (1.26 M observations).  Oracle on a slice
+    # of the evaluation; LM through properties (the LDL oracle is far too slow here).
+    p = ba.synth.make_problem("dubrovnik-356")
+    m = _model(ba, p)
+    cx, vals = m.cons_jac_coord_(p.x0)
+    s0 = p.nobs - 5000
+    from conftest import assert_jac_rel, assert_rel
+    assert_rel(cx[2 * s0:], oracle.cons(p.cam_idx[s0:], p.pnt_idx[s0:], p.pt2d[2 * s0:], p.x0, p.npnts), TOL,
+               scale=np.abs(p.pt2d).max())
+    assert_jac_rel(vals[24 * s0:], oracle.jac_coord(p.cam_idx[s0:], p.pnt_idx[s0:], p.x0, p.npnts), TOL)
+    lam = 100.0
+    d, dr2, obj, jtr, it = ba.lm_step(m, p.x0, lam, want_jtr=True)
+    Jd = m.jprod_(p.x0, d)
+    assert np.linalg.norm(m.jtprod_(p.x0, Jd) + lam * d + jtr) <= 1e-10 * np.linalg.norm(jtr)
+    assert abs(dr2 - 0.5 * np.linalg.norm(Jd + cx) ** 2) <= 1e-11 * dr2
+    st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=3)
+    f = [r["f"] for r in st.rows]
+    assert all(b <= a for a, b in zip(f[:-1], f[1:])) and st.objective < 0.1 * f[0]
+
+
+def test_final_shape_on_one_gpu(ba, oracle):
+    # BASELINE.json configs[4]: Final problem-13682-4456117 shape (29 M observations).  Specified as 8-way
+    # sharded, but it fits one 180 GB B200: evaluation slice vs oracle, adjointness over all observations,
+    # assembly (J'r, objective) of the LM path, and the 8-way partition the sharded run would use.
+    import ctypes as C
+    p = ba.synth.make_problem("final-13682")
+    m = _model(ba, p)
+    cx = m.cons(p.x0)
+    assert np.all(np.isfinite(cx))
+    s0 = p.nobs - 5000
+    from conftest import assert_rel
+    assert_rel(cx[2 * s0:], oracle.cons(p.cam_idx[s0:], p.pnt_idx[s0:], p.pt2d[2 * s0:], p.x0, p.npnts), TOL,
+               scale=np.abs(p.pt2d).max())
+    rng = np.random.default_rng(4)
+    v = rng.normal(size=p.nvar)
+    w = rng.normal(size=2 * p.nobs)
+    Jv = m.jprod_(p.x0, v)
+    Jtw = m.jtprod_(p.x0, w)
+    assert abs(float(Jv @ w) - float(v @ Jtw)) <= 1e-11 * np.linalg.norm(Jv) * np.linalg.norm(w)
+    d, dr2, obj, jtr, it = ba.lm_step(m, p.x0, 1e3, pcg_max_iter=8, want_jtr=True)   # 8 PCG iterations only
+    assert it == 8
+    assert abs(obj - 0.5 * float(cx @ cx)) <= 1e-11 * obj
+    g = m.jtprod_(p.x0, cx)
+    assert np.linalg.norm(jtr - g) <= 1e-10 * np.linalg.norm(g)
+    cuts = np.empty(9, dtype=np.int64)
+    assert ba._lib.lib().ba_partition_observations(p.nobs, p.pnt_idx.ctypes.data_as(C.c_void_p), 8,
+                                                   cuts.ctypes.data_as(C.c_void_p)) == 0
+    assert np.diff(cuts).min() > 0.99 * p.nobs / 8 and np.diff(cuts).max() < 1.01 * p.nobs / 8
