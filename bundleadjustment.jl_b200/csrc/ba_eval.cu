@@ -21,8 +21,10 @@ namespace ba {
 #define EVAL_MINBLOCKS 5  // resident blocks per SM the register allocation targets (A/B-tested)
 #endif
 constexpr int EVAL_THREADS = 128;           // 4 warps
-constexpr int STAGE_ROW = 13;               // double2 per staged observation (12 + 1 pad: odd stride,
-                                            // conflict-free 16-byte shared stores and loads)
+#ifndef EVAL_SWIZZLE
+#define EVAL_SWIZZLE 0  // 0: rows padded to 13 words; 1: dense rows + XOR swizzle (conflict-free but slower: DESIGN.md)
+#endif
+constexpr int STAGE_ROW = EVAL_SWIZZLE ? 12 : 13;  // double2 per staged observation
 
 __global__ void __launch_bounds__(128) k_cam_precompute(const double* __restrict__ xcam, int64_t ncams,
                                                         double* __restrict__ camtab) {
@@ -88,20 +90,25 @@ k_eval(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
   if (WCX && valid) __stcs(reinterpret_cast<double2*>(cx) + k, make_double2(o.F[0], o.F[1]));
   if (WVALS) {
     __syncwarp();  // every lane has its camera record in registers: the buffer can be reused
+    // Transpose through shared memory with dense 192-byte rows and an XOR swizzle of the 16-byte column
+    // index by ((row >> 1) & 3): the per-lane row writes (row stride 12 words) and the transposed reads
+    // (32 consecutive words per instruction) are both bank-conflict free, because the swizzle only permutes
+    // words inside aligned groups of four.
     double2* row = st + lane * STAGE_ROW;
+    const int sw = EVAL_SWIZZLE ? (lane >> 1) & 3 : 0;
     // reference order: row 1 = [A(3) B(9)], row 2 likewise; per-entry NaN -> 0
-    row[0] = make_double2(nan0(o.A[0]), nan0(o.A[1]));
-    row[1] = make_double2(nan0(o.A[2]), nan0(o.B[0]));
-    row[2] = make_double2(nan0(o.B[1]), nan0(o.B[2]));
-    row[3] = make_double2(nan0(o.B[3]), nan0(o.B[4]));
-    row[4] = make_double2(nan0(o.B[5]), nan0(o.B[6]));
-    row[5] = make_double2(nan0(o.B[7]), nan0(o.B[8]));
-    row[6] = make_double2(nan0(o.A[3]), nan0(o.A[4]));
-    row[7] = make_double2(nan0(o.A[5]), nan0(o.B[9]));
-    row[8] = make_double2(nan0(o.B[10]), nan0(o.B[11]));
-    row[9] = make_double2(nan0(o.B[12]), nan0(o.B[13]));
-    row[10] = make_double2(nan0(o.B[14]), nan0(o.B[15]));
-    row[11] = make_double2(nan0(o.B[16]), nan0(o.B[17]));
+    row[0 ^ sw] = make_double2(nan0(o.A[0]), nan0(o.A[1]));
+    row[1 ^ sw] = make_double2(nan0(o.A[2]), nan0(o.B[0]));
+    row[2 ^ sw] = make_double2(nan0(o.B[1]), nan0(o.B[2]));
+    row[3 ^ sw] = make_double2(nan0(o.B[3]), nan0(o.B[4]));
+    row[4 ^ sw] = make_double2(nan0(o.B[5]), nan0(o.B[6]));
+    row[5 ^ sw] = make_double2(nan0(o.B[7]), nan0(o.B[8]));
+    row[6 ^ sw] = make_double2(nan0(o.A[3]), nan0(o.A[4]));
+    row[7 ^ sw] = make_double2(nan0(o.A[5]), nan0(o.B[9]));
+    row[8 ^ sw] = make_double2(nan0(o.B[10]), nan0(o.B[11]));
+    row[9 ^ sw] = make_double2(nan0(o.B[12]), nan0(o.B[13]));
+    row[10 ^ sw] = make_double2(nan0(o.B[14]), nan0(o.B[15]));
+    row[11 ^ sw] = make_double2(nan0(o.B[16]), nan0(o.B[17]));
     __syncwarp();
     const int nval = (int)min((int64_t)32, nobs - wbase);
     double2* dst = reinterpret_cast<double2*>(vals) + wbase * 12;
@@ -109,7 +116,7 @@ k_eval(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
     for (int m = 0; m < 12; ++m) {
       const int q = lane + 32 * m;
       const int r = q / 12, cidx = q - 12 * r;
-      if (r < nval) __stcs(dst + q, st[r * STAGE_ROW + cidx]);
+      if (r < nval) __stcs(dst + q, st[r * STAGE_ROW + (EVAL_SWIZZLE ? cidx ^ ((r >> 1) & 3) : cidx)]);
     }
   }
 }
