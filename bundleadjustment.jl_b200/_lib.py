@@ -78,6 +78,8 @@ SYMBOLS = {
     "ba_lm_solve": (C.c_int, [_vp, _vp, C.POINTER(LMParams), C.POINTER(LMStats), _vp, _vp]),
     "ba_comm_unique_id": (C.c_int, [_vp]),
     "ba_comm_init": (C.c_int, [_vp, _vp]),
+    "ba_comm_ipc_export": (C.c_int, [_vp, _vp]),
+    "ba_comm_ipc_import": (C.c_int, [_vp, _vp]),
 }
 
 _lib = None

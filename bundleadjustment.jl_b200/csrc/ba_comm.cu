@@ -6,7 +6,9 @@
 // single-GPU entry point works) in processes that never touch NCCL; inside a torch process the
 // already-loaded libnccl.so.2 is reused.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 #include "ba_internal.h"
 
 namespace {
@@ -70,6 +72,14 @@ int allreduce_sum(ba_handle* h, double* buf, size_t n) {
 void comm_release(ba_handle* h) {
   if (h->comm && api().ok) api().destroy(h->comm);
   h->comm = nullptr;
+  ba_p2p_state& P = h->p2p;
+  for (int r = 0; r < P.nranks; ++r)
+    if (P.peer_block[r] && P.peer_block[r] != P.block) cudaIpcCloseMemHandle(P.peer_block[r]);
+  cudaFree(P.d_mail);
+  cudaFree(P.d_flags);
+  cudaFree(P.d_seq);
+  cudaFree(P.block);
+  P = ba_p2p_state();
 }
 
 }  // namespace ba
@@ -110,6 +120,63 @@ int ba_comm_init(ba_handle* h, const uint8_t id128[128]) {
   BA_CUDA(cudaStreamSynchronize(h->stream));
   cudaFree(warm);
   return wrc;
+}
+
+int ba_comm_ipc_export(ba_handle* h, uint8_t handle64[64]) {
+  if (!h || !handle64) return BA_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (h->nranks > 16) {
+    h->err = "peer-memory exchange supports at most 16 ranks";
+    return BA_ERR_ARG;
+  }
+  BA_CUDA(cudaSetDevice(h->device));
+  ba_p2p_state& P = h->p2p;
+  if (!P.block) {
+    const size_t bytes = P.mail_off + 2 * 9 * (size_t)h->ncams * sizeof(double);
+    BA_CUDA(cudaMalloc(&P.block, bytes));
+    BA_CUDA(cudaMemset(P.block, 0, bytes));
+  }
+  cudaIpcMemHandle_t mh;
+  BA_CUDA(cudaIpcGetMemHandle(&mh, P.block));
+  memcpy(handle64, &mh, 64);
+  return BA_OK;
+}
+
+int ba_comm_ipc_import(ba_handle* h, const uint8_t* handles) {
+  if (!h || !handles) return BA_ERR_ARG;
+  ba_p2p_state& P = h->p2p;
+  if (!P.block) {
+    h->err = "ba_comm_ipc_import before ba_comm_ipc_export";
+    return BA_ERR_ARG;
+  }
+  BA_CUDA(cudaSetDevice(h->device));
+  P.nranks = h->nranks;
+  P.rank = h->rank;
+  std::vector<double*> mail((size_t)h->nranks);
+  std::vector<unsigned long long*> flags((size_t)h->nranks);
+  for (int r = 0; r < h->nranks; ++r) {
+    if (r == h->rank) {
+      P.peer_block[r] = P.block;
+    } else {
+      cudaIpcMemHandle_t mh;
+      memcpy(&mh, handles + 64 * (size_t)r, 64);
+      BA_CUDA(cudaIpcOpenMemHandle(&P.peer_block[r], mh, cudaIpcMemLazyEnablePeerAccess));
+    }
+    flags[(size_t)r] = reinterpret_cast<unsigned long long*>(P.peer_block[r]);
+    mail[(size_t)r] = reinterpret_cast<double*>(static_cast<char*>(P.peer_block[r]) + P.mail_off);
+  }
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_mail), sizeof(double*) * 16));
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_flags), sizeof(unsigned long long*) * 16));
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_seq), sizeof(unsigned long long)));
+  BA_CUDA(cudaMemcpy(P.d_mail, mail.data(), sizeof(double*) * (size_t)h->nranks, cudaMemcpyHostToDevice));
+  BA_CUDA(cudaMemcpy(P.d_flags, flags.data(), sizeof(unsigned long long*) * (size_t)h->nranks, cudaMemcpyHostToDevice));
+  BA_CUDA(cudaMemset(P.d_seq, 0, sizeof(unsigned long long)));
+  static const bool off = getenv("BAGPU_NO_P2P") != nullptr;
+  P.ready = !off;
+  // a captured PCG graph holds the NCCL variant: drop it
+  if (h->lm.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(h->lm.pcg_graph));
+  h->lm.pcg_graph = nullptr;
+  return BA_OK;
 }
 
 }  // extern "C"

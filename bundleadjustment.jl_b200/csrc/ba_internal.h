@@ -73,6 +73,19 @@ struct ba_lm_state {
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
+// Peer-memory exchange for the per-PCG-iteration camera vector (one process per GPU, CUDA IPC over
+// NVLink/NVSwitch): every rank owns one exported block [flags (16 x u64) | pad | mail[2][9 ncams]].
+struct ba_p2p_state {
+  bool ready = false;
+  int nranks = 0, rank = 0;
+  void* block = nullptr;                 // own allocation (cudaMalloc, exported)
+  void* peer_block[16] = {nullptr};      // opened peer blocks (own entry = block)
+  double** d_mail = nullptr;             // device array [nranks]: base of each rank's mail[2][n9]
+  unsigned long long** d_flags = nullptr;  // device array [nranks]: each rank's flag slots
+  unsigned long long* d_seq = nullptr;   // exchange sequence number (device, local)
+  size_t mail_off = 256;                 // byte offset of mail inside a block
+};
+
 struct ba_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -97,6 +110,7 @@ struct ba_handle {
   bool profile = false;
   ba_lm_state lm;
   ncclComm* comm = nullptr;
+  ba_p2p_state p2p;
   mutable std::string err;
   int64_t nvar() const { return 9 * ncams + 3 * npnts; }
   int64_t nobs_l() const { return obs1 - obs0; }

@@ -247,9 +247,10 @@ k_cam_pass(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, i
            const int32_t* __restrict__ cperm, const int32_t* __restrict__ pntc, int64_t nl,
            const double* __restrict__ camtab, const double2* __restrict__ x4, const double2* __restrict__ F,
            const double2* __restrict__ w, const double* __restrict__ T, double* taskpart, double* __restrict__ out,
-           const double* __restrict__ scal) {
+           const double* __restrict__ scal, double* mail, const unsigned long long* seqp, int64_t n9) {
   if (MODE == 2 && scal[S_DONE] != 0.0) return;
   constexpr int NACC = (MODE == 2) ? 9 : NV;
+  if (MODE == 2 && mail) out = mail + ((*seqp) & 1ull) * n9;  // this exchange's half of the peer-visible mailbox
   const int lane = threadIdx.x & 31;
   const int64_t task = blockIdx.x * (int64_t)(PT_THREADS / 32) + (threadIdx.x >> 5);
   if (task >= nctasks) return;
@@ -351,7 +352,9 @@ k_pad_points(const double* __restrict__ x, int64_t p_lo, int64_t p_hi, double2* 
 }
 
 // cameras without observations on this rank: their sums are zero
-__global__ void k_zero_cams(const int32_t* __restrict__ cams, int n, int nacc, double* __restrict__ out) {
+__global__ void k_zero_cams(const int32_t* __restrict__ cams, int n, int nacc, double* __restrict__ out,
+                            double* mail, const unsigned long long* seqp, int64_t n9) {
+  if (mail) out = mail + ((*seqp) & 1ull) * n9;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n * nacc) out[(int64_t)cams[i / nacc] * nacc + (i % nacc)] = 0.0;
 }
@@ -681,18 +684,79 @@ __device__ __forceinline__ double sum_partials(const double* part, int n, double
   return block_sum<VEC_THREADS>(s, sh);
 }
 
-// K7c: on entry q holds sum_k B'w (allreduced over ranks in sharded mode); q = (U + lambda I) p - q = S p,
-// per-CTA partials of p.q.  Also publishes the r.z of the previous iteration as the current one.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// K7c: q = (U + lambda I) p - sum_k B'w = S p, per-CTA partials of p.q; also publishes the r.z of the
+// previous iteration as the current one.
+//   P2P = false: on entry q holds sum_k B'w (already allreduced by NCCL in sharded mode).
+//   P2P = true : the sum over ranks is FUSED here.  Every rank's camera pass left its partial in its own
+//     IPC-exported mailbox half (seq & 1); block 0 tells every peer "my partial #seq+1 is complete" with a
+//     release store into the peer's flag slot (over NVLink), every CTA waits until all ranks have said so,
+//     then each row adds the R partials in rank order straight from peer memory -- the same order on every
+//     rank, so all ranks get bit-identical q.  Two mailbox halves suffice: nobody can be two exchanges ahead
+//     of a rank that has not yet passed this wait.  A wait is bounded (~2 s) and flags an error instead of
+//     hanging.
+template <bool P2P>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_pcg_q(int64_t n9, const double* __restrict__ H, const double* p, double* q, double* __restrict__ part_pq,
-        double* scal) {
+        double* scal, double* const* __restrict__ mails, unsigned long long* const* __restrict__ flags,
+        const unsigned long long* seqp, int nranks, int rank) {
   __shared__ double sh[VEC_THREADS / 32];
+  __shared__ int timed_out;
   if (scal[S_DONE] != 0.0) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_RZ] = scal[S_RZN];
+  unsigned long long seq = 0;
+  if (P2P) {
+    seq = *seqp;
+    if (threadIdx.x == 0) timed_out = 0;
+    if (blockIdx.x == 0 && threadIdx.x < nranks) {
+      __threadfence_system();  // the camera pass of this rank finished before this kernel started
+      st_release_sys(flags[threadIdx.x] + rank, seq + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < nranks) {
+      const unsigned long long* f = flags[rank] + threadIdx.x;  // my slots, written by the peers
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) < seq + 1) {
+        if (clock64() - t0 > 4000000000ll) {
+          timed_out = 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if (timed_out) {
+      if (threadIdx.x == 0) {
+        scal[S_DONE] = 2.0;
+        scal[S_ERR] = 3.0;
+      }
+      return;
+    }
+  }
   const int64_t i = blockIdx.x * (int64_t)VEC_ROWS + threadIdx.x;
   double pq = 0.0;
   if (threadIdx.x < VEC_ROWS && i < n9) {
-    const double qi = row9(H, p, i) - q[i];
+    double sum;
+    if (P2P) {
+      const int64_t off = (int64_t)(seq & 1ull) * n9 + i;
+      sum = 0.0;
+      for (int r = 0; r < nranks; ++r) sum += ld_volatile_f64(mails[r] + off);
+    } else {
+      sum = q[i];
+    }
+    const double qi = row9(H, p, i) - sum;
     q[i] = qi;
     pq = p[i] * qi;
   }
@@ -741,7 +805,7 @@ k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __r
 template <bool INIT>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_pq, const double* part_rz,
-        double* scal, double tol) {
+        double* scal, double tol, unsigned long long* seqp) {
   __shared__ double sh[VEC_THREADS / 32];
   const int64_t i = blockIdx.x * (int64_t)VEC_ROWS + threadIdx.x;
   const bool live = threadIdx.x < VEC_ROWS && i < n9;
@@ -772,6 +836,7 @@ k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_p
   const double rzn = sum_partials(part_rz, nparts, sh);
   const double beta = rzn / scal[S_RZ];
   if (live) p[i] = z[i] + beta * p[i];
+  if (lead && seqp) *seqp += 1;  // next exchange uses the other mailbox half (no CTA of this kernel reads it)
   if (lead) {
     const double rel = sqrt(rzn / scal[S_RZ0]);
     scal[S_RZN] = rzn;
@@ -981,9 +1046,11 @@ struct Solver {
     if (S.nctasks)
       k_cam_pass<MODE><<<nblk(S.nctasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
           S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_ctask_cam, S.d_cam_t0, S.d_cam_cnt, S.d_cperm, S.d_pntc, nl,
-          h->d_camtab, S.d_x4, S.d_F, S.d_w, S.d_T, S.d_taskpart, out, S.d_scal);
+          h->d_camtab, S.d_x4, S.d_F, S.d_w, S.d_T, S.d_taskpart, out, S.d_scal, nullptr, nullptr, n9);
     (void)check_done;
-    if (S.nempty) k_zero_cams<<<nblk((int64_t)S.nempty * nacc, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, nacc, out);
+    if (S.nempty)
+      k_zero_cams<<<nblk((int64_t)S.nempty * nacc, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, nacc, out,
+                                                                     nullptr, nullptr, n9);
     int rc = check();
     if (rc) return rc;
     return allreduce_sum(h, out, (size_t)(ncams * nacc));
@@ -1030,19 +1097,30 @@ struct Solver {
           S.d_tstart, S.ntasks, h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_F, p, S.d_Vinv, S.d_gp, S.d_w,
           nullptr, nullptr, S.d_part, S.d_scal);
     if (checks && (rc = check())) return rc;
+    const ba_p2p_state& P = h->p2p;
+    const bool p2p = h->nranks > 1 && P.ready;
+    double* mail = p2p ? reinterpret_cast<double*>(static_cast<char*>(P.block) + P.mail_off) : nullptr;
     if (S.nctasks)
       k_cam_pass<2><<<nblk(S.nctasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
           S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_ctask_cam, S.d_cam_t0, S.d_cam_cnt, S.d_cperm, S.d_pntc, nl,
-          h->d_camtab, S.d_x4, S.d_F, S.d_w, S.d_T, S.d_taskpart, q, S.d_scal);
-    if (S.nempty) k_zero_cams<<<nblk((int64_t)S.nempty * 9, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, 9, q);
+          h->d_camtab, S.d_x4, S.d_F, S.d_w, S.d_T, S.d_taskpart, q, S.d_scal, mail, P.d_seq, n9);
+    if (S.nempty)
+      k_zero_cams<<<nblk((int64_t)S.nempty * 9, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, 9, q, mail, P.d_seq,
+                                                                   n9);
     if (checks && (rc = check())) return rc;
-    if ((rc = allreduce_sum(h, q, (size_t)n9))) return rc;
     const int nvb = (int)nblk(n9, VEC_ROWS);
     double* ppq = S.d_pcgpart;
     double* prz = S.d_pcgpart + nvb;
-    k_pcg_q<<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, ppq, S.d_scal);
+    if (p2p) {
+      // the sum over ranks is fused into the kernel that consumes it (peer loads over NVLink)
+      k_pcg_q<true><<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, ppq, S.d_scal, P.d_mail, P.d_flags, P.d_seq,
+                                                 h->nranks, h->rank);
+    } else {
+      if ((rc = allreduce_sum(h, q, (size_t)n9))) return rc;
+      k_pcg_q<false><<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, ppq, S.d_scal, nullptr, nullptr, nullptr, 1, 0);
+    }
     k_pcg_xr<false><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, b, S.d_Minv, p, q, xc, r, z, ppq, prz, S.d_scal);
-    k_pcg_p<false><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol);
+    k_pcg_p<false><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol, p2p ? P.d_seq : nullptr);
     return checks ? check() : BA_OK;
   }
   // block-Jacobi PCG on S dc = b; result in xc.  Convergence is decided on the device (S_DONE): the host
@@ -1057,7 +1135,7 @@ struct Solver {
       double* ppq = S.d_pcgpart;
       double* prz = S.d_pcgpart + nvb;
       k_pcg_xr<true><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, b, S.d_Minv, p, q, xc, r, z, ppq, prz, S.d_scal);
-      k_pcg_p<true><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol);
+      k_pcg_p<true><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol, nullptr);
     }
     int rc = check();
     if (rc) return rc;

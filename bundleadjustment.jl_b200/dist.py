@@ -7,9 +7,11 @@ import ctypes as C
 from . import _lib
 
 
-def init_comm(model, group=None):
+def init_comm(model, group=None, p2p=True):
     """Create the NCCL communicator of a sharded BALNLPModel.  Needs an initialised torch.distributed
-    process group (any backend) whose ranks match model.rank / model.nranks."""
+    process group (any backend) whose ranks match model.rank / model.nranks.  With ``p2p`` (default) the ranks
+    also exchange CUDA IPC handles so that the per-PCG-iteration sum runs over peer memory (NVLink) fused into
+    the kernel that consumes it; BAGPU_NO_P2P=1 keeps that exchange on NCCL."""
     import torch
     import torch.distributed as dist
     if model.nranks == 1:
@@ -28,3 +30,15 @@ def init_comm(model, group=None):
     dist.broadcast(t, 0, group=group)
     arr = (C.c_uint8 * 128)(*t.cpu().tolist())
     _lib.check(L.ba_comm_init(model.handle, arr), model.handle)
+    if p2p:
+        # peer-memory mailboxes for the per-PCG-iteration exchange: swap CUDA IPC handles (64 bytes per rank)
+        mine = (C.c_uint8 * 64)()
+        _lib.check(L.ba_comm_ipc_export(model.handle, mine), model.handle)
+        t = torch.tensor(list(mine), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(model.device)
+        parts = [torch.empty_like(t) for _ in range(model.nranks)]
+        dist.all_gather(parts, t, group=group)
+        flat = [b for q in parts for b in q.cpu().tolist()]
+        allh = (C.c_uint8 * (64 * model.nranks))(*flat)
+        _lib.check(L.ba_comm_ipc_import(model.handle, allh), model.handle)

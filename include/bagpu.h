@@ -144,6 +144,14 @@ BA_API int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* p, ba_
  * MPI, a file); every rank then calls ba_comm_init on its sharded handle. */
 BA_API int ba_comm_unique_id(uint8_t id128[128]);
 BA_API int ba_comm_init(ba_handle* h, const uint8_t id128[128]);
+/* Optional peer-memory path for the one exchange that happens every PCG iteration (sum over ranks of the
+ * camera-sized vector  sum_k B'w, 9*ncams doubles): each rank exports a mailbox with CUDA IPC
+ * (ba_comm_ipc_export, 64 bytes), the handles of ALL ranks in rank order are passed to ba_comm_ipc_import,
+ * and from then on the vector kernel that consumes the sum reads every peer's partial directly over
+ * NVLink/NVSwitch (flag handshake, fixed rank order => bit-identical on all ranks) instead of calling
+ * ncclAllReduce.  The other, per-LM-iteration collectives stay on NCCL. */
+BA_API int ba_comm_ipc_export(ba_handle* h, uint8_t handle64[64]);
+BA_API int ba_comm_ipc_import(ba_handle* h, const uint8_t* handles64_by_rank);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,14 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def ba():
+    """The package under test.  If libbagpu.so has not been built yet (fresh checkout), build it in-tree
+    first (nvcc cross-compiles sm_100a without a GPU) -- building is not a fallback: there is none."""
+    import importlib.util as u
+    spec = u.spec_from_file_location("_ba_build", os.path.join(ROOT, "bundleadjustment.jl_b200", "build.py"))
+    mod = u.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if not os.path.exists(mod.LIB):
+        mod.build_lib()
     import bundleadjustment.jl_b200 as pkg
     return pkg
 
