@@ -70,6 +70,7 @@ SYMBOLS = {
     "ba_jprod_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "ba_jtprod_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "ba_sync": (C.c_int, [_vp]),
+    "ba_set_coarse_clusters": (C.c_int, [_vp, C.c_int]),
     "ba_set_profiling": (C.c_int, [_vp, C.c_int]),
     "ba_last_eval_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ba_lm_default_params": (None, [C.POINTER(LMParams)]),

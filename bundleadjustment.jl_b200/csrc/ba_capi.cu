@@ -1,5 +1,6 @@
 // ba_capi.cu -- the extern "C" boundary of libbagpu.so (see include/bagpu.h for the contract).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "ba_internal.h"
@@ -44,6 +45,7 @@ int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, 
   *out = h;  // returned even on failure so that ba_last_error can be read; caller destroys it
   h->device = device;
   h->ncams = ncams; h->npnts = npnts; h->nobs = nobs; h->rank = rank; h->nranks = nranks;
+  if (const char* e = getenv("BAGPU_COARSE")) h->coarse_clusters = atoi(e);
   bool sorted = true;
   for (int64_t k = 0; k < nobs; ++k) {
     if (cam[k] < 1 || cam[k] > ncams || pnt[k] < 1 || pnt[k] > npnts)
@@ -170,6 +172,17 @@ int ba_sync(ba_handle* h) {
   if (!h) return BA_ERR_ARG;
   BA_CUDA(cudaSetDevice(h->device));
   BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+int ba_set_coarse_clusters(ba_handle* h, int n) {
+  if (!h || n < 0) return BA_ERR_ARG;
+  if (n != h->coarse_clusters) {
+    BA_CUDA(cudaSetDevice(h->device));
+    if (h->stream) BA_CUDA(cudaStreamSynchronize(h->stream));
+    ba::lm_release(h);  // schedules and the captured PCG graph depend on it; rebuilt on next use
+    h->coarse_clusters = n;
+  }
   return BA_OK;
 }
 

@@ -57,6 +57,13 @@ struct ba_lm_state {
   double* d_Minv = nullptr;  // ncams x 81: inverse Schur diagonal block (block-Jacobi preconditioner)
   double* d_pcg = nullptr;   // 6 vectors of 9 ncams: b, xc, r, z, p, q
   double* d_pcgpart = nullptr;  // per-CTA partials of the two PCG dot products
+  // two-level preconditioner (coarse space of piecewise-constant camera clusters)
+  int ncl = 0, ctas_per_cluster = 1, mc = 0;  // clusters, vector-kernel CTAs (28 cameras) per cluster, 9 ncl
+  double* d_Ac = nullptr;     // mc x mc: P' S P
+  double* d_Aci = nullptr;    // its inverse
+  double* d_Wc = nullptr;     // mc x 2mc scratch of the inversion
+  double* d_yc = nullptr;     // mc: coarse correction of the current residual
+  double* d_cpart = nullptr;  // 9 per vector-kernel CTA: restriction partials
   // ---- iterates -------------------------------------------------------------------------------
   double* d_x = nullptr;      // current iterate (nvar; only this rank's point slice + cameras are live)
   double* d_xt = nullptr;     // trial iterate
@@ -108,6 +115,7 @@ struct ba_handle {
   int64_t* d_cols = nullptr;
   cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (profiling only)
   bool profile = false;
+  int coarse_clusters = 8;   // two-level PCG preconditioner: target number of camera clusters (0 = off)
   ba_lm_state lm;
   ncclComm* comm = nullptr;
   ba_p2p_state p2p;

@@ -46,7 +46,7 @@ enum {
   S_GC2 = 8,  // sum g_c^2 (cameras are replicated)
   S_DC2,      // sum delta_c^2
   S_XC2,      // sum (x + delta)_c^2
-  S_RZ = 16, S_RZ0, S_PQ, S_DONE, S_ITERS, S_REL, S_ERR, S_RZN,
+  S_RZ = 16, S_RZ0, S_PQ, S_DONE, S_ITERS, S_REL, S_ERR, S_RZN, S_RCY,
   S_COUNT = 32
 };
 
@@ -770,8 +770,9 @@ template <bool INIT>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __restrict__ Minv, const double* p,
          const double* q, double* xc, double* r, double* z, const double* part_pq, double* __restrict__ part_rz,
-         const double* scal) {
+         const double* scal, double* __restrict__ cpart) {
   __shared__ double sh[VEC_THREADS / 32];
+  __shared__ double rs[VEC_ROWS];
   const int64_t i = blockIdx.x * (int64_t)VEC_ROWS + threadIdx.x;
   const bool live = threadIdx.x < VEC_ROWS && i < n9;
   if (INIT) {
@@ -798,6 +799,47 @@ k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __r
   }
   rz = block_sum<VEC_THREADS>(rz, sh);
   if (threadIdx.x == 0) part_rz[blockIdx.x] = rz;
+  if (cpart) {  // restriction to the coarse space: this CTA's 28 cameras summed per component (fixed order)
+    if (threadIdx.x < VEC_ROWS) rs[threadIdx.x] = live ? r[i] : 0.0;
+    __syncthreads();
+    if (threadIdx.x < 9) {
+      double t = 0.0;
+      for (int c = 0; c < VEC_ROWS / 9; ++c) t += rs[c * 9 + threadIdx.x];
+      cpart[blockIdx.x * 9 + threadIdx.x] = t;
+    }
+  }
+}
+
+// Coarse level of the two-level preconditioner  M^-1 = blkdiag(S_cc)^-1 + P Ac^-1 P':  P = piecewise-constant
+// interpolation from `ncl` clusters of consecutive cameras (9 coarse unknowns per cluster), Ac = P' S P.
+// rc = P' r from the per-CTA partials (a CTA never straddles clusters), yc = Ac^-1 rc, and r.(P yc) = rc.yc
+// for the r.z dot product.  One CTA; m = 9 ncl <= 144.
+__global__ void __launch_bounds__(160)
+k_pcg_coarse(int nvb, int ctas_per_cluster, int m, const double* __restrict__ cpart, const double* __restrict__ Aci,
+             double* __restrict__ yc, double* scal, int init) {
+  __shared__ double rc[144], yy[144];
+  if (!init && scal[S_DONE] != 0.0) return;
+  const int a = threadIdx.x;
+  if (a < m) {
+    const int I = a / 9, jj = a - 9 * I;
+    const int b0 = I * ctas_per_cluster, b1 = min(nvb, b0 + ctas_per_cluster);
+    double t = 0.0;
+    for (int bb = b0; bb < b1; ++bb) t += cpart[bb * 9 + jj];
+    rc[a] = t;
+  }
+  __syncthreads();
+  if (a < m) {
+    double t = 0.0;
+    for (int bq = 0; bq < m; ++bq) t += Aci[a * m + bq] * rc[bq];
+    yy[a] = t;
+    yc[a] = t;
+  }
+  __syncthreads();
+  if (a == 0) {
+    double t = 0.0;
+    for (int bq = 0; bq < m; ++bq) t += rc[bq] * yy[bq];
+    scal[S_RCY] = t;
+  }
 }
 
 // K7e: beta = r.z(new) / r.z(old); p = z + beta p; iteration count and convergence flag.
@@ -805,14 +847,17 @@ k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __r
 template <bool INIT>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_pq, const double* part_rz,
-        double* scal, double tol, unsigned long long* seqp) {
+        double* scal, double tol, unsigned long long* seqp, const double* __restrict__ yc, int ctas_per_cluster) {
   __shared__ double sh[VEC_THREADS / 32];
   const int64_t i = blockIdx.x * (int64_t)VEC_ROWS + threadIdx.x;
   const bool live = threadIdx.x < VEC_ROWS && i < n9;
   const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+  // coarse correction of this row: z_i = (Minv r)_i + (P yc)_i; its share of r.z is scal[S_RCY]
+  double zc = 0.0;
+  if (yc && live) zc = yc[(blockIdx.x / ctas_per_cluster) * 9 + (int)(i % 9)];
   if (INIT) {
-    const double rz = sum_partials(part_rz, nparts, sh);
-    if (live) p[i] = z[i];
+    const double rz = sum_partials(part_rz, nparts, sh) + (yc ? scal[S_RCY] : 0.0);
+    if (live) p[i] = z[i] + zc;
     if (lead) {
       scal[S_RZN] = rz;
       scal[S_RZ0] = rz;
@@ -833,9 +878,9 @@ k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_p
     }
     return;
   }
-  const double rzn = sum_partials(part_rz, nparts, sh);
+  const double rzn = sum_partials(part_rz, nparts, sh) + (yc ? scal[S_RCY] : 0.0);
   const double beta = rzn / scal[S_RZ];
-  if (live) p[i] = z[i] + beta * p[i];
+  if (live) p[i] = (z[i] + zc) + beta * p[i];
   if (lead && seqp) *seqp += 1;  // next exchange uses the other mailbox half (no CTA of this kernel reads it)
   if (lead) {
     const double rel = sqrt(rzn / scal[S_RZ0]);
@@ -846,6 +891,67 @@ k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_p
     if (!(rel > tol)) scal[S_DONE] = (rel == rel) ? 1.0 : 2.0;
   }
 }
+
+// coarse-space setup: basis vector (cluster I, component j) of P, restriction of S v, inversion of Ac
+__global__ void __launch_bounds__(256)
+k_coarse_basis(int64_t n9, int rows_per_cluster, int col, double* __restrict__ v) {
+  const int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x;
+  if (i >= n9) return;
+  const int I = col / 9, j = col - 9 * I;
+  v[i] = ((int)(i / rows_per_cluster) == I && (int)(i % 9) == j) ? 1.0 : 0.0;
+}
+
+// Ac[:, col] = P' q: one CTA per cluster, 32 x 9 threads, fixed summation order
+__global__ void __launch_bounds__(288)
+k_coarse_restrict(int64_t ncams, int cams_per_cluster, int m, int col, const double* __restrict__ q,
+                  double* __restrict__ Ac) {
+  __shared__ double part[288];
+  const int I = blockIdx.x, t = threadIdx.x / 9, jj = threadIdx.x - 9 * t;
+  const int64_t c0 = (int64_t)I * cams_per_cluster, c1 = min(ncams, c0 + cams_per_cluster);
+  double sum = 0.0;
+  for (int64_t c = c0 + t; c < c1; c += 32) sum += q[c * 9 + jj];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double tot = 0.0;
+    for (int u = 0; u < 32; ++u) tot += part[u * 9 + threadIdx.x];
+    Ac[(I * 9 + threadIdx.x) * m + col] = tot;
+  }
+}
+
+// Aci = Ac^-1 (m <= 144, SPD) by Gauss-Jordan without pivoting on a symmetrised copy; one CTA, global memory
+__global__ void __launch_bounds__(256)
+k_coarse_invert(int m, const double* __restrict__ Ac, double* W /* m x 2m scratch */, double* __restrict__ Aci,
+                double* scal) {
+  const int n2 = 2 * m;
+  for (int e = threadIdx.x; e < m * m; e += 256) {
+    const int a = e / m, bq = e - a * m;
+    W[a * n2 + bq] = 0.5 * (Ac[a * m + bq] + Ac[bq * m + a]);
+    W[a * n2 + m + bq] = (a == bq) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < m; ++k) {
+    const double piv = W[k * n2 + k];
+    if (!(piv > 0.0) && threadIdx.x == 0) scal[S_ERR] = 2.0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n2; e += 256) W[k * n2 + e] /= piv;
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * n2; e += 256) {
+      const int a = e / n2, col = e - a * n2;
+      if (a != k && col != k) W[a * n2 + col] -= W[a * n2 + k] * W[k * n2 + col];
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < m; a += 256)
+      if (a != k) W[a * n2 + k] = 0.0;
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < m * m; e += 256) {
+    const int a = e / m, bq = e - a * m;
+    Aci[e] = 0.5 * (W[a * n2 + m + bq] + W[bq * n2 + m + a]);
+  }
+}
+
+__global__ void k_seq_inc(unsigned long long* seqp) { *seqp += 1; }
 
 __global__ void k_copy_cam_delta(int64_t n9, const double* __restrict__ xc, double* __restrict__ delta_c) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -960,6 +1066,21 @@ int lm_prepare(ba_handle* h) {
   ALLOC(S.d_Minv, ncams * 81);
   ALLOC(S.d_pcg, 6 * 9 * ncams);
   ALLOC(S.d_pcgpart, 2 * (int64_t)nblk(9 * ncams, VEC_ROWS));
+  {  // two-level preconditioner: clusters of whole vector-kernel CTAs (28 cameras each), at most 16 clusters
+    const int nvb = (int)nblk(9 * ncams, VEC_ROWS);
+    const int want = std::max(0, std::min(16, h->coarse_clusters));
+    S.ncl = 0;
+    if (want > 0 && ncams > 0) {
+      S.ctas_per_cluster = (nvb + want - 1) / want;
+      S.ncl = (nvb + S.ctas_per_cluster - 1) / S.ctas_per_cluster;
+    }
+    S.mc = 9 * S.ncl;
+    ALLOC(S.d_Ac, S.mc * S.mc);
+    ALLOC(S.d_Aci, S.mc * S.mc);
+    ALLOC(S.d_Wc, 2 * S.mc * S.mc);
+    ALLOC(S.d_yc, S.mc);
+    ALLOC(S.d_cpart, 9 * (int64_t)nvb);
+  }
   ALLOC(S.d_x, h->nvar());
   ALLOC(S.d_xt, h->nvar());
   ALLOC(S.d_delta, h->nvar());
@@ -996,7 +1117,7 @@ void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,
                   S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
-                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
+                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_Wc, S.d_yc, S.d_cpart, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
   for (void* p : ptrs) cudaFree(p);
   if (S.h_scal) cudaFreeHost(S.h_scal);
   if (S.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph));
@@ -1082,6 +1203,22 @@ struct Solver {
     if ((rc = check())) return rc;
     if ((rc = cam_pass<1>(S.d_Cr, 0))) return rc;
     k_cam_finish<<<nblk(ncams, 64), 64, 0, s>>>(ncams, lambda, S.d_Ug, S.d_Cr, S.d_H, S.d_Minv, b, S.d_scal);
+    if ((rc = check())) return rc;
+    return coarse_setup();
+  }
+  // Ac = P' S P column by column (9 ncl applications of S to the basis vectors of P), then Ac^-1
+  int coarse_setup() {
+    if (S.ncl == 0) return BA_OK;
+    int rc;
+    BA_CUDA(cudaMemsetAsync(S.d_scal + S_DONE, 0, sizeof(double), s));  // the product kernels honour S_DONE
+    const bool p2p = h->nranks > 1 && h->p2p.ready;
+    for (int col = 0; col < S.mc; ++col) {
+      k_coarse_basis<<<nblk(n9, 256), 256, 0, s>>>(n9, 9 * 28 * S.ctas_per_cluster, col, p);
+      if ((rc = s_product(false))) return rc;
+      k_coarse_restrict<<<S.ncl, 288, 0, s>>>(ncams, 28 * S.ctas_per_cluster, S.mc, col, q, S.d_Ac);
+      if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
+    }
+    k_coarse_invert<<<1, 256, 0, s>>>(S.mc, S.d_Ac, S.d_Wc, S.d_Aci, S.d_scal);
     return check();
   }
   int read_scalars() {
@@ -1089,8 +1226,8 @@ struct Solver {
     BA_CUDA(cudaStreamSynchronize(s));
     return BA_OK;
   }
-  // one PCG iteration: point-major pass, camera-major pass (+ allreduce over ranks), cluster update
-  int pcg_iteration(double tol, bool checks) {
+  // q = S p: point-major pass, camera-major pass, sum over ranks (fused over peer memory, or NCCL), finalise
+  int s_product(bool checks) {
     int rc;
     if (S.ntasks)
       k_point_solve<0><<<nblk(S.ntasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
@@ -1109,18 +1246,38 @@ struct Solver {
                                                                    n9);
     if (checks && (rc = check())) return rc;
     const int nvb = (int)nblk(n9, VEC_ROWS);
-    double* ppq = S.d_pcgpart;
-    double* prz = S.d_pcgpart + nvb;
     if (p2p) {
       // the sum over ranks is fused into the kernel that consumes it (peer loads over NVLink)
-      k_pcg_q<true><<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, ppq, S.d_scal, P.d_mail, P.d_flags, P.d_seq,
+      k_pcg_q<true><<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, S.d_pcgpart, S.d_scal, P.d_mail, P.d_flags, P.d_seq,
                                                  h->nranks, h->rank);
     } else {
       if ((rc = allreduce_sum(h, q, (size_t)n9))) return rc;
-      k_pcg_q<false><<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, ppq, S.d_scal, nullptr, nullptr, nullptr, 1, 0);
+      k_pcg_q<false><<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, S.d_pcgpart, S.d_scal, nullptr, nullptr, nullptr, 1,
+                                                  0);
     }
-    k_pcg_xr<false><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, b, S.d_Minv, p, q, xc, r, z, ppq, prz, S.d_scal);
-    k_pcg_p<false><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol, p2p ? P.d_seq : nullptr);
+    return checks ? check() : BA_OK;
+  }
+  // the vector half of a PCG iteration (or of its initialisation)
+  template <bool INIT>
+  void pcg_vectors(double tol) {
+    const int nvb = (int)nblk(n9, VEC_ROWS);
+    double* ppq = S.d_pcgpart;
+    double* prz = S.d_pcgpart + nvb;
+    const bool coarse = S.ncl > 0;
+    const bool p2p = h->nranks > 1 && h->p2p.ready;
+    k_pcg_xr<INIT><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, b, S.d_Minv, p, q, xc, r, z, ppq, prz, S.d_scal,
+                                               coarse ? S.d_cpart : nullptr);
+    if (coarse)
+      k_pcg_coarse<<<1, 160, 0, s>>>(nvb, S.ctas_per_cluster, S.mc, S.d_cpart, S.d_Aci, S.d_yc, S.d_scal, INIT ? 1 : 0);
+    k_pcg_p<INIT><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol,
+                                              (!INIT && p2p) ? h->p2p.d_seq : nullptr, coarse ? S.d_yc : nullptr,
+                                              std::max(S.ctas_per_cluster, 1));
+  }
+  // one PCG iteration
+  int pcg_iteration(double tol, bool checks) {
+    int rc = s_product(checks);
+    if (rc) return rc;
+    pcg_vectors<false>(tol);
     return checks ? check() : BA_OK;
   }
   // block-Jacobi PCG on S dc = b; result in xc.  Convergence is decided on the device (S_DONE): the host
@@ -1130,13 +1287,7 @@ struct Solver {
   int pcg(double tol, int maxit, int* iters) {
     constexpr int PCG_POLL = 8;
     static const bool no_graph = getenv("BAGPU_NO_GRAPH") != nullptr || getenv("BAGPU_DEBUG_SYNC") != nullptr;
-    {
-      const int nvb = (int)nblk(n9, VEC_ROWS);
-      double* ppq = S.d_pcgpart;
-      double* prz = S.d_pcgpart + nvb;
-      k_pcg_xr<true><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, b, S.d_Minv, p, q, xc, r, z, ppq, prz, S.d_scal);
-      k_pcg_p<true><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol, nullptr);
-    }
+    pcg_vectors<true>(tol);
     int rc = check();
     if (rc) return rc;
     if (!no_graph && !S.pcg_graph_off && (!S.pcg_graph || S.pcg_graph_tol != tol)) {

@@ -142,6 +142,11 @@ class BALNLPModel:
             raise RuntimeError("model is closed")
         return self._h
 
+    def set_coarse_clusters(self, n: int):
+        """PCG preconditioner of the LM solve: block-Jacobi plus an additive coarse level over ``n`` camera
+        clusters (default 8, at most 16; 0 = plain block-Jacobi).  Changes iteration counts, not solutions."""
+        _lib.check(_lib.lib().ba_set_coarse_clusters(self.handle, int(n)), self.handle)
+
     # ---- NLPModels surface ---------------------------------------------------------------------
     def obj(self, x):
         """NLPModels.obj: identically 0 (src/BALNLPModels.jl:109)."""

@@ -247,3 +247,17 @@ def test_final_shape_on_one_gpu(ba, oracle):
     assert ba._lib.lib().ba_partition_observations(p.nobs, p.pnt_idx.ctypes.data_as(C.c_void_p), 8,
                                                    cuts.ctypes.data_as(C.c_void_p)) == 0
     assert np.diff(cuts).min() > 0.99 * p.nobs / 8 and np.diff(cuts).max() < 1.01 * p.nobs / 8
+
+
+def test_two_level_preconditioner_changes_iterations_not_the_step(ba, oracle):
+    # block-Jacobi + coarse level over camera clusters vs plain block-Jacobi: same solve, fewer PCG iterations
+    p = ba.synth.make_problem("ladybug-49")
+    m = _model(ba, p)
+    d_ref, dr2_ref = oracle.lm_step(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, 30.0)
+    out = {}
+    for n in (0, 2, 8):
+        m.set_coarse_clusters(n)
+        d, dr2, _, _, it = ba.lm_step(m, p.x0, 30.0, pcg_tol=1e-13, pcg_max_iter=2000)
+        assert _rel(d, d_ref) <= TOL and abs(dr2 - dr2_ref) <= TOL * dr2_ref
+        out[n] = it
+    assert out[2] <= out[0] and out[8] <= out[0]
