@@ -30,6 +30,9 @@
 
 namespace ba {
 
+#ifndef PS_MINBLOCKS
+#define PS_MINBLOCKS 5  // resident blocks per SM targeted by k_point_solve (A/B-tested)
+#endif
 constexpr int NV = 54;         // per-camera accumulators: 45 (symmetric 9x9) + 9
 constexpr int PT_THREADS = 128;
 constexpr int RED_THREADS = 1024;
@@ -498,7 +501,7 @@ __device__ __forceinline__ void pt_first(PtLane& L, const double* __restrict__ v
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(PT_THREADS, 5)
+__global__ void __launch_bounds__(PT_THREADS, PS_MINBLOCKS)
 k_point_solve(const int32_t* __restrict__ tstart, int64_t ntasks, const int32_t* __restrict__ cam_idx,
               const int32_t* __restrict__ pnt_idx, int64_t pnt0, int64_t nl, const double2* __restrict__ Jp,
               const double2* __restrict__ F, const double* __restrict__ vcam, const double* __restrict__ Vinv,

@@ -261,3 +261,18 @@ def test_two_level_preconditioner_changes_iterations_not_the_step(ba, oracle):
         assert _rel(d, d_ref) <= TOL and abs(dr2 - dr2_ref) <= TOL * dr2_ref
         out[n] = it
     assert out[2] <= out[0] and out[8] <= out[0]
+
+
+def test_points_seen_by_more_than_32_cameras(ba, oracle):
+    # the point-major pass packs whole points into warps; a point with more than 32 observations takes the
+    # multi-chunk path (one warp sweeps the point twice).  Parity of the step and of the trajectory there.
+    p = ba.synth.make_problem((40, 200, 4000))
+    deg = np.bincount(p.pnt_idx)[1:]
+    assert (deg > 32).sum() >= 1 and deg.max() <= 40
+    m = _model(ba, p)
+    d_ref, dr2_ref = oracle.lm_step(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, 100.0)
+    d, dr2, _, _, _ = ba.lm_step(m, p.x0, 100.0)
+    assert _rel(d, d_ref) <= TOL and abs(dr2 - dr2_ref) <= TOL * dr2_ref
+    st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=6)
+    ref = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, oracle.default_params(ite_max=6))
+    _compare_trajectories(st, ref, f_tol=1e-8)
