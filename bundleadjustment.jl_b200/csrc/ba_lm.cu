@@ -668,6 +668,8 @@ k_ls_dr(double2* __restrict__ dr, const double2* __restrict__ F, int64_t nl, dou
 // 13682 cameras; this version spreads the matrix reads over all SMs: profiles/r01_pcg_vector_*.]
 // ---------------------------------------------------------------------------------------------
 constexpr int VEC_THREADS = 256;
+constexpr int CDOF = 6;  // coarse unknowns per camera cluster: the pose components (r, t); adding k1, k2, f to the
+                       // coarse space does not reduce PCG iterations further (prototype: 165 vs 166)
 constexpr int VEC_ROWS = 252;  // 28 cameras x 9 rows per CTA
 
 __device__ __forceinline__ double row9(const double* __restrict__ M, const double* v, int64_t i) {
@@ -814,9 +816,10 @@ k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __r
 }
 
 // Coarse level of the two-level preconditioner  M^-1 = blkdiag(S_cc)^-1 + P Ac^-1 P':  P = piecewise-constant
-// interpolation from `ncl` clusters of consecutive cameras (9 coarse unknowns per cluster), Ac = P' S P.
+// interpolation of the pose components from `ncl` clusters of consecutive cameras (CDOF = 6 coarse unknowns per
+// cluster), Ac = P' S P.
 // rc = P' r from the per-CTA partials (a CTA never straddles clusters), yc = Ac^-1 rc, and r.(P yc) = rc.yc
-// for the r.z dot product.  One CTA; m = 9 ncl <= 144.
+// for the r.z dot product.  One CTA; m = CDOF ncl <= 144.
 __global__ void __launch_bounds__(160)
 k_pcg_coarse(int nvb, int ctas_per_cluster, int m, const double* __restrict__ cpart, const double* __restrict__ Aci,
              double* __restrict__ yc, double* scal, int init) {
@@ -824,7 +827,7 @@ k_pcg_coarse(int nvb, int ctas_per_cluster, int m, const double* __restrict__ cp
   if (!init && scal[S_DONE] != 0.0) return;
   const int a = threadIdx.x;
   if (a < m) {
-    const int I = a / 9, jj = a - 9 * I;
+    const int I = a / CDOF, jj = a - CDOF * I;
     const int b0 = I * ctas_per_cluster, b1 = min(nvb, b0 + ctas_per_cluster);
     double t = 0.0;
     for (int bb = b0; bb < b1; ++bb) t += cpart[bb * 9 + jj];
@@ -857,7 +860,10 @@ k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_p
   const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
   // coarse correction of this row: z_i = (Minv r)_i + (P yc)_i; its share of r.z is scal[S_RCY]
   double zc = 0.0;
-  if (yc && live) zc = yc[(blockIdx.x / ctas_per_cluster) * 9 + (int)(i % 9)];
+  if (yc && live) {
+    const int comp = (int)(i % 9);
+    if (comp < CDOF) zc = yc[(blockIdx.x / ctas_per_cluster) * CDOF + comp];
+  }
   if (INIT) {
     const double rz = sum_partials(part_rz, nparts, sh) + (yc ? scal[S_RCY] : 0.0);
     if (live) p[i] = z[i] + zc;
@@ -900,7 +906,7 @@ __global__ void __launch_bounds__(256)
 k_coarse_basis(int64_t n9, int rows_per_cluster, int col, double* __restrict__ v) {
   const int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x;
   if (i >= n9) return;
-  const int I = col / 9, j = col - 9 * I;
+  const int I = col / CDOF, j = col - CDOF * I;
   v[i] = ((int)(i / rows_per_cluster) == I && (int)(i % 9) == j) ? 1.0 : 0.0;
 }
 
@@ -915,10 +921,10 @@ k_coarse_restrict(int64_t ncams, int cams_per_cluster, int m, int col, const dou
   for (int64_t c = c0 + t; c < c1; c += 32) sum += q[c * 9 + jj];
   part[threadIdx.x] = sum;
   __syncthreads();
-  if (threadIdx.x < 9) {
+  if (threadIdx.x < CDOF) {
     double tot = 0.0;
     for (int u = 0; u < 32; ++u) tot += part[u * 9 + threadIdx.x];
-    Ac[(I * 9 + threadIdx.x) * m + col] = tot;
+    Ac[(I * CDOF + threadIdx.x) * m + col] = tot;
   }
 }
 
@@ -1071,13 +1077,13 @@ int lm_prepare(ba_handle* h) {
   ALLOC(S.d_pcgpart, 2 * (int64_t)nblk(9 * ncams, VEC_ROWS));
   {  // two-level preconditioner: clusters of whole vector-kernel CTAs (28 cameras each), at most 16 clusters
     const int nvb = (int)nblk(9 * ncams, VEC_ROWS);
-    const int want = std::max(0, std::min(16, h->coarse_clusters));
+    const int want = std::max(0, std::min(144 / CDOF, h->coarse_clusters));
     S.ncl = 0;
     if (want > 0 && ncams > 0) {
       S.ctas_per_cluster = (nvb + want - 1) / want;
       S.ncl = (nvb + S.ctas_per_cluster - 1) / S.ctas_per_cluster;
     }
-    S.mc = 9 * S.ncl;
+    S.mc = CDOF * S.ncl;
     ALLOC(S.d_Ac, S.mc * S.mc);
     ALLOC(S.d_Aci, S.mc * S.mc);
     ALLOC(S.d_Wc, 2 * S.mc * S.mc);
@@ -1209,7 +1215,7 @@ struct Solver {
     if ((rc = check())) return rc;
     return coarse_setup();
   }
-  // Ac = P' S P column by column (9 ncl applications of S to the basis vectors of P), then Ac^-1
+  // Ac = P' S P column by column (CDOF ncl applications of S to the basis vectors of P), then Ac^-1
   int coarse_setup() {
     if (S.ncl == 0) return BA_OK;
     int rc;
