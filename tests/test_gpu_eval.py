@@ -204,3 +204,21 @@ def test_model_from_bal_file(ba, oracle, tmp_path):
     assert np.array_equal(m.meta.x0, p.x0)
     assert_rel(m.cons(m.meta.x0), oracle.cons(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.npnts), TOL,
                scale=np.abs(p.pt2d).max())
+
+
+def test_profiling_switch_and_kernel_time(ba):
+    import ctypes as C
+    p = small_problem(ba, shape=(9, 300, 1500))
+    m = _model(ba, p)
+    L = ba._lib.lib()
+    ms = C.c_float()
+    m.cons_jac_coord_(p.x0)
+    assert L.ba_last_eval_ms(m.handle, C.byref(ms)) == ba._lib.BA_ERR_ARG     # profiling is off by default
+    assert b"ba_set_profiling" in L.ba_last_error(m.handle)
+    ba._lib.check(L.ba_set_profiling(m.handle, 1), m.handle)
+    cx, vals = m.cons_jac_coord_(p.x0)
+    ba._lib.check(L.ba_last_eval_ms(m.handle, C.byref(ms)), m.handle)
+    assert 0.0 < ms.value < 50.0
+    ba._lib.check(L.ba_set_profiling(m.handle, 0), m.handle)
+    cx2, vals2 = m.cons_jac_coord_(p.x0)
+    assert np.array_equal(cx, cx2) and np.array_equal(vals, vals2)   # same kernel with and without the events
