@@ -244,7 +244,7 @@ k_point_prep(const int32_t* __restrict__ pnt_idx, int64_t pnt0, int64_t nl, cons
 //   MODE 2: accumulate B' w (9)                         (Schur product)
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __launch_bounds__(PT_THREADS, MODE == 2 ? 4 : 1)
 k_cam_pass(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, int64_t nctasks,
            const int32_t* __restrict__ task_cam, const int32_t* __restrict__ cam_t0, int32_t* __restrict__ cam_cnt,
            const int32_t* __restrict__ cperm, const int32_t* __restrict__ pntc, int64_t nl,
@@ -272,26 +272,44 @@ k_cam_pass(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, i
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
   const int e = tend[task];
-  for (int pos = tbeg[task] + lane; pos < e; pos += 32) {
+  // Software pipeline: the gathers of the next observation (index -> point sector / w: two dependent L2 round
+  // trips) are issued before the ~300 FP64 operations of the current one, so they overlap.
+  struct Obs {
+    double2 xa, xb, wk;
+    double t00, t01, t11;
+  };
+  auto fetch = [&](int pos, Obs& ob) {
     const int k = __ldg(cperm + pos);
     const int p = __ldg(pntc + pos);
-    const double2 xa = __ldg(x4 + 2 * (int64_t)p), xb = __ldg(x4 + 2 * (int64_t)p + 1);  // one 32-byte sector
-    double2 wk = make_double2(0.0, 0.0);
-    double t00 = 1.0, t01 = 0.0, t11 = 1.0;
+    ob.xa = __ldg(x4 + 2 * (int64_t)p);  // one 32-byte sector
+    ob.xb = __ldg(x4 + 2 * (int64_t)p + 1);
+    ob.t00 = 1.0;
+    ob.t01 = 0.0;
+    ob.t11 = 1.0;
     if (MODE == 0) {
       const double2 f = F[k];
-      wk = make_double2(-f.x, -f.y);
+      ob.wk = make_double2(-f.x, -f.y);
     } else {
-      wk = w[k];
+      ob.wk = w[k];
       if (MODE == 1) {
-        t00 = T[k];
-        t01 = T[nl + k];
-        t11 = T[2 * nl + k];
+        ob.t00 = T[k];
+        ob.t01 = T[nl + k];
+        ob.t11 = T[2 * nl + k];
       }
     }
+  };
+  int pos = tbeg[task] + lane;
+  Obs cur, nxt;
+  if (pos < e) fetch(pos, cur);
+  for (; pos < e; pos += 32) {
+    const bool more = pos + 32 < e;
+    if (more) fetch(pos + 32, nxt);
+    const double2 xa = cur.xa, xb = cur.xb, wk = cur.wk;
+    const double t00 = cur.t00, t01 = cur.t01, t11 = cur.t11;
+    if (more) cur = nxt;
     const double X[3] = {xa.x, xa.y, xb.x};
     ObsBlock o;
-    eval_block(X, cam, 0.0, 0.0, o);
+    eval_block<false>(X, cam, 0.0, 0.0, o);  // camera part only
     double2 B[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) B[j] = make_double2(nan0(o.B[j]), nan0(o.B[9 + j]));

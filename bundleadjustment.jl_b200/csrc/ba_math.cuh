@@ -190,7 +190,10 @@ __device__ __forceinline__ void apply_T(double alpha, double beta, double gamma,
   o2 = (alpha * v2 + d * k2) - gamma * (k0 * v1 - k1 * v0);
 }
 
-// Fast path: residual + 2x12 Jacobian block from the camera record.
+// Fast path: residual + 2x12 Jacobian block from the camera record.  WANT_A = false skips the point part
+// A = G R (callers that only need the camera part B; B is then bit-identical to the full evaluation, and a
+// non-finite A implies a non-finite G, which the t-columns of B carry, so the fallback triggers the same way).
+template <bool WANT_A = true>
 __device__ __forceinline__ void eval_block(const double X[3], const double* __restrict__ cam,
                                            double ox, double oy, ObsBlock& o) {
   Proj q;
@@ -209,8 +212,10 @@ __device__ __forceinline__ void eval_block(const double X[3], const double* __re
   const double g00 = -iz * j00, g01 = -iz * j01, g02 = -iz * (j00 * u + j01 * v);
   const double g10 = g01, g11 = -iz * j11, g12 = -iz * (j01 * u + j11 * v);
   // A = G R : row i = (R^T g_i)^T
-  apply_T(c, 1.0 - c, s, k0, k1, k2, g00, g01, g02, o.A[0], o.A[1], o.A[2]);
-  apply_T(c, 1.0 - c, s, k0, k1, k2, g10, g11, g12, o.A[3], o.A[4], o.A[5]);
+  if (WANT_A) {
+    apply_T(c, 1.0 - c, s, k0, k1, k2, g00, g01, g02, o.A[0], o.A[1], o.A[2]);
+    apply_T(c, 1.0 - c, s, k0, k1, k2, g10, g11, g12, o.A[3], o.A[4], o.A[5]);
+  }
   // dF/dr = G (-[Y]x N) : row i = (N^T (Y x g_i))^T
   apply_T(a, 1.0 - a, g, k0, k1, k2, Y1 * g02 - Y2 * g01, Y2 * g00 - Y0 * g02, Y0 * g01 - Y1 * g00,
           o.B[0], o.B[1], o.B[2]);
@@ -224,8 +229,10 @@ __device__ __forceinline__ void eval_block(const double X[3], const double* __re
   // (t-columns carry G, k1/k2/f-columns carry JP3, X/r-columns carry R and N).  Rare: redo
   // the block the reference's way so zeros, NaN -> 0 and surviving Infs land identically.
   bool bad = false;
+  if (WANT_A) {
 #pragma unroll
-  for (int i = 0; i < 6; ++i) bad |= nonfinite(o.A[i]);
+    for (int i = 0; i < 6; ++i) bad |= nonfinite(o.A[i]);
+  }
 #pragma unroll
   for (int i = 0; i < 18; ++i) bad |= nonfinite(o.B[i]);
   if (bad) {
