@@ -919,6 +919,123 @@ k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_p
   }
 }
 
+// Small camera systems (9 ncams <= 1152 rows, i.e. up to 128 cameras): the whole vector half of a PCG iteration
+// -- k_pcg_q, k_pcg_xr, k_pcg_coarse and k_pcg_p above -- as ONE CTA, the two dot products being block sums.
+// Measured: LadyBug-49 (441 rows) 20.9 vs 34.6 us per PCG iteration; from ~2000 rows on the single CTA is the
+// slower choice (Trafalgar-257, 2313 rows: 50.7 vs 46.6 us), hence the threshold.
+constexpr int SMALL_THREADS = 1024;
+template <bool P2P>
+__global__ void __launch_bounds__(SMALL_THREADS)
+k_pcg_small(int64_t n9, int64_t ncams, const double* __restrict__ H, const double* __restrict__ Minv, double* p,
+            double* q, double* xc, double* r, double* z, double* scal, double tol, double* const* __restrict__ mails,
+            unsigned long long* const* __restrict__ flags, unsigned long long* seqp, int nranks, int rank,
+            const double* __restrict__ Aci, int m, int cams_per_cluster) {
+  __shared__ double sh[SMALL_THREADS / 32];
+  __shared__ double rc[144], yy[144];
+  __shared__ int timed_out;
+  if (scal[S_DONE] != 0.0) return;
+  const double rz = scal[S_RZN], rz0 = scal[S_RZ0];
+  unsigned long long seq = 0;
+  if (P2P) {  // same handshake as k_pcg_q<true>
+    seq = *seqp;
+    if (threadIdx.x == 0) timed_out = 0;
+    if (threadIdx.x < nranks) {
+      __threadfence_system();
+      st_release_sys(flags[threadIdx.x] + rank, seq + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < nranks) {
+      const unsigned long long* f = flags[rank] + threadIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) < seq + 1) {
+        if (clock64() - t0 > 4000000000ll) {
+          timed_out = 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if (timed_out) {
+      if (threadIdx.x == 0) {
+        scal[S_DONE] = 2.0;
+        scal[S_ERR] = 3.0;
+      }
+      return;
+    }
+  }
+  double pq = 0.0;
+  for (int64_t i = threadIdx.x; i < n9; i += SMALL_THREADS) {
+    double sum;
+    if (P2P) {
+      const int64_t off = (int64_t)(seq & 1ull) * n9 + i;
+      sum = 0.0;
+      for (int rr = 0; rr < nranks; ++rr) sum += ld_volatile_f64(mails[rr] + off);
+    } else {
+      sum = q[i];
+    }
+    const double qi = row9(H, p, i) - sum;
+    q[i] = qi;
+    pq += p[i] * qi;
+  }
+  pq = block_sum<SMALL_THREADS>(pq, sh);
+  if (!(pq > 0.0)) {
+    if (threadIdx.x == 0) {
+      scal[S_DONE] = 2.0;
+      scal[S_PQ] = pq;
+    }
+    return;
+  }
+  const double alpha = rz / pq;
+  for (int64_t i = threadIdx.x; i < n9; i += SMALL_THREADS) {
+    xc[i] += alpha * p[i];
+    r[i] -= alpha * q[i];
+  }
+  __syncthreads();
+  double rzb = 0.0;
+  for (int64_t i = threadIdx.x; i < n9; i += SMALL_THREADS) {
+    const double zi = row9(Minv, r, i);
+    z[i] = zi;
+    rzb += r[i] * zi;
+  }
+  double rcy = 0.0;
+  if (m > 0) {  // coarse level: rc = P' r, yc = Ac^-1 rc
+    if (threadIdx.x < m) {
+      const int I = threadIdx.x / CDOF, jj = threadIdx.x - CDOF * I;
+      const int64_t c0 = (int64_t)I * cams_per_cluster, c1 = min((long long)ncams, (long long)(c0 + cams_per_cluster));
+      double t = 0.0;
+      for (int64_t c = c0; c < c1; ++c) t += r[c * 9 + jj];
+      rc[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < m) {
+      double t = 0.0;
+      for (int bq = 0; bq < m; ++bq) t += Aci[threadIdx.x * m + bq] * rc[bq];
+      yy[threadIdx.x] = t;
+    }
+    __syncthreads();
+    for (int bq = 0; bq < m; ++bq) rcy += rc[bq] * yy[bq];
+  }
+  const double rzn = block_sum<SMALL_THREADS>(rzb, sh) + rcy;
+  const double beta = rzn / rz;
+  for (int64_t i = threadIdx.x; i < n9; i += SMALL_THREADS) {
+    double zc = 0.0;
+    if (m > 0) {
+      const int comp = (int)(i % 9);
+      if (comp < CDOF) zc = yy[(int)((i / 9) / cams_per_cluster) * CDOF + comp];
+    }
+    p[i] = (z[i] + zc) + beta * p[i];
+  }
+  if (threadIdx.x == 0) {
+    const double rel = sqrt(rzn / rz0);
+    scal[S_RZN] = rzn;
+    scal[S_PQ] = pq;
+    scal[S_ITERS] += 1.0;
+    scal[S_REL] = rel;
+    if (!(rel > tol)) scal[S_DONE] = (rel == rel) ? 1.0 : 2.0;
+    if (P2P) *seqp += 1;
+  }
+}
+
 // coarse-space setup: basis vector (cluster I, component j) of P, restriction of S v, inversion of Ac
 __global__ void __launch_bounds__(256)
 k_coarse_basis(int64_t n9, int rows_per_cluster, int col, double* __restrict__ v) {
@@ -1254,7 +1371,7 @@ struct Solver {
     return BA_OK;
   }
   // q = S p: point-major pass, camera-major pass, sum over ranks (fused over peer memory, or NCCL), finalise
-  int s_product(bool checks) {
+  int s_product(bool checks, bool finalize = true) {
     int rc;
     if (S.ntasks)
       k_point_solve<0><<<nblk(S.ntasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
@@ -1273,12 +1390,13 @@ struct Solver {
                                                                    n9);
     if (checks && (rc = check())) return rc;
     const int nvb = (int)nblk(n9, VEC_ROWS);
+    if (!p2p && (rc = allreduce_sum(h, q, (size_t)n9))) return rc;
+    if (!finalize) return BA_OK;  // the fused small-system kernel finishes the product itself
     if (p2p) {
       // the sum over ranks is fused into the kernel that consumes it (peer loads over NVLink)
       k_pcg_q<true><<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, S.d_pcgpart, S.d_scal, P.d_mail, P.d_flags, P.d_seq,
                                                  h->nranks, h->rank);
     } else {
-      if ((rc = allreduce_sum(h, q, (size_t)n9))) return rc;
       k_pcg_q<false><<<nvb, VEC_THREADS, 0, s>>>(n9, S.d_H, p, q, S.d_pcgpart, S.d_scal, nullptr, nullptr, nullptr, 1,
                                                   0);
     }
@@ -1302,9 +1420,22 @@ struct Solver {
   }
   // one PCG iteration
   int pcg_iteration(double tol, bool checks) {
-    int rc = s_product(checks);
+    static const int64_t small_max = getenv("BAGPU_VEC_SMALL_MAX") ? atoll(getenv("BAGPU_VEC_SMALL_MAX")) : 1152;
+    const bool small = n9 <= small_max;
+    int rc = s_product(checks, !small);
     if (rc) return rc;
-    pcg_vectors<false>(tol);
+    if (small) {
+      const ba_p2p_state& P = h->p2p;
+      const int cpc = 28 * std::max(S.ctas_per_cluster, 1);
+      if (h->nranks > 1 && P.ready)
+        k_pcg_small<true><<<1, SMALL_THREADS, 0, s>>>(n9, ncams, S.d_H, S.d_Minv, p, q, xc, r, z, S.d_scal, tol, P.d_mail,
+                                                       P.d_flags, P.d_seq, h->nranks, h->rank, S.d_Aci, S.mc, cpc);
+      else
+        k_pcg_small<false><<<1, SMALL_THREADS, 0, s>>>(n9, ncams, S.d_H, S.d_Minv, p, q, xc, r, z, S.d_scal, tol, nullptr,
+                                                        nullptr, nullptr, 1, 0, S.d_Aci, S.mc, cpc);
+    } else {
+      pcg_vectors<false>(tol);
+    }
     return checks ? check() : BA_OK;
   }
   // block-Jacobi PCG on S dc = b; result in xc.  Convergence is decided on the device (S_DONE): the host
