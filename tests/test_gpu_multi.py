@@ -10,8 +10,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, small_max):
     sys.path.insert(0, ROOT)
+    if small_max is not None:
+        os.environ["BAGPU_VEC_SMALL_MAX"] = small_max  # read once by libbagpu: selects the PCG vector path
     import torch
     import torch.distributed as dist
     import bundleadjustment.jl_b200 as ba
@@ -36,7 +38,8 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_gpu_lm_matches_one_gpu(ba):
+@pytest.mark.parametrize("small_max", [None, "0"])  # fused single-CTA vector kernel / multi-CTA kernels
+def test_two_gpu_lm_matches_one_gpu(ba, small_max):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two CUDA devices")
@@ -44,7 +47,7 @@ def test_two_gpu_lm_matches_one_gpu(ba):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port + (7 if small_max else 0), q, small_max)) for r in range(2)]
     for pr in procs:
         pr.start()
     got = q.get(timeout=600)
