@@ -81,6 +81,7 @@ SYMBOLS = {
     "ba_comm_init": (C.c_int, [_vp, _vp]),
     "ba_comm_ipc_export": (C.c_int, [_vp, _vp]),
     "ba_comm_ipc_import": (C.c_int, [_vp, _vp]),
+    "ba_comm_ipc_disable": (C.c_int, [_vp]),
 }
 
 _lib = None

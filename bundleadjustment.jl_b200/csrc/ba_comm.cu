@@ -179,4 +179,13 @@ int ba_comm_ipc_import(ba_handle* h, const uint8_t* handles) {
   return BA_OK;
 }
 
+// Back to NCCL for the per-iteration exchange (all ranks must agree: call it on every rank or on none).
+int ba_comm_ipc_disable(ba_handle* h) {
+  if (!h) return BA_ERR_ARG;
+  h->p2p.ready = false;
+  if (h->lm.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(h->lm.pcg_graph));
+  h->lm.pcg_graph = nullptr;
+  return BA_OK;
+}
+
 }  // extern "C"

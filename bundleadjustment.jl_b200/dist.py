@@ -31,14 +31,25 @@ def init_comm(model, group=None, p2p=True):
     arr = (C.c_uint8 * 128)(*t.cpu().tolist())
     _lib.check(L.ba_comm_init(model.handle, arr), model.handle)
     if p2p:
-        # peer-memory mailboxes for the per-PCG-iteration exchange: swap CUDA IPC handles (64 bytes per rank)
-        mine = (C.c_uint8 * 64)()
-        _lib.check(L.ba_comm_ipc_export(model.handle, mine), model.handle)
+        # peer-memory mailboxes for the per-PCG-iteration exchange: swap CUDA IPC handles (64 bytes per rank).
+        # Every rank must end up on the same path, so success is agreed on collectively.
+        ok = 1
+        try:
+            mine = (C.c_uint8 * 64)()
+            _lib.check(L.ba_comm_ipc_export(model.handle, mine), model.handle)
+        except _lib.BAError:
+            ok, mine = 0, (C.c_uint8 * 64)()
+        on_gpu = dist.get_backend(group) == "nccl"
         t = torch.tensor(list(mine), dtype=torch.uint8)
-        if dist.get_backend(group) == "nccl":
-            t = t.cuda(model.device)
+        t = t.cuda(model.device) if on_gpu else t
         parts = [torch.empty_like(t) for _ in range(model.nranks)]
         dist.all_gather(parts, t, group=group)
-        flat = [b for q in parts for b in q.cpu().tolist()]
-        allh = (C.c_uint8 * (64 * model.nranks))(*flat)
-        _lib.check(L.ba_comm_ipc_import(model.handle, allh), model.handle)
+        if ok:
+            flat = [b for q in parts for b in q.cpu().tolist()]
+            allh = (C.c_uint8 * (64 * model.nranks))(*flat)
+            ok = 1 if L.ba_comm_ipc_import(model.handle, allh) == 0 else 0
+        flag = torch.tensor([ok], dtype=torch.int32)
+        flag = flag.cuda(model.device) if on_gpu else flag
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            _lib.check(L.ba_comm_ipc_disable(model.handle), model.handle)  # NCCL for everybody

@@ -156,6 +156,9 @@ BA_API int ba_comm_init(ba_handle* h, const uint8_t id128[128]);
  * ncclAllReduce.  The other, per-LM-iteration collectives stay on NCCL. */
 BA_API int ba_comm_ipc_export(ba_handle* h, uint8_t handle64[64]);
 BA_API int ba_comm_ipc_import(ba_handle* h, const uint8_t* handles64_by_rank);
+/* Return to NCCL for that exchange, e.g. when ba_comm_ipc_import failed on some rank (peer access
+ * unavailable): every rank must take the same path, so call it on all ranks or on none. */
+BA_API int ba_comm_ipc_disable(ba_handle* h);
 
 #ifdef __cplusplus
 }
