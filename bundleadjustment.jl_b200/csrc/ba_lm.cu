@@ -1,5 +1,6 @@
 // ba_lm.cu -- device-resident Levenberg-Marquardt (K5-K8): block JtJ / Jtr assembly, Schur
-// complement onto the reduced camera system, block-Jacobi PCG, back-substitution, and the LM loop.
+// complement onto the reduced camera system, PCG (block-Jacobi + a coarse level over camera clusters),
+// back-substitution, and the LM loop.
 //
 // Reference semantics: src/lm.jl:15-418 (control flow, kept decision for decision) with the damped
 // solve  (J'J + lambda I) delta = -J'r  that src/lm.jl:61-100,138-152,175-229 obtains from
@@ -18,7 +19,11 @@
 // sector each; measured faster on B200 than streaming 144 B/obs, profiles/r01_pcg_*).  All sums are two-level and
 // ordered (per-task partials, then a fixed-order gather by the last task of a camera): results are
 // reproducible run to run and no FP64 atomics are used.  The camera-sized vector updates of PCG are
-// three small multi-CTA kernels; its dot products are per-CTA partials summed in fixed order.
+// a few small multi-CTA kernels (one fused CTA for up to 128 cameras); its dot products are per-CTA partials
+// summed in fixed order.  Eight PCG iterations form one CUDA graph; convergence is decided on the device.
+// Sharded over ranks (one process per GPU), the sum over ranks inside the PCG iteration is fused into the
+// kernel that consumes it and read from the peers' IPC-mapped memory over NVLink (ba_comm.cu); the
+// per-LM-iteration collectives use NCCL.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -1306,13 +1311,12 @@ struct Solver {
 #define reduce_to(...) reduce_to_at(__LINE__, __VA_ARGS__)
   // camera-major pass + ordered gather (+ allreduce over ranks) into out (ncams x nacc)
   template <int MODE>
-  int cam_pass(double* out, int check_done) {
+  int cam_pass(double* out) {
     constexpr int nacc = (MODE == 2) ? 9 : NV;
     if (S.nctasks)
       k_cam_pass<MODE><<<nblk(S.nctasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
           S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_ctask_cam, S.d_cam_t0, S.d_cam_cnt, S.d_cperm, S.d_pntc, nl,
           h->d_camtab, S.d_x4, S.d_F, S.d_w, S.d_T, S.d_taskpart, out, S.d_scal, nullptr, nullptr, n9);
-    (void)check_done;
     if (S.nempty)
       k_zero_cams<<<nblk((int64_t)S.nempty * nacc, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, nacc, out,
                                                                      nullptr, nullptr, n9);
@@ -1333,7 +1337,7 @@ struct Solver {
     if (rc) return rc;
     k_point_assemble<<<npb, PT_THREADS, 0, s>>>(S.d_pstart, npl, nl, S.d_Jp, S.d_F, S.d_V, S.d_gp, S.d_part);
     if ((rc = reduce_to(npb, 1, S_GP2))) return rc;
-    if ((rc = cam_pass<0>(S.d_Ug, 0))) return rc;
+    if ((rc = cam_pass<0>(S.d_Ug))) return rc;
     k_gc_norm<<<1, RED_THREADS, 0, s>>>(ncams, S.d_Ug, S.d_scal);
     if ((rc = check())) return rc;
     return allreduce_sum(h, S.d_scal + S_F2, 2);
@@ -1345,7 +1349,7 @@ struct Solver {
     if (rc) return rc;
     k_point_prep<<<nblk(nl, PT_THREADS), PT_THREADS, 0, s>>>(h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_Vinv, S.d_wp, S.d_w, S.d_T);
     if ((rc = check())) return rc;
-    if ((rc = cam_pass<1>(S.d_Cr, 0))) return rc;
+    if ((rc = cam_pass<1>(S.d_Cr))) return rc;
     k_cam_finish<<<nblk(ncams, 64), 64, 0, s>>>(ncams, lambda, S.d_Ug, S.d_Cr, S.d_H, S.d_Minv, b, S.d_scal);
     if ((rc = check())) return rc;
     return coarse_setup();
