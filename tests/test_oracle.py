@@ -211,3 +211,28 @@ def test_lm_linesearch_variant_runs(oracle, ba):
                           oracle.default_params(linesearch=1))
     assert res.status != "exception"
     assert res.objective < 0.05 * res.log[0]["f"]
+
+
+# ---- column normalisation (src/lma_aux.jl:98-178; reference test runtests.jl:31-88) -----------------
+def test_normalize_variants_solve_the_same_system(oracle, ba):
+    # normalize = :J / :A only equilibrate columns (J D^-1, -lambda D^-2, delta = y / d), so the
+    # LM step is the one of (J'J + lambda I) delta = -J'r for every `normalize` argument.  That is why the
+    # device path can accept the argument and solve one system.
+    p = small_problem(ba)
+    lam = 30.0
+    rows, cols = oracle.jac_structure(p.cam_idx, p.pnt_idx, p.npnts)
+    vals = oracle.jac_coord(p.cam_idx, p.pnt_idx, p.x0, p.npnts)
+    r = oracle.cons(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.npnts)
+    m, n = 2 * p.nobs, p.nvar
+    J = np.zeros((m, n))
+    np.add.at(J, (rows - 1, cols - 1), vals)
+    ref = np.linalg.solve(J.T @ J + lam * np.eye(n), -J.T @ r)
+    d = np.linalg.norm(J, axis=0)                       # normalize_ldl!: norms of the columns of J
+    d[d == 0] = 1.0
+    Jn = J / d
+    K = np.block([[np.eye(m), Jn], [Jn.T, -np.diag(lam / d ** 2)]])   # [[I J D^-1]; [. -lambda D^-2]]
+    xr = np.linalg.solve(K, np.concatenate([-r, np.zeros(n)]))
+    delta = xr[m:] / d                                   # denormalize_vect!
+    assert np.linalg.norm(delta - ref) <= 1e-10 * np.linalg.norm(ref)
+    dr = xr[:m]                                          # = -(r + J delta): the model residual of the LDL path
+    assert np.linalg.norm(dr + r + J @ ref) <= 1e-9 * np.linalg.norm(r)
