@@ -6,6 +6,7 @@
 // single-GPU entry point works) in processes that never touch NCCL; inside a torch process the
 // already-loaded libnccl.so.2 is reused.
 #include <dlfcn.h>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -110,13 +111,16 @@ int ba_comm_init(ba_handle* h, const uint8_t id128[128]) {
     h->comm = nullptr;
     return BA_ERR_COMM;
   }
-  // NCCL sets its channels up lazily inside the first collective (hundreds of ms): pay that here, not in
-  // the first LM iteration
+  // NCCL sets up channels / protocols lazily inside the first collective of each size class (tens to hundreds
+  // of ms): pay that here, at the message sizes the solver uses, not in the first LM iteration
+  const size_t sizes[3] = {8, 9 * (size_t)h->ncams, 54 * (size_t)h->ncams};
   double* warm = nullptr;
-  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&warm), 1024 * sizeof(double)));
-  BA_CUDA(cudaMemsetAsync(warm, 0, 1024 * sizeof(double), h->stream));
-  int wrc = ba::allreduce_sum(h, warm, 1024);
-  if (!wrc) wrc = ba::allreduce_sum(h, warm, 8);
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&warm), std::max<size_t>(sizes[2], 8) * sizeof(double)));
+  BA_CUDA(cudaMemsetAsync(warm, 0, std::max<size_t>(sizes[2], 8) * sizeof(double), h->stream));
+  int wrc = BA_OK;
+  for (int rep = 0; rep < 2 && !wrc; ++rep)
+    for (size_t n : sizes)
+      if (n && !wrc) wrc = ba::allreduce_sum(h, warm, n);
   BA_CUDA(cudaStreamSynchronize(h->stream));
   cudaFree(warm);
   return wrc;
