@@ -258,8 +258,11 @@ int ba_jtprod_dev(ba_handle* h, const double* x, const double* v, double* Jtv) {
   BA_CUDA(cudaSetDevice(h->device));
   int rc = refresh_cams(h, x);
   if (rc) return rc;
-  ba::launch_jtprod(h, x, h->d_camtab, v, Jtv, h->stream);
+  // point-major problems: camera sums by the ordered camera-major pass (deterministic, no atomics on hot
+  // cameras); otherwise L2 atomics
+  ba::launch_jtprod(h, x, h->d_camtab, v, Jtv, !h->sorted, h->stream);
   BA_CUDA(cudaGetLastError());
+  if (h->sorted && (rc = ba::lm_jtprod_cams(h, x, v, Jtv + 3 * h->npnts))) return rc;
   if (h->nranks > 1 && h->comm) return ba::allreduce_sum(h, Jtv, (size_t)h->nvar());
   return BA_OK;
 }

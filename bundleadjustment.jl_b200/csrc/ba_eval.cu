@@ -174,7 +174,10 @@ k_jprod(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx
 }
 
 // J'v: point-side sums are reduced inside the warp over runs of equal point id (observations
-// are point-major in BAL order) before one atomic per run; camera-side sums go to L2 atomics.
+// are point-major in BAL order) before one atomic per run.  Camera-side sums: CAMS = true sends them to L2
+// atomics (any observation order); CAMS = false leaves them to the ordered camera-major pass of ba_lm.cu
+// (point-major problems: deterministic, and no contention on cameras with 10^4 observations).
+template <bool CAMS>
 __global__ void __launch_bounds__(128)
 k_jtprod(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
          const double2* __restrict__ pt2d, const double* __restrict__ x, int64_t npnts,
@@ -198,9 +201,11 @@ k_jtprod(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_id
     eval_block(X, cam, ob.x, ob.y, o);
 #pragma unroll
     for (int i = 0; i < 3; ++i) gp[i] = nan0(o.A[i]) * w.x + nan0(o.A[3 + i]) * w.y;
-    double* jc = Jtv + 3 * npnts + (int64_t)c * 9;
+    if (CAMS) {
+      double* jc = Jtv + 3 * npnts + (int64_t)c * 9;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) atomicAdd(jc + i, nan0(o.B[i]) * w.x + nan0(o.B[9 + i]) * w.y);
+      for (int i = 0; i < 9; ++i) atomicAdd(jc + i, nan0(o.B[i]) * w.x + nan0(o.B[9 + i]) * w.y);
+    }
   }
   // segmented inclusive scan over runs of equal p
   const int pprev = __shfl_up_sync(0xffffffffu, p, 1);
@@ -280,13 +285,17 @@ void launch_jprod(const ba_handle* h, const double* x, const double* camtab, con
 }
 
 void launch_jtprod(const ba_handle* h, const double* x, const double* camtab, const double* v, double* Jtv,
-                   cudaStream_t s) {
+                   bool with_cameras, cudaStream_t s) {
   const int64_t n = h->nobs_l();
   cudaMemsetAsync(Jtv, 0, sizeof(double) * (size_t)h->nvar(), s);
   if (n == 0) return;
   const unsigned blocks = (unsigned)((n + 127) / 128);
-  k_jtprod<<<blocks, 128, 0, s>>>(h->d_cam, h->d_pnt, h->d_pt2d, x, h->npnts, camtab,
-                                 reinterpret_cast<const double2*>(v), Jtv, n);
+  if (with_cameras)
+    k_jtprod<true><<<blocks, 128, 0, s>>>(h->d_cam, h->d_pnt, h->d_pt2d, x, h->npnts, camtab,
+                                         reinterpret_cast<const double2*>(v), Jtv, n);
+  else
+    k_jtprod<false><<<blocks, 128, 0, s>>>(h->d_cam, h->d_pnt, h->d_pt2d, x, h->npnts, camtab,
+                                          reinterpret_cast<const double2*>(v), Jtv, n);
 }
 
 }  // namespace ba

@@ -134,9 +134,12 @@ void launch_jac_structure(const ba_handle* h, int64_t* rows, int64_t* cols, cuda
 void launch_jprod(const ba_handle* h, const double* x, const double* camtab, const double* v, double* Jv,
                   cudaStream_t s);
 void launch_jtprod(const ba_handle* h, const double* x, const double* camtab, const double* v, double* Jtv,
-                   cudaStream_t s);
+                   bool with_cameras, cudaStream_t s);
 // ---- ba_lm.cu -------------------------------------------------------------------------------
 int lm_prepare(ba_handle* h);
+// camera part of J(x)'v by the ordered camera-major pass (needs point-major observations; h->d_camtab must
+// hold the records of x): Jtv_cams = sum_k B_k' v_k, 9 per camera
+int lm_jtprod_cams(ba_handle* h, const double* x, const double* v, double* Jtv_cams);
 void lm_release(ba_handle* h);
 // ---- ba_comm.cu -----------------------------------------------------------------------------
 int allreduce_sum(ba_handle* h, double* buf, size_t n);

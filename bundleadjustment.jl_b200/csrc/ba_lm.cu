@@ -1262,6 +1262,26 @@ int lm_prepare(ba_handle* h) {
   return BA_OK;
 }
 
+int lm_jtprod_cams(ba_handle* h, const double* x, const double* v, double* out) {
+  int rc = lm_prepare(h);
+  if (rc) return rc;
+  ba_lm_state& S = h->lm;
+  cudaStream_t s = h->stream;
+  const int64_t nl = h->nobs_l(), n9 = 9 * h->ncams;
+  BA_CUDA(cudaMemsetAsync(S.d_scal + S_DONE, 0, sizeof(double), s));  // the pass honours the PCG done flag
+  k_pad_points<<<(unsigned)std::max<int64_t>((h->npnts_l() + 255) / 256, 1), 256, 0, s>>>(x, h->pnt0, h->pnt1, S.d_x4);
+  if (S.nctasks)
+    k_cam_pass<2><<<(unsigned)((S.nctasks + PT_THREADS / 32 - 1) / (PT_THREADS / 32)), PT_THREADS, 0, s>>>(
+        S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_ctask_cam, S.d_cam_t0, S.d_cam_cnt, S.d_cperm, S.d_pntc, nl,
+        h->d_camtab, S.d_x4, S.d_F, reinterpret_cast<const double2*>(v), S.d_T, S.d_taskpart, out, S.d_scal, nullptr,
+        nullptr, n9);
+  if (S.nempty)
+    k_zero_cams<<<(unsigned)((S.nempty * 9 + 255) / 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, 9, out, nullptr,
+                                                                      nullptr, n9);
+  BA_CUDA(cudaGetLastError());
+  return BA_OK;
+}
+
 void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,

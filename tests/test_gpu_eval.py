@@ -222,3 +222,14 @@ def test_profiling_switch_and_kernel_time(ba):
     ba._lib.check(L.ba_set_profiling(m.handle, 0), m.handle)
     cx2, vals2 = m.cons_jac_coord_(p.x0)
     assert np.array_equal(cx, cx2) and np.array_equal(vals, vals2)   # same kernel with and without the events
+
+
+def test_jtprod_camera_part_is_reproducible(ba):
+    # point-major problems: the camera side of J'v is an ordered camera-major sum (no FP64 atomics)
+    p = small_problem(ba, shape=(9, 300, 1500))
+    m = _model(ba, p)
+    w = np.random.default_rng(3).normal(size=2 * p.nobs)
+    a = m.jtprod_(p.x0, w)
+    for _ in range(3):
+        b = m.jtprod_(p.x0, w)
+        assert np.array_equal(a[3 * p.npnts:], b[3 * p.npnts:])
