@@ -165,6 +165,11 @@ def test_unsorted_observations_are_rejected_for_lm_only(ba, oracle):
     m = ba.BALNLPModel(cam, pnt, pt, p.x0, p.ncams, p.npnts, p.nobs)
     cx = m.cons(p.x0)  # the operator surface works in any order
     assert np.allclose(cx, oracle.cons(cam, pnt, pt, p.x0, p.npnts), rtol=0, atol=1e-9)
+    # J'v in arbitrary order takes the atomics path
+    rows, cols = oracle.jac_structure(cam, pnt, p.npnts)
+    vals = oracle.jac_coord(cam, pnt, p.x0, p.npnts)
+    w = np.random.default_rng(9).normal(size=2 * p.nobs)
+    assert _rel(m.jtprod_(p.x0, w), oracle.mul_sparse(cols, rows, vals, w, p.nvar)) <= TOL
     with pytest.raises(ba.BAError) as e:
         ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False)
     assert e.value.code == ba._lib.BA_ERR_UNSORTED
