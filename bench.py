@@ -90,6 +90,15 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """Cores this process may use.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, which would
+    quietly turn the CPU arm into a single-thread run; the oracle takes the thread count explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     """CPU arm: the restatement of the reference (oracle/ba_oracle.c) on the host cores.  cons! uses all
     threads (Threads.@threads, src/BALNLPModels.jl:45); jac_coord! is capped at 3 like the reference
@@ -99,7 +108,7 @@ def run_reference(args):
     import bundleadjustment.jl_b200.synth as synth  # host-only generator
     from oracle import oracle as O
     p = synth.make_problem(args.workload)
-    nt = O.max_threads()
+    nt = host_threads()
     cx = np.empty(2 * p.nobs)
     vals = np.empty(24 * p.nobs)
 
@@ -128,7 +137,7 @@ def run_reference(args):
 
 def cpu_baseline(p, workload, budget_s=12.0):
     from oracle import oracle as O
-    nt = O.max_threads()
+    nt = host_threads()
     cx = np.empty(2 * p.nobs)
     vals = np.empty(24 * p.nobs)
     O.cons_jac(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.npnts, nt, cx, vals)  # warm-up / page-in
