@@ -70,6 +70,21 @@ int allreduce_sum(ba_handle* h, double* buf, size_t n) {
   return BA_OK;
 }
 
+// exact (order-independent) sum of 64-bit integers over the ranks
+int allreduce_sum_i64(ba_handle* h, long long* buf, size_t n) {
+  if (h->nranks == 1 || n == 0) return BA_OK;
+  if (!h->comm) {
+    h->err = "sharded handle used before ba_comm_init";
+    return BA_ERR_COMM;
+  }
+  const int rc = api().allreduce(buf, buf, n, 4 /* ncclInt64 */, NCCL_SUM, h->comm, h->stream);
+  if (rc != 0) {
+    h->err = std::string("ncclAllReduce: ") + (api().errstr ? api().errstr(rc) : "error");
+    return BA_ERR_COMM;
+  }
+  return BA_OK;
+}
+
 void comm_release(ba_handle* h) {
   if (h->comm && api().ok) api().destroy(h->comm);
   h->comm = nullptr;

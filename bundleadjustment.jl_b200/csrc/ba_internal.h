@@ -64,6 +64,8 @@ struct ba_lm_state {
   double* d_Wc = nullptr;     // mc x 2mc scratch of the inversion
   double* d_yc = nullptr;     // mc: coarse correction of the current residual
   double* d_cpart = nullptr;  // 9 per vector-kernel CTA: restriction partials
+  long long* d_Acq = nullptr; // mc x mc: fixed-point sums of the Schur part of P' S P (order-independent)
+  double* d_cdiag = nullptr;  // mc: sqrt of the diagonal of P' (U + lambda I) P (normalisation of d_Acq)
   // ---- iterates -------------------------------------------------------------------------------
   double* d_x = nullptr;      // current iterate (nvar; only this rank's point slice + cameras are live)
   double* d_xt = nullptr;     // trial iterate
@@ -115,7 +117,7 @@ struct ba_handle {
   int64_t* d_cols = nullptr;
   cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (profiling only)
   bool profile = false;
-  int coarse_clusters = 8;   // two-level PCG preconditioner: target number of camera clusters (0 = off)
+  int coarse_clusters = 16;  // two-level PCG preconditioner: target number of camera clusters (0 = off)
   ba_lm_state lm;
   ncclComm* comm = nullptr;
   ba_p2p_state p2p;
@@ -143,5 +145,6 @@ int lm_jtprod_cams(ba_handle* h, const double* x, const double* v, double* Jtv_c
 void lm_release(ba_handle* h);
 // ---- ba_comm.cu -----------------------------------------------------------------------------
 int allreduce_sum(ba_handle* h, double* buf, size_t n);
+int allreduce_sum_i64(ba_handle* h, long long* buf, size_t n);
 void comm_release(ba_handle* h);
 }  // namespace ba

@@ -1041,6 +1041,96 @@ k_pcg_small(int64_t n9, int64_t ncams, const double* __restrict__ H, const doubl
   }
 }
 
+// Direct assembly of the coarse matrix  Ac = P'HP - sum_p G_p Vinv_p G_p',  G_p[I] = sum_{k in p, cam in I} B_k[:, :6]' A_k:
+// one pass over the points instead of CDOF*ncl applications of S.  Sums are accumulated in 64-bit fixed
+// point (entries normalised by sqrt(diag P'HP), scale 2^40), first per CTA in shared memory, then globally:
+// integer addition is associative, so the result does not depend on the order of the atomics (or of the
+// ranks) and the preconditioner -- hence the PCG iterates -- stay bit-reproducible.
+constexpr int NCL_MAX = 24;
+constexpr double CQ_SCALE = 1099511627776.0;  // 2^40
+
+// d[a] = sqrt(sum_{c in I} H_c[jj][jj]) for a = (I, jj): one thread per coarse unknown
+__global__ void k_coarse_diag(int64_t ncams, int cams_per_cluster, int m, const double* __restrict__ H,
+                              double* __restrict__ d) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= m) return;
+  const int I = a / CDOF, jj = a - CDOF * I;
+  const int64_t c0 = (int64_t)I * cams_per_cluster, c1 = min((long long)ncams, (long long)(c0 + cams_per_cluster));
+  double t = 0.0;
+  for (int64_t c = c0; c < c1; ++c) t += H[c * 81 + jj * 10];
+  d[a] = sqrt(t);
+}
+
+__global__ void __launch_bounds__(256)
+k_coarse_assemble(const int32_t* __restrict__ pstart, int64_t npl, int64_t nl, const int32_t* __restrict__ cam_idx,
+                  const double2* __restrict__ Jp, const double* __restrict__ Vinv, int cams_per_cluster, int m,
+                  const double* __restrict__ d, unsigned long long* __restrict__ Acq) {
+  extern __shared__ unsigned long long sacc[];  // m x m
+  for (int e = threadIdx.x; e < m * m; e += 256) sacc[e] = 0ull;
+  __syncthreads();
+  for (int64_t p = blockIdx.x * (int64_t)256 + threadIdx.x; p < npl; p += (int64_t)gridDim.x * 256) {
+    const int k0 = pstart[p], k1 = pstart[p + 1];
+    if (k0 == k1) continue;
+    const double* vi = Vinv + p * 6;
+    const double V[3][3] = {{vi[0], vi[1], vi[2]}, {vi[1], vi[3], vi[4]}, {vi[2], vi[4], vi[5]}};
+    int n = 0, ids[NCL_MAX];
+    double G[NCL_MAX][18];
+    for (int k = k0; k < k1; ++k) {
+      const int I = __ldg(cam_idx + k) / cams_per_cluster;
+      int e = n - 1;
+      while (e >= 0 && ids[e] != I) --e;  // cameras ascend within a point in BAL order: normally the last entry
+      if (e < 0) {
+        e = n++;
+        ids[e] = I;
+        for (int q = 0; q < 18; ++q) G[e][q] = 0.0;
+      }
+      const double2 a0 = Jp[k], a1 = Jp[nl + k], a2 = Jp[2 * nl + k];
+#pragma unroll
+      for (int a = 0; a < CDOF; ++a) {
+        const double2 b = Jp[(int64_t)(3 + a) * nl + k];
+        G[e][a * 3 + 0] += b.x * a0.x + b.y * a0.y;
+        G[e][a * 3 + 1] += b.x * a1.x + b.y * a1.y;
+        G[e][a * 3 + 2] += b.x * a2.x + b.y * a2.y;
+      }
+    }
+    for (int e1 = 0; e1 < n; ++e1) {
+      double T[CDOF][3];
+      for (int a = 0; a < CDOF; ++a)
+        for (int t = 0; t < 3; ++t)
+          T[a][t] = (G[e1][a * 3] * V[0][t] + G[e1][a * 3 + 1] * V[1][t]) + G[e1][a * 3 + 2] * V[2][t];
+      for (int e2 = 0; e2 < n; ++e2)
+        for (int a = 0; a < CDOF; ++a) {
+          const int row = ids[e1] * CDOF + a;
+          for (int b = 0; b < CDOF; ++b) {
+            const int col = ids[e2] * CDOF + b;
+            const double v = (T[a][0] * G[e2][b * 3] + T[a][1] * G[e2][b * 3 + 1]) + T[a][2] * G[e2][b * 3 + 2];
+            const long long qv = __double2ll_rn(v / (d[row] * d[col]) * CQ_SCALE);
+            atomicAdd(&sacc[row * m + col], (unsigned long long)qv);
+          }
+        }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < m * m; e += 256)
+    if (sacc[e]) atomicAdd(&Acq[e], sacc[e]);
+}
+
+// Ac = P'HP - dequantised Schur part
+__global__ void __launch_bounds__(256)
+k_coarse_finish(int64_t ncams, int cams_per_cluster, int m, const double* __restrict__ H, const double* __restrict__ d,
+                const long long* __restrict__ Acq, double* __restrict__ Ac) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= m * m) return;
+  const int row = e / m, col = e - row * m;
+  const int I = row / CDOF, a = row - CDOF * I, J = col / CDOF, b = col - CDOF * J;
+  double t = 0.0;
+  if (I == J) {
+    const int64_t c0 = (int64_t)I * cams_per_cluster, c1 = min((long long)ncams, (long long)(c0 + cams_per_cluster));
+    for (int64_t c = c0; c < c1; ++c) t += H[c * 81 + a * 9 + b];
+  }
+  Ac[e] = t - ((double)Acq[e] / CQ_SCALE) * (d[row] * d[col]);
+}
+
 // coarse-space setup: basis vector (cluster I, component j) of P, restriction of S v, inversion of Ac
 __global__ void __launch_bounds__(256)
 k_coarse_basis(int64_t n9, int rows_per_cluster, int col, double* __restrict__ v) {
@@ -1229,6 +1319,8 @@ int lm_prepare(ba_handle* h) {
     ALLOC(S.d_Wc, 2 * S.mc * S.mc);
     ALLOC(S.d_yc, S.mc);
     ALLOC(S.d_cpart, 9 * (int64_t)nvb);
+    ALLOC(S.d_Acq, S.mc * S.mc);
+    ALLOC(S.d_cdiag, S.mc);
   }
   ALLOC(S.d_x, h->nvar());
   ALLOC(S.d_xt, h->nvar());
@@ -1286,7 +1378,7 @@ void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,
                   S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
-                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_Wc, S.d_yc, S.d_cpart, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
+                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_Wc, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
   for (void* p : ptrs) cudaFree(p);
   if (S.h_scal) cudaFreeHost(S.h_scal);
   if (S.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph));
@@ -1374,10 +1466,31 @@ struct Solver {
     if ((rc = check())) return rc;
     return coarse_setup();
   }
-  // Ac = P' S P column by column (CDOF ncl applications of S to the basis vectors of P), then Ac^-1
+  // Ac = P' S P, then Ac^-1.  Default: direct assembly in one pass over the points (k_coarse_assemble);
+  // BAGPU_COARSE_PRODUCTS=1: column by column with CDOF ncl applications of S (the cross-check).
   int coarse_setup() {
     if (S.ncl == 0) return BA_OK;
     int rc;
+    static const bool by_products = getenv("BAGPU_COARSE_PRODUCTS") != nullptr;
+    if (!by_products) {
+      const int cpc = 28 * S.ctas_per_cluster, m = S.mc;
+      k_coarse_diag<<<nblk(m, 64), 64, 0, s>>>(ncams, cpc, m, S.d_H, S.d_cdiag);
+      BA_CUDA(cudaMemsetAsync(S.d_Acq, 0, sizeof(long long) * (size_t)(m * m), s));
+      const size_t smem = sizeof(unsigned long long) * (size_t)(m * m);
+      static bool attr_set = false;
+      if (!attr_set) {
+        BA_CUDA(cudaFuncSetAttribute(k_coarse_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 144 * 8));
+        attr_set = true;
+      }
+      const unsigned grid = (unsigned)std::min<int64_t>(nblk(npl, 256), 148 * 2);
+      k_coarse_assemble<<<grid, 256, smem, s>>>(S.d_pstart, npl, nl, h->d_cam, S.d_Jp, S.d_Vinv, cpc, m, S.d_cdiag,
+                                                reinterpret_cast<unsigned long long*>(S.d_Acq));
+      if ((rc = check())) return rc;
+      if ((rc = allreduce_sum_i64(h, S.d_Acq, (size_t)(m * m)))) return rc;
+      k_coarse_finish<<<nblk((int64_t)m * m, 256), 256, 0, s>>>(ncams, cpc, m, S.d_H, S.d_cdiag, S.d_Acq, S.d_Ac);
+      k_coarse_invert<<<1, 256, 0, s>>>(m, S.d_Ac, S.d_Wc, S.d_Aci, S.d_scal);
+      return check();
+    }
     BA_CUDA(cudaMemsetAsync(S.d_scal + S_DONE, 0, sizeof(double), s));  // the product kernels honour S_DONE
     const bool p2p = h->nranks > 1 && h->p2p.ready;
     for (int col = 0; col < S.mc; ++col) {

@@ -144,7 +144,7 @@ class BALNLPModel:
 
     def set_coarse_clusters(self, n: int):
         """PCG preconditioner of the LM solve: block-Jacobi plus an additive coarse level over ``n`` camera
-        clusters (default 8, at most 16; 0 = plain block-Jacobi).  Changes iteration counts, not solutions."""
+        clusters (default 16, at most 24; 0 = plain block-Jacobi).  Changes iteration counts, not solutions."""
         _lib.check(_lib.lib().ba_set_coarse_clusters(self.handle, int(n)), self.handle)
 
     # ---- NLPModels surface ---------------------------------------------------------------------

@@ -92,7 +92,7 @@ BA_API int ba_jtprod_dev(ba_handle* h, const double* x_dev, const double* v_dev,
 BA_API int ba_sync(ba_handle* h);
 /* PCG preconditioner: block-Jacobi (exact 9x9 diagonal blocks of the reduced camera system) plus an additive
  * coarse level over `n` clusters of consecutive cameras (piecewise-constant interpolation of the six pose
- * components, n <= 24; default 8; 0 = plain block-Jacobi).  Changes the iteration count, not the solution. */
+ * components, n <= 24; default 16; 0 = plain block-Jacobi).  Changes the iteration count, not the solution. */
 BA_API int ba_set_coarse_clusters(ba_handle* h, int n);
 /* Profiling: with it on, the per-observation evaluation kernel (k_eval: cons!/jac_coord!/fused) is
  * bracketed by CUDA events on the handle's stream and ba_last_eval_ms returns its device time alone
