@@ -92,3 +92,44 @@ def test_named_shapes_match_baseline_configs(ba):
     assert S["dubrovnik-356"] == (356, 226730, 1255268)
     assert S["venice-1778"] == (1778, 993923, 5001946)
     assert S["final-13682"] == (13682, 4456117, 28987644)
+
+
+def test_struct_layouts_match_the_header(ba, tmp_path):
+    """The ctypes mirrors (and the isbits structs of julia/BALGPUModels.jl, which list the same fields in the
+    same order) must have the layout a C compiler gives include/bagpu.h."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "bagpu.h"
+#define P(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+  printf("ba_lm_params %zu\n", sizeof(ba_lm_params));
+  printf("ba_lm_row %zu\n", sizeof(ba_lm_row));
+  printf("ba_lm_stats %zu\n", sizeof(ba_lm_stats));
+  P(ba_lm_params, restol); P(ba_lm_params, nu_d); P(ba_lm_params, lambda); P(ba_lm_params, ite_max);
+  P(ba_lm_params, linesearch); P(ba_lm_params, pcg_max_iter); P(ba_lm_params, pcg_tol);
+  P(ba_lm_row, iter); P(ba_lm_row, rho); P(ba_lm_row, accepted); P(ba_lm_row, ntimes);
+  P(ba_lm_stats, status); P(ba_lm_stats, iter); P(ba_lm_stats, objective); P(ba_lm_stats, pcg_iters_total);
+  P(ba_lm_stats, t_backsub_ms);
+  return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.rsplit(" ", 1) for line in subprocess.check_output([str(exe)], text=True).strip().splitlines())
+    L = ba._lib
+    assert int(got["ba_lm_params"]) == C.sizeof(L.LMParams)
+    assert int(got["ba_lm_row"]) == C.sizeof(L.LMRow)
+    assert int(got["ba_lm_stats"]) == C.sizeof(L.LMStats)
+    for cname, cls, names in (("ba_lm_params", L.LMParams, {"restol": "restol", "nu_d": "nu_d", "lambda": "lam",
+                                                             "ite_max": "ite_max", "linesearch": "linesearch",
+                                                             "pcg_max_iter": "pcg_max_iter", "pcg_tol": "pcg_tol"}),
+                              ("ba_lm_row", L.LMRow, {"iter": "iter", "rho": "rho", "accepted": "accepted",
+                                                       "ntimes": "ntimes"}),
+                              ("ba_lm_stats", L.LMStats, {"status": "status", "iter": "iter", "objective": "objective",
+                                                           "pcg_iters_total": "pcg_iters_total",
+                                                           "t_backsub_ms": "t_backsub_ms"})):
+        for cf, pf in names.items():
+            assert int(got["%s.%s" % (cname, cf)]) == getattr(cls, pf).offset, (cname, cf)
