@@ -133,3 +133,15 @@ int main(void) {
                                                            "t_backsub_ms": "t_backsub_ms"})):
         for cf, pf in names.items():
             assert int(got["%s.%s" % (cname, cf)]) == getattr(cls, pf).offset, (cname, cf)
+
+
+def test_plain_c_consumer(ba, tmp_path):
+    import subprocess
+    lib = ba._lib.LIB_PATH
+    exe = tmp_path / "abi_driver"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi_driver.c"), "-o", str(exe), lib,
+                           "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "abi ok" in out.stdout
