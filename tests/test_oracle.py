@@ -236,3 +236,22 @@ def test_normalize_variants_solve_the_same_system(oracle, ba):
     assert np.linalg.norm(delta - ref) <= 1e-10 * np.linalg.norm(ref)
     dr = xr[:m]                                          # = -(r + J delta): the model residual of the LDL path
     assert np.linalg.norm(dr + r + J @ ref) <= 1e-9 * np.linalg.norm(r)
+
+
+def test_ldl_oracle_agrees_with_an_independent_sparse_solver(oracle, ba):
+    # the restated ldl_aux.jl against SuperLU on the same augmented SQD system [[I J];[J' -lambda I]]
+    # (plays the role of the reference's `A \\ b` checks, test/runtests.jl:111-128, at a realistic size)
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    p = ba.synth.make_problem((20, 1000, 5000))
+    lam = 75.0
+    rows, cols = oracle.jac_structure(p.cam_idx, p.pnt_idx, p.npnts)
+    vals = oracle.jac_coord(p.cam_idx, p.pnt_idx, p.x0, p.npnts)
+    r = oracle.cons(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.npnts)
+    m, n = 2 * p.nobs, p.nvar
+    J = sp.csr_matrix((vals, (rows - 1, cols - 1)), shape=(m, n))
+    K = sp.bmat([[sp.identity(m), J], [J.T, -lam * sp.identity(n)]], format="csc")
+    xr = spla.splu(K).solve(np.concatenate([-r, np.zeros(n)]))
+    delta, dr2 = oracle.lm_step(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, lam)
+    assert np.linalg.norm(delta - xr[m:]) <= 1e-9 * np.linalg.norm(xr[m:])
+    assert abs(dr2 - 0.5 * float(xr[:m] @ xr[:m])) <= 1e-10 * dr2
