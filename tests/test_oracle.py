@@ -243,7 +243,7 @@ def test_ldl_oracle_agrees_with_an_independent_sparse_solver(oracle, ba):
     # (plays the role of the reference's `A \\ b` checks, test/runtests.jl:111-128, at a realistic size)
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
-    p = ba.synth.make_problem((20, 1000, 5000))
+    p = ba.synth.make_problem((16, 600, 3000))
     lam = 75.0
     rows, cols = oracle.jac_structure(p.cam_idx, p.pnt_idx, p.npnts)
     vals = oracle.jac_coord(p.cam_idx, p.pnt_idx, p.x0, p.npnts)
