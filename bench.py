@@ -99,6 +99,17 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference(args):
     """CPU arm: the restatement of the reference (oracle/ba_oracle.c) on the host cores.  cons! uses all
     threads (Threads.@threads, src/BALNLPModels.jl:45); jac_coord! is capped at 3 like the reference
@@ -127,7 +138,7 @@ def run_reference(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": args.workload, "ncams": p.ncams, "npnts": p.npnts, "nobs": p.nobs},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "port", "cpu_model": cpu_model(),
                             "sample": "full %s problem per step; cons! on %d threads, jac_coord! on %d "
                                       "(reference caps it at 3)" % (args.workload, nt, min(nt, 3))},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -152,7 +163,7 @@ def cpu_baseline(p, workload, budget_s=12.0):
     t1 = time.perf_counter()
     O.cons_jac(p.cam_idx[:n1], p.pnt_idx[:n1], p.pt2d[:2 * n1], p.x0, p.npnts, 1, cx[:2 * n1], vals[:24 * n1])
     dt1 = time.perf_counter() - t1
-    return {"value": p.nobs / dt / 1e6, "unit": UNIT, "cores": nt, "kind": "port",
+    return {"value": p.nobs / dt / 1e6, "unit": UNIT, "cores": nt, "kind": "port", "cpu_model": cpu_model(),
             "sample": "%d full passes of the %s problem (cons! + jac_coord!, all %d threads for both)"
                       % (reps, workload, nt),
             "single_thread_value": n1 / dt1 / 1e6}
