@@ -333,7 +333,8 @@ def main():
                        "l2": "per-step footprint %.0f MB, outputs rotate over %d buffers (> L2)" % (
                            step_bytes / 1e6, ring)},
             "e2e": {"value": p.nobs / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "pcie_GB/s": (h2d + d2h) / e2e_s / 1e9,
+                    "note": "bound by the device-to-host copy of vals (192 B/obs) over PCIe, not by the kernel",
                     "api": "ba_residual_jac (host pointers, pinned), per rank"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "ba::k_eval<true,true>", "achieved": achieved, "peak": peak,
