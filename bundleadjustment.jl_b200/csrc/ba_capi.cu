@@ -4,6 +4,7 @@
 #include <cstring>
 #include <new>
 #include "ba_internal.h"
+#include "ba_ritz.h"
 
 namespace {
 
@@ -348,6 +349,26 @@ int ba_jtprod(ba_handle* h, const double* x, const double* v, double* Jtv) {
   if ((rc = ba_jtprod_dev(h, h->d_x, h->d_w, h->d_v))) return rc;
   BA_CUDA(cudaMemcpyAsync(Jtv, h->d_v, sizeof(double) * (size_t)h->nvar(), cudaMemcpyDeviceToHost, h->stream));
   BA_CUDA(cudaStreamSynchronize(h->stream));
+  return BA_OK;
+}
+
+// ---- host-only numerical helpers of the PCG deflation space, exported for CPU unit tests --------------
+int ba_dbg_tridiag_eig(const double* alpha, const double* beta, int32_t m, double* evals, double* evecs_colmajor) {
+  if (!alpha || !beta || m < 1 || !evals || !evecs_colmajor) return BA_ERR_ARG;
+  std::vector<double> d, e, V;
+  ba::lanczos_tridiagonal(alpha, beta, m, d, e);
+  if (!ba::tridiag_eig(d, e, m, V)) return BA_ERR_NUMERIC;
+  std::copy(d.begin(), d.end(), evals);
+  std::copy(V.begin(), V.end(), evecs_colmajor);
+  return BA_OK;
+}
+
+int ba_dbg_select_columns(const double* gram_rowmajor, int32_t n, int32_t k, double tol, double* coeff_rowmajor,
+                          int32_t* kept) {
+  if (!gram_rowmajor || n < 1 || k < 1 || !coeff_rowmajor || !kept) return BA_ERR_ARG;
+  std::vector<double> G(gram_rowmajor, gram_rowmajor + (size_t)n * n), Cm;
+  *kept = ba::select_orthonormal(G, n, k, tol, Cm);
+  std::copy(Cm.begin(), Cm.begin() + (size_t)n * (*kept), coeff_rowmajor);
   return BA_OK;
 }
 

@@ -1,0 +1,134 @@
+// ba_ritz.h -- host-side small dense algebra for the PCG deflation space: eigenpairs of the Lanczos
+// tridiagonal that a PCG solve produces for free, and the selection of a well-conditioned subset of the
+// Ritz vectors (converged Ritz values come with "ghost" copies).  Header-only, no CUDA: unit-tested on
+// the CPU through ba_dbg_tridiag_smallest / ba_dbg_select_columns (tests/test_host.py).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace ba {
+
+// Lanczos tridiagonal of preconditioned CG (Z~' S Z~ with Z~_j = z_j / sqrt(r_j.z_j)):
+//   T_jj = 1/a_j + b_{j-1}/a_{j-1},   T_{j,j+1} = -sqrt(b_j)/a_j      (a = alpha, b = beta of CG)
+inline void lanczos_tridiagonal(const double* alpha, const double* beta, int m, std::vector<double>& d,
+                                std::vector<double>& e) {
+  d.assign((size_t)m, 0.0);
+  e.assign((size_t)m, 0.0);  // e[j] couples j and j+1; e[m-1] unused
+  for (int j = 0; j < m; ++j) {
+    d[(size_t)j] = 1.0 / alpha[j] + (j ? beta[j - 1] / alpha[j - 1] : 0.0);
+    if (j + 1 < m) e[(size_t)j] = -std::sqrt(beta[j]) / alpha[j];
+  }
+}
+
+// Eigen-decomposition of a symmetric tridiagonal matrix (implicit QL with Wilkinson shifts, the classic
+// tql2 scheme).  d: diagonal (m) -> eigenvalues ascending; e: off-diagonal (e[j] couples j, j+1);
+// V (m x m, column-major, V[i + m*j]) -> eigenvectors in columns.  Returns false if an eigenvalue fails to
+// converge in 60 sweeps.
+inline bool tridiag_eig(std::vector<double>& d, std::vector<double> e, int m, std::vector<double>& V) {
+  V.assign((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) V[(size_t)i + (size_t)m * i] = 1.0;
+  if (m == 0) return true;
+  e[(size_t)m - 1] = 0.0;
+  for (int l = 0; l < m; ++l) {
+    int iter = 0, mm;
+    do {
+      for (mm = l; mm < m - 1; ++mm) {
+        const double dd = std::fabs(d[(size_t)mm]) + std::fabs(d[(size_t)mm + 1]);
+        if (std::fabs(e[(size_t)mm]) <= 2.220446049250313e-16 * dd) break;
+      }
+      if (mm != l) {
+        if (iter++ == 60) return false;
+        double g = (d[(size_t)l + 1] - d[(size_t)l]) / (2.0 * e[(size_t)l]);
+        double r = std::hypot(g, 1.0);
+        g = d[(size_t)mm] - d[(size_t)l] + e[(size_t)l] / (g + (g >= 0 ? std::fabs(r) : -std::fabs(r)));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i;
+        for (i = mm - 1; i >= l; --i) {
+          double f = s * e[(size_t)i], b = c * e[(size_t)i];
+          r = std::hypot(f, g);
+          e[(size_t)i + 1] = r;
+          if (r == 0.0) {
+            d[(size_t)i + 1] -= p;
+            e[(size_t)mm] = 0.0;
+            break;
+          }
+          s = f / r;
+          c = g / r;
+          g = d[(size_t)i + 1] - p;
+          r = (d[(size_t)i] - g) * s + 2.0 * c * b;
+          p = s * r;
+          d[(size_t)i + 1] = g + p;
+          g = c * r - b;
+          for (int k = 0; k < m; ++k) {
+            double* vk = &V[(size_t)k];
+            f = vk[(size_t)m * (i + 1)];
+            vk[(size_t)m * (i + 1)] = s * vk[(size_t)m * i] + c * f;
+            vk[(size_t)m * i] = c * vk[(size_t)m * i] - s * f;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[(size_t)l] -= p;
+        e[(size_t)l] = g;
+        e[(size_t)mm] = 0.0;
+      }
+    } while (mm != l);
+  }
+  // sort ascending, permuting the eigenvector columns
+  std::vector<int> idx((size_t)m);
+  for (int i = 0; i < m; ++i) idx[(size_t)i] = i;
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return d[(size_t)a] < d[(size_t)b]; });
+  std::vector<double> d2((size_t)m), V2((size_t)m * m);
+  for (int j = 0; j < m; ++j) {
+    d2[(size_t)j] = d[(size_t)idx[(size_t)j]];
+    std::copy(V.begin() + (size_t)m * idx[(size_t)j], V.begin() + (size_t)m * (idx[(size_t)j] + 1),
+              V2.begin() + (size_t)m * j);
+  }
+  d.swap(d2);
+  V.swap(V2);
+  return true;
+}
+
+// Given the Gram matrix G (n x n, row-major) of n candidate vectors y_1..y_n (in preference order), pick up to
+// k of them whose orthogonalised remainder is at least `tol` of their norm (Gram-Schmidt in coefficient
+// space, i.e. Cholesky with a fixed pivot order and rejection), and return C (n x kept, row-major) such that
+// the columns of Y C are orthonormal.  Returns the number kept.
+inline int select_orthonormal(const std::vector<double>& G, int n, int k, double tol, std::vector<double>& C) {
+  std::vector<std::vector<double>> cols;  // coefficient vectors (length n) of the kept orthonormal vectors
+  for (int j = 0; j < n && (int)cols.size() < k; ++j) {
+    std::vector<double> c((size_t)n, 0.0);
+    c[(size_t)j] = 1.0;
+    const double njj = G[(size_t)j * n + j];
+    if (!(njj > 0.0)) continue;
+    for (int pass = 0; pass < 2; ++pass)  // twice is enough
+      for (const auto& u : cols) {
+        // <u, c>_G
+        double dot = 0.0;
+        for (int a = 0; a < n; ++a) {
+          if (u[(size_t)a] == 0.0) continue;
+          double t = 0.0;
+          for (int b = 0; b < n; ++b) t += G[(size_t)a * n + b] * c[(size_t)b];
+          dot += u[(size_t)a] * t;
+        }
+        for (int a = 0; a < n; ++a) c[(size_t)a] -= dot * u[(size_t)a];
+      }
+    double nrm2 = 0.0;
+    for (int a = 0; a < n; ++a) {
+      if (c[(size_t)a] == 0.0) continue;
+      double t = 0.0;
+      for (int b = 0; b < n; ++b) t += G[(size_t)a * n + b] * c[(size_t)b];
+      nrm2 += c[(size_t)a] * t;
+    }
+    if (!(nrm2 > tol * tol * njj)) continue;  // a ghost copy (or numerically dependent): drop it
+    const double inv = 1.0 / std::sqrt(nrm2);
+    for (auto& v : c) v *= inv;
+    cols.push_back(c);
+  }
+  const int kept = (int)cols.size();
+  C.assign((size_t)n * std::max(kept, 1), 0.0);
+  for (int j = 0; j < kept; ++j)
+    for (int a = 0; a < n; ++a) C[(size_t)a * kept + j] = cols[(size_t)j][(size_t)a];
+  return kept;
+}
+
+}  // namespace ba

@@ -160,6 +160,17 @@ BA_API int ba_comm_ipc_import(ba_handle* h, const uint8_t* handles64_by_rank);
  * unavailable): every rank must take the same path, so call it on all ranks or on none. */
 BA_API int ba_comm_ipc_disable(ba_handle* h);
 
+/* ---- host-only helpers of the PCG deflation space (no GPU; exported so that they can be unit-tested) ------ */
+/* Eigenpairs of the Lanczos tridiagonal defined by the CG coefficients alpha[0..m), beta[0..m-1):
+ * evals ascending (m), evecs column-major (m x m). */
+BA_API int ba_dbg_tridiag_eig(const double* alpha, const double* beta, int32_t m, double* evals,
+                              double* evecs_colmajor);
+/* From the Gram matrix (n x n, row-major) of n candidate vectors in preference order keep up to k that are
+ * numerically independent (remainder >= tol of their norm) and return coefficients (n x kept, row-major) that
+ * orthonormalise them. */
+BA_API int ba_dbg_select_columns(const double* gram_rowmajor, int32_t n, int32_t k, double tol,
+                                 double* coeff_rowmajor, int32_t* kept);
+
 #ifdef __cplusplus
 }
 #endif

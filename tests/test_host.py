@@ -145,3 +145,62 @@ def test_plain_c_consumer(ba, tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "abi ok" in out.stdout
+
+
+def test_lanczos_tridiagonal_eigensolver_matches_numpy(ba):
+    # CG coefficients of a real PCG run define T; its eigenpairs are the Ritz pairs of the deflation space
+    rng = np.random.default_rng(0)
+    n = 60
+    A = rng.normal(size=(n, n))
+    A = A @ A.T + n * np.eye(n)
+    b = rng.normal(size=n)
+    x, r = np.zeros(n), b.copy()
+    p, rz = r.copy(), r @ r
+    al, be = [], []
+    for _ in range(25):
+        q = A @ p
+        a = rz / (p @ q)
+        x += a * p
+        r -= a * q
+        rzn = r @ r
+        al.append(a)
+        be.append(rzn / rz)
+        p = r + be[-1] * p
+        rz = rzn
+    m = len(al)
+    al, be = np.array(al), np.array(be)
+    T = np.zeros((m, m))
+    for j in range(m):
+        T[j, j] = 1 / al[j] + (be[j - 1] / al[j - 1] if j else 0.0)
+        if j + 1 < m:
+            T[j, j + 1] = T[j + 1, j] = -np.sqrt(be[j]) / al[j]
+    w_ref, _ = np.linalg.eigh(T)
+    w = np.empty(m)
+    V = np.empty(m * m)
+    rc = ba._lib.lib().ba_dbg_tridiag_eig(al.ctypes.data_as(C.c_void_p), be.ctypes.data_as(C.c_void_p), m,
+                                          w.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert np.allclose(w, w_ref, rtol=1e-12, atol=1e-12 * abs(w_ref).max())
+    V = V.reshape(m, m).T                       # column-major -> V[:, j] eigenvector j
+    assert np.allclose(T @ V, V * w, atol=1e-10 * abs(w_ref).max())
+    assert np.allclose(V.T @ V, np.eye(m), atol=1e-12)
+    # Ritz values of A lie inside its spectrum
+    ev = np.linalg.eigvalsh(A)
+    assert w.min() >= ev.min() * (1 - 1e-10) and w.max() <= ev.max() * (1 + 1e-10)
+
+
+def test_select_orthonormal_drops_dependent_columns(ba):
+    rng = np.random.default_rng(1)
+    Y = rng.normal(size=(200, 6))
+    Y = np.concatenate([Y[:, :3], Y[:, :1] * 2.0 + 1e-9 * rng.normal(size=(200, 1)), Y[:, 3:]], axis=1)  # col 3 ~ ghost of col 0
+    n = Y.shape[1]
+    G = np.ascontiguousarray(Y.T @ Y)
+    Cc = np.zeros(n * n)
+    kept = C.c_int32()
+    rc = ba._lib.lib().ba_dbg_select_columns(G.ctypes.data_as(C.c_void_p), n, 5, 1e-3, Cc.ctypes.data_as(C.c_void_p),
+                                             C.byref(kept))
+    assert rc == 0 and kept.value == 5
+    Cm = Cc[: n * kept.value].reshape(n, kept.value)
+    assert np.all(Cm[3] == 0.0)                 # the ghost column takes no part
+    Q = Y @ Cm
+    assert np.allclose(Q.T @ Q, np.eye(kept.value), atol=1e-10)
