@@ -77,7 +77,9 @@ SYMBOLS = {
     "ba_lm_step": (C.c_int, [_vp, _vp, _f64, _f64, _i32, _vp, C.POINTER(_f64), C.POINTER(_f64), _vp,
                              C.POINTER(_i32)]),
     "ba_lm_solve": (C.c_int, [_vp, _vp, C.POINTER(LMParams), C.POINTER(LMStats), _vp, _vp]),
+    "ba_set_deflation": (C.c_int, [_vp, C.c_int]),
     "ba_dbg_tridiag_eig": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    "ba_dbg_tridiag_smallest": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "ba_dbg_select_columns": (C.c_int, [_vp, _i32, _i32, _f64, _vp, C.POINTER(_i32)]),
     "ba_comm_unique_id": (C.c_int, [_vp]),
     "ba_comm_init": (C.c_int, [_vp, _vp]),

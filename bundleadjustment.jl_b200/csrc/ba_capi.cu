@@ -47,6 +47,7 @@ int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, 
   h->device = device;
   h->ncams = ncams; h->npnts = npnts; h->nobs = nobs; h->rank = rank; h->nranks = nranks;
   if (const char* e = getenv("BAGPU_COARSE")) h->coarse_clusters = atoi(e);
+  if (const char* e = getenv("BAGPU_DEFLATE")) h->deflate = std::max(0, std::min(32, atoi(e)));
   bool sorted = true;
   for (int64_t k = 0; k < nobs; ++k) {
     if (cam[k] < 1 || cam[k] > ncams || pnt[k] < 1 || pnt[k] > npnts)
@@ -183,6 +184,17 @@ int ba_set_coarse_clusters(ba_handle* h, int n) {
     if (h->stream) BA_CUDA(cudaStreamSynchronize(h->stream));
     ba::lm_release(h);  // schedules and the captured PCG graph depend on it; rebuilt on next use
     h->coarse_clusters = n;
+  }
+  return BA_OK;
+}
+
+int ba_set_deflation(ba_handle* h, int k) {
+  if (!h || k < 0 || k > 32) return BA_ERR_ARG;
+  if (k != h->deflate) {
+    BA_CUDA(cudaSetDevice(h->device));
+    if (h->stream) BA_CUDA(cudaStreamSynchronize(h->stream));
+    ba::lm_release(h);  // buffers, harvested vectors and the captured PCG graph depend on it
+    h->deflate = k;
   }
   return BA_OK;
 }
@@ -359,6 +371,17 @@ int ba_dbg_tridiag_eig(const double* alpha, const double* beta, int32_t m, doubl
   ba::lanczos_tridiagonal(alpha, beta, m, d, e);
   if (!ba::tridiag_eig(d, e, m, V)) return BA_ERR_NUMERIC;
   std::copy(d.begin(), d.end(), evals);
+  std::copy(V.begin(), V.end(), evecs_colmajor);
+  return BA_OK;
+}
+
+int ba_dbg_tridiag_smallest(const double* alpha, const double* beta, int32_t m, int32_t k, int32_t full_below,
+                            double* evals, double* evecs_colmajor) {
+  if (!alpha || !beta || m < 1 || k < 1 || k > m || !evals || !evecs_colmajor) return BA_ERR_ARG;
+  std::vector<double> d, e, w, V;
+  ba::lanczos_tridiagonal(alpha, beta, m, d, e);
+  if (!ba::tridiag_smallest(d, e, m, k, w, V, full_below)) return BA_ERR_NUMERIC;
+  std::copy(w.begin(), w.end(), evals);
   std::copy(V.begin(), V.end(), evecs_colmajor);
   return BA_OK;
 }

@@ -61,11 +61,23 @@ struct ba_lm_state {
   int ncl = 0, ctas_per_cluster = 1, mc = 0;  // clusters, vector-kernel CTAs (28 cameras) per cluster, 9 ncl
   double* d_Ac = nullptr;     // mc x mc: P' S P
   double* d_Aci = nullptr;    // its inverse
-  double* d_Wc = nullptr;     // mc x 2mc scratch of the inversion
   double* d_yc = nullptr;     // mc: coarse correction of the current residual
   double* d_cpart = nullptr;  // 9 per vector-kernel CTA: restriction partials
   long long* d_Acq = nullptr; // mc x mc: fixed-point sums of the Schur part of P' S P (order-independent)
   double* d_cdiag = nullptr;  // mc: sqrt of the diagonal of P' (U + lambda I) P (normalisation of d_Acq)
+  // deflation vectors harvested from the PCG solves (coarse space [P | Z], mc + kz <= 144 unknowns)
+  int kz = 0, kz_base = 0;      // live columns of Z; the first kz_base come from the first long solve
+  int kz_base_max = 0, kz_max = 0;  // limits for this problem (0: deflation not in use)
+  int hcap = 0;                 // harvest capacity (Lanczos vectors)
+  double* d_Z = nullptr;        // n9 x kz_max, column-major, Euclidean-orthonormal columns
+  double* d_Zcand = nullptr;    // n9 x 64 candidates
+  double* d_harv = nullptr;     // n9 x hcap: z_j / sqrt(r_j.z_j)
+  double* d_hcoef = nullptr;    // [alpha (hcap) | beta (hcap)] of the harvested solve
+  double* d_zpart = nullptr;    // per vector-kernel CTA: kz partial dot products Z_j . r
+  double* d_dsmall = nullptr;   // hcap x 64 coefficient matrix / 64 x 64 Gram matrix
+  int pcg_graph_kz = -1;        // kz the captured PCG graph was built for
+  int z_gen = 0, coarse_gen = 0;  // version of Z, and the version the current Ac^-1 was built for
+  int defl_iters_first = 0;     // PCG iterations of the solve the base vectors came from
   // ---- iterates -------------------------------------------------------------------------------
   double* d_x = nullptr;      // current iterate (nvar; only this rank's point slice + cameras are live)
   double* d_xt = nullptr;     // trial iterate
@@ -118,6 +130,7 @@ struct ba_handle {
   cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (profiling only)
   bool profile = false;
   int coarse_clusters = 16;  // two-level PCG preconditioner: target number of camera clusters (0 = off)
+  int deflate = 32;          // PCG deflation: base Ritz vectors wanted (0 = off)
   ba_lm_state lm;
   ncclComm* comm = nullptr;
   ba_p2p_state p2p;

@@ -31,6 +31,7 @@
 #include <cstring>
 #include "ba_internal.h"
 #include "ba_math.cuh"
+#include "ba_ritz.h"
 
 
 #include "ba_lm_kernels.cuh"
@@ -49,6 +50,15 @@ int dmalloc(ba_handle* h, T** p, size_t n) {
 }
 
 inline unsigned nblk(int64_t n, int per) { return (unsigned)std::max<int64_t>((n + per - 1) / per, 1); }
+
+// camera systems of up to this many rows run the vector half of a PCG iteration as one CTA (k_pcg_small)
+inline int64_t small_rows_max() {
+  static const int64_t v = getenv("BAGPU_VEC_SMALL_MAX") ? atoll(getenv("BAGPU_VEC_SMALL_MAX")) : 1152;
+  return v;
+}
+constexpr int DEFL_ROLL = 16;   // deflation vectors refreshed after every solve (on top of the base ones)
+constexpr int DEFL_CAND = 64;   // candidates per selection (= DG_N, the widest k_defl_gemm output)
+constexpr int DEFL_HCAP = 1024; // Lanczos vectors kept per solve at most
 
 }  // namespace
 
@@ -154,13 +164,26 @@ int lm_prepare(ba_handle* h) {
       S.ncl = (nvb + S.ctas_per_cluster - 1) / S.ctas_per_cluster;
     }
     S.mc = CDOF * S.ncl;
-    ALLOC(S.d_Ac, S.mc * S.mc);
-    ALLOC(S.d_Aci, S.mc * S.mc);
-    ALLOC(S.d_Wc, 2 * S.mc * S.mc);
-    ALLOC(S.d_yc, S.mc);
+    // deflation vectors share the coarse solve (mc + kz <= 144); small systems use the fused kernel without them
+    S.kz_max = S.kz_base_max = 0;
+    // (sharded runs: the code path is rank-symmetric but has not been validated on several GPUs yet)
+    static const bool defl_multi = getenv("BAGPU_DEFLATE_MULTI") != nullptr;
+    if (h->deflate > 0 && 9 * ncams > small_rows_max() && (h->nranks == 1 || defl_multi)) {
+      S.kz_max = std::min(144 - S.mc, h->deflate + DEFL_ROLL);
+      S.kz_base_max = std::min(h->deflate, S.kz_max);
+    }
+    const int64_t mt = S.mc + S.kz_max;
+    ALLOC(S.d_Ac, mt * mt);
+    ALLOC(S.d_Aci, mt * mt);
+    ALLOC(S.d_yc, mt);
     ALLOC(S.d_cpart, 9 * (int64_t)nvb);
     ALLOC(S.d_Acq, S.mc * S.mc);
     ALLOC(S.d_cdiag, S.mc);
+    if (S.kz_max > 0) {
+      ALLOC(S.d_Z, 9 * ncams * S.kz_max);
+      ALLOC(S.d_Zcand, 9 * ncams * DEFL_CAND);
+      ALLOC(S.d_zpart, (int64_t)nvb * S.kz_max);
+    }
   }
   ALLOC(S.d_x, h->nvar());
   ALLOC(S.d_xt, h->nvar());
@@ -218,7 +241,7 @@ void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,
                   S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
-                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_Wc, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
+                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_Z, S.d_Zcand, S.d_harv, S.d_hcoef, S.d_zpart, S.d_dsmall, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
   for (void* p : ptrs) cudaFree(p);
   if (S.h_scal) cudaFreeHost(S.h_scal);
   if (S.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph));
@@ -306,40 +329,117 @@ struct Solver {
     if ((rc = check())) return rc;
     return coarse_setup();
   }
-  // Ac = P' S P, then Ac^-1.  Default: direct assembly in one pass over the points (k_coarse_assemble);
-  // BAGPU_COARSE_PRODUCTS=1: column by column with CDOF ncl applications of S (the cross-check).
+  // Ac = [P Z]' S [P Z], then Ac^-1.  P block: direct assembly in one pass over the points (k_coarse_assemble;
+  // BAGPU_COARSE_PRODUCTS=1: column by column with CDOF ncl applications of S, the cross-check).  Z block
+  // (deflation vectors, dense): one application of S per vector.
   int coarse_setup() {
-    if (S.ncl == 0) return BA_OK;
+    const int m = S.mc + S.kz;
+    S.coarse_gen = S.z_gen;
+    if (m == 0) return BA_OK;
     int rc;
     static const bool by_products = getenv("BAGPU_COARSE_PRODUCTS") != nullptr;
-    if (!by_products) {
-      const int cpc = 28 * S.ctas_per_cluster, m = S.mc;
-      k_coarse_diag<<<nblk(m, 64), 64, 0, s>>>(ncams, cpc, m, S.d_H, S.d_cdiag);
-      BA_CUDA(cudaMemsetAsync(S.d_Acq, 0, sizeof(long long) * (size_t)(m * m), s));
-      const size_t smem = sizeof(unsigned long long) * (size_t)(m * m);
+    const int cpc = 28 * S.ctas_per_cluster;
+    const bool p2p = h->nranks > 1 && h->p2p.ready;
+    if (S.ncl > 0 && !by_products) {
+      const int mcl = S.mc;
+      k_coarse_diag<<<nblk(mcl, 64), 64, 0, s>>>(ncams, cpc, mcl, S.d_H, S.d_cdiag);
+      BA_CUDA(cudaMemsetAsync(S.d_Acq, 0, sizeof(long long) * (size_t)(mcl * mcl), s));
+      const size_t smem = sizeof(unsigned long long) * (size_t)(mcl * mcl);
       static bool attr_set = false;
       if (!attr_set) {
         BA_CUDA(cudaFuncSetAttribute(k_coarse_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 144 * 8));
         attr_set = true;
       }
       const unsigned grid = (unsigned)std::min<int64_t>(nblk(npl, 256), 148 * 2);
-      k_coarse_assemble<<<grid, 256, smem, s>>>(S.d_pstart, npl, nl, h->d_cam, S.d_Jp, S.d_Vinv, cpc, m, S.d_cdiag,
+      k_coarse_assemble<<<grid, 256, smem, s>>>(S.d_pstart, npl, nl, h->d_cam, S.d_Jp, S.d_Vinv, cpc, mcl, S.d_cdiag,
                                                 reinterpret_cast<unsigned long long*>(S.d_Acq));
       if ((rc = check())) return rc;
-      if ((rc = allreduce_sum_i64(h, S.d_Acq, (size_t)(m * m)))) return rc;
-      k_coarse_finish<<<nblk((int64_t)m * m, 256), 256, 0, s>>>(ncams, cpc, m, S.d_H, S.d_cdiag, S.d_Acq, S.d_Ac);
-      k_coarse_invert<<<1, 256, 0, s>>>(m, S.d_Ac, S.d_Wc, S.d_Aci, S.d_scal);
-      return check();
+      if ((rc = allreduce_sum_i64(h, S.d_Acq, (size_t)(mcl * mcl)))) return rc;
+      k_coarse_finish<<<nblk((int64_t)mcl * mcl, 256), 256, 0, s>>>(ncams, cpc, mcl, S.d_H, S.d_cdiag, S.d_Acq, S.d_Ac,
+                                                                    m);
+      if ((rc = check())) return rc;
     }
-    BA_CUDA(cudaMemsetAsync(S.d_scal + S_DONE, 0, sizeof(double), s));  // the product kernels honour S_DONE
-    const bool p2p = h->nranks > 1 && h->p2p.ready;
-    for (int col = 0; col < S.mc; ++col) {
-      k_coarse_basis<<<nblk(n9, 256), 256, 0, s>>>(n9, 9 * 28 * S.ctas_per_cluster, col, p);
-      if ((rc = s_product(false))) return rc;
-      k_coarse_restrict<<<S.ncl, 288, 0, s>>>(ncams, 28 * S.ctas_per_cluster, S.mc, col, q, S.d_Ac);
-      if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
+    if ((S.ncl > 0 && by_products) || S.kz > 0) {
+      BA_CUDA(cudaMemsetAsync(S.d_scal + S_DONE, 0, sizeof(double), s));  // the product kernels honour S_DONE
+      if (S.ncl > 0 && by_products)
+        for (int col = 0; col < S.mc; ++col) {
+          k_coarse_basis<<<nblk(n9, 256), 256, 0, s>>>(n9, 9 * cpc, col, p);
+          if ((rc = s_product(false))) return rc;
+          k_coarse_restrict<<<S.ncl, 288, 0, s>>>(ncams, cpc, m, col, q, S.d_Ac);
+          if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
+        }
+      for (int j = 0; j < S.kz; ++j) {  // columns S Z_j: P rows by restriction, Z rows by dot products
+        BA_CUDA(cudaMemcpyAsync(p, S.d_Z + (int64_t)j * n9, sizeof(double) * (size_t)n9, cudaMemcpyDeviceToDevice, s));
+        if ((rc = s_product(false))) return rc;
+        if (S.ncl > 0) k_coarse_restrict<<<S.ncl, 288, 0, s>>>(ncams, cpc, m, S.mc + j, q, S.d_Ac);
+        k_defl_zdot<<<S.kz, 256, 0, s>>>(n9, S.d_Z, q, S.d_Ac, m, S.mc, S.mc + j);
+        if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
+      }
+      if (S.kz > 0 && S.mc > 0) k_defl_symfill<<<nblk((int64_t)S.kz * S.mc, 256), 256, 0, s>>>(m, S.mc, S.d_Ac);
     }
-    k_coarse_invert<<<1, 256, 0, s>>>(S.mc, S.d_Ac, S.d_Wc, S.d_Aci, S.d_scal);
+    static bool inv_attr_set = false;
+    if (!inv_attr_set) {
+      BA_CUDA(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 144 * 8));
+      inv_attr_set = true;
+    }
+    k_coarse_invert<<<1, INV_THREADS, sizeof(double) * (size_t)(m * m), s>>>(m, S.d_Ac, S.d_Aci, S.d_scal);
+    S.coarse_gen = S.z_gen;
+    return check();
+  }
+  // After a solve: rebuild the deflation vectors from the Lanczos vectors it harvested (z_j / sqrt(r_j.z_j) and
+  // the CG coefficients).  First long solve: the kz_base_max smallest Ritz vectors become the base.  Every later
+  // solve: its smallest Ritz vectors -- the slow modes the current space misses -- orthogonalised against the
+  // base, replace the DEFL_ROLL refreshed columns.  The small dense algebra runs on the host (ba_ritz.h): the
+  // inputs are bit-identical on all ranks, so the vectors are too.  A failed or degenerate harvest keeps the
+  // vectors as they are: nothing here can change the solution, only the iteration count.
+  int defl_update(int iters) {
+    const int mh = std::min(iters, S.hcap);
+    const bool first = S.kz == 0;
+    if (first ? (mh < 48) : (S.kz_max <= S.kz_base || mh < 16)) return BA_OK;
+    std::vector<double> hc((size_t)(2 * S.hcap));
+    BA_CUDA(cudaMemcpyAsync(hc.data(), S.d_hcoef, hc.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+    const double *alpha = hc.data(), *beta = hc.data() + S.hcap;
+    for (int j = 0; j < mh; ++j)
+      if (!(alpha[j] > 0.0) || !(beta[j] >= 0.0) || !std::isfinite(alpha[j]) || !std::isfinite(beta[j])) return BA_OK;
+    std::vector<double> d, e, w, V;
+    lanczos_tridiagonal(alpha, beta, mh, d, e);
+    const int base = first ? 0 : S.kz_base;
+    const int ncand = std::min(first ? DEFL_CAND : std::min(DEFL_CAND - base, 2 * DEFL_ROLL), mh);
+    if (!tridiag_smallest(d, e, mh, ncand, w, V)) return BA_OK;
+    std::vector<double> cf((size_t)mh * ncand);  // row-major mh x ncand
+    for (int j = 0; j < mh; ++j)
+      for (int c = 0; c < ncand; ++c) cf[(size_t)j * ncand + c] = V[(size_t)c * mh + j];
+    for (double v : cf)
+      if (!std::isfinite(v)) return BA_OK;
+    BA_CUDA(cudaMemcpyAsync(S.d_dsmall, cf.data(), cf.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (base)
+      BA_CUDA(cudaMemcpyAsync(S.d_Zcand, S.d_Z, sizeof(double) * (size_t)(n9 * base), cudaMemcpyDeviceToDevice, s));
+    k_defl_gemm<<<nblk(n9, 128), 128, 0, s>>>(n9, mh, ncand, S.d_harv, S.d_dsmall, S.d_Zcand + (int64_t)base * n9);
+    const int n = base + ncand;
+    double* d_G = S.d_dsmall + (size_t)S.hcap * DEFL_CAND;
+    k_defl_gram<<<(unsigned)(n * n), 256, 0, s>>>(n9, n, S.d_Zcand, d_G);
+    int rc = check();
+    if (rc) return rc;
+    std::vector<double> G((size_t)n * n), Cm;
+    BA_CUDA(cudaMemcpyAsync(G.data(), d_G, G.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    BA_CUDA(cudaStreamSynchronize(s));  // (also: cf is read by the copy above before it goes out of scope)
+    for (double v : G)
+      if (!std::isfinite(v)) return BA_OK;
+    const int kept = select_orthonormal(G, n, first ? S.kz_base_max : S.kz_max, 1e-3, Cm);
+    if (kept == 0 || (!first && kept < S.kz_base)) return BA_OK;
+    if (!first)  // the base columns must have survived as the first kept ones
+      for (int j = 0; j < S.kz_base; ++j)
+        if (!(std::fabs(Cm[(size_t)j * kept + j]) > 0.5)) return BA_OK;
+    BA_CUDA(cudaMemcpyAsync(S.d_dsmall, Cm.data(), sizeof(double) * (size_t)n * kept, cudaMemcpyHostToDevice, s));
+    k_defl_gemm<<<nblk(n9, 128), 128, 0, s>>>(n9, n, kept, S.d_Zcand, S.d_dsmall, S.d_Z);
+    BA_CUDA(cudaStreamSynchronize(s));  // Cm goes out of scope
+    S.kz = kept;
+    S.z_gen += 1;
+    if (first) {
+      S.kz_base = kept;
+      S.defl_iters_first = iters;
+    }
     return check();
   }
   int read_scalars() {
@@ -385,20 +485,22 @@ struct Solver {
     const int nvb = (int)nblk(n9, VEC_ROWS);
     double* ppq = S.d_pcgpart;
     double* prz = S.d_pcgpart + nvb;
-    const bool coarse = S.ncl > 0;
+    const int m = S.mc + S.kz;  // coarse unknowns: cluster components, then deflation vectors
+    const bool coarse = m > 0;
     const bool p2p = h->nranks > 1 && h->p2p.ready;
     k_pcg_xr<INIT><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, b, S.d_Minv, p, q, xc, r, z, ppq, prz, S.d_scal,
-                                               coarse ? S.d_cpart : nullptr);
+                                               S.ncl > 0 ? S.d_cpart : nullptr, S.d_Z, S.kz, S.d_zpart);
     if (coarse)
-      k_pcg_coarse<<<1, 160, 0, s>>>(nvb, S.ctas_per_cluster, S.mc, S.d_cpart, S.d_Aci, S.d_yc, S.d_scal, INIT ? 1 : 0);
+      k_pcg_coarse<<<1, 160, 0, s>>>(nvb, S.ctas_per_cluster, m, S.d_cpart, S.d_Aci, S.d_yc, S.d_scal, INIT ? 1 : 0,
+                                     S.kz, S.d_zpart);
     k_pcg_p<INIT><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol,
                                               (!INIT && p2p) ? h->p2p.d_seq : nullptr, coarse ? S.d_yc : nullptr,
-                                              std::max(S.ctas_per_cluster, 1));
+                                              std::max(S.ctas_per_cluster, 1), S.d_Z, S.kz, S.mc,
+                                              S.kz_max > 0 ? S.d_harv : nullptr, S.hcap, S.d_hcoef);
   }
   // one PCG iteration
   int pcg_iteration(double tol, bool checks) {
-    static const int64_t small_max = getenv("BAGPU_VEC_SMALL_MAX") ? atoll(getenv("BAGPU_VEC_SMALL_MAX")) : 1152;
-    const bool small = n9 <= small_max;
+    const bool small = n9 <= small_rows_max();
     int rc = s_product(checks, !small);
     if (rc) return rc;
     if (small) {
@@ -422,10 +524,17 @@ struct Solver {
   int pcg(double tol, int maxit, int* iters) {
     constexpr int PCG_POLL = 8;
     static const bool no_graph = getenv("BAGPU_NO_GRAPH") != nullptr || getenv("BAGPU_DEBUG_SYNC") != nullptr;
+    int rc;
+    if (S.kz_max > 0 && !S.d_harv) {  // harvest buffers, sized once by the first solve's iteration limit
+      S.hcap = std::max(1, std::min(DEFL_HCAP, maxit));
+      if ((rc = dmalloc(h, &S.d_harv, (size_t)(n9 * S.hcap)))) return rc;
+      if ((rc = dmalloc(h, &S.d_hcoef, (size_t)(2 * S.hcap)))) return rc;
+      if ((rc = dmalloc(h, &S.d_dsmall, (size_t)(S.hcap + DEFL_CAND) * DEFL_CAND))) return rc;
+    }
+    if (S.coarse_gen != S.z_gen && (rc = coarse_setup())) return rc;  // vectors changed since the last factor()
     pcg_vectors<true>(tol);
-    int rc = check();
-    if (rc) return rc;
-    if (!no_graph && !S.pcg_graph_off && (!S.pcg_graph || S.pcg_graph_tol != tol)) {
+    if ((rc = check())) return rc;
+    if (!no_graph && !S.pcg_graph_off && (!S.pcg_graph || S.pcg_graph_tol != tol || S.pcg_graph_kz != S.kz)) {
       if (S.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph));
       S.pcg_graph = nullptr;
       cudaGraph_t g = nullptr;
@@ -442,6 +551,7 @@ struct Solver {
         cudaGraphDestroy(g);
         S.pcg_graph = ge;
         S.pcg_graph_tol = tol;
+        S.pcg_graph_kz = S.kz;
       }
     }
     int launched = 0;
@@ -459,6 +569,17 @@ struct Solver {
       if (S.h_scal[S_DONE] != 0.0 || launched >= maxit) break;
     }
     *iters = (int)S.h_scal[S_ITERS];
+    if (S.kz > 0 && (S.h_scal[S_DONE] == 2.0 || S.h_scal[S_ERR] == 2.0)) {
+      // the extended coarse matrix lost definiteness (nearly dependent vectors): drop the deflation vectors
+      // for good, rebuild the cluster level and solve again
+      S.kz = S.kz_base = S.kz_max = 0;
+      S.z_gen += 1;
+      BA_CUDA(cudaMemsetAsync(S.d_scal + S_ERR, 0, sizeof(double), s));
+      BA_CUDA(cudaMemsetAsync(S.d_scal + S_DONE, 0, sizeof(double), s));
+      if ((rc = coarse_setup())) return rc;
+      return pcg(tol, maxit, iters);
+    }
+    if (S.kz_max > 0 && S.h_scal[S_DONE] == 1.0 && (rc = defl_update(*iters))) return rc;
     if (S.h_scal[S_DONE] == 2.0) {
       h->err = "PCG breakdown (non-finite or non-positive curvature in the reduced camera system)";
       return BA_ERR_NUMERIC;
@@ -591,12 +712,16 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
   }
   ba_lm_params prm;
   if (prm_in) prm = *prm_in; else ba_lm_default_params(&prm);
+  static const bool trace = getenv("BAGPU_TRACE") != nullptr;  // per-iteration phase times on stderr
+  const auto wall_prep = std::chrono::steady_clock::now();
   int rc = lm_prepare(h);
   if (rc) return rc;
   BA_CUDA(cudaSetDevice(h->device));
   Solver sv(h);
   ba_lm_state& S = h->lm;
   const auto wall0 = std::chrono::steady_clock::now();
+  if (trace)
+    fprintf(stderr, "[bagpu] lm_prepare %.1f ms\n", std::chrono::duration<double>(wall0 - wall_prep).count() * 1e3);
   double t_eval = 0, t_asm = 0, t_pcg = 0, t_back = 0;
   int64_t pcg_total = 0;
   auto rec = [&](int i) { cudaEventRecord(S.ev[i], h->stream); };
@@ -651,6 +776,10 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
     rec(4);
     BA_CUDA(cudaEventSynchronize(S.ev[4]));
     t_asm += lap(0, 1); t_pcg += lap(1, 2); t_back += lap(2, 3); t_eval += lap(3, 4);
+    if (trace)
+      fprintf(stderr, "[bagpu] iter %lld: factor %.2f ms, pcg %.2f ms (%d iterations, %d deflation vectors), backsub %.2f ms, "
+              "trial %.2f ms, wall %.1f ms\n", (long long)iter, lap(0, 1), lap(1, 2), pit, S.kz, lap(2, 3), lap(3, 4),
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count() * 1e3);
     dr2 = sq_to_half_norm2(S.h_scal[S_DR2]);
     double norm_rsuiv = sqrt(S.h_scal[S_TR2]);
     double obj_suiv = norm_rsuiv * norm_rsuiv / 2;

@@ -28,6 +28,7 @@ enum {
   S_DC2,      // sum delta_c^2
   S_XC2,      // sum (x + delta)_c^2
   S_RZ = 16, S_RZ0, S_PQ, S_DONE, S_ITERS, S_REL, S_ERR, S_RZN, S_RCY,
+  S_ITK,      // S_ITERS as it was when the current PCG iteration started (read by every CTA of k_pcg_p)
   S_COUNT = 32
 };
 
@@ -717,7 +718,10 @@ k_pcg_q(int64_t n9, const double* __restrict__ H, const double* p, double* q, do
   __shared__ double sh[VEC_THREADS / 32];
   __shared__ int timed_out;
   if (scal[S_DONE] != 0.0) return;
-  if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_RZ] = scal[S_RZN];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[S_RZ] = scal[S_RZN];
+    scal[S_ITK] = scal[S_ITERS];
+  }
   unsigned long long seq = 0;
   if (P2P) {
     seq = *seqp;
@@ -771,7 +775,8 @@ template <bool INIT>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __restrict__ Minv, const double* p,
          const double* q, double* xc, double* r, double* z, const double* part_pq, double* __restrict__ part_rz,
-         const double* scal, double* __restrict__ cpart) {
+         const double* scal, double* __restrict__ cpart, const double* __restrict__ Zb, int kz,
+         double* __restrict__ zpart) {
   __shared__ double sh[VEC_THREADS / 32];
   __shared__ double rs[VEC_ROWS];
   const int64_t i = blockIdx.x * (int64_t)VEC_ROWS + threadIdx.x;
@@ -800,13 +805,27 @@ k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __r
   }
   rz = block_sum<VEC_THREADS>(rz, sh);
   if (threadIdx.x == 0) part_rz[blockIdx.x] = rz;
-  if (cpart) {  // restriction to the coarse space: this CTA's 28 cameras summed per component (fixed order)
+  if (cpart || kz > 0) {
     if (threadIdx.x < VEC_ROWS) rs[threadIdx.x] = live ? r[i] : 0.0;
     __syncthreads();
+  }
+  if (cpart) {  // restriction to the coarse space: this CTA's 28 cameras summed per component (fixed order)
     if (threadIdx.x < 9) {
       double t = 0.0;
       for (int c = 0; c < VEC_ROWS / 9; ++c) t += rs[c * 9 + threadIdx.x];
       cpart[blockIdx.x * 9 + threadIdx.x] = t;
+    }
+  }
+  if (kz > 0) {  // restriction to the deflation vectors: this CTA's slice of Z_j . r, one warp per vector
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i0 = blockIdx.x * (int64_t)VEC_ROWS;
+    const int nrow = (int)min((long long)VEC_ROWS, (long long)(n9 - i0));
+    for (int j = warp; j < kz; j += VEC_THREADS / 32) {
+      const double* zj = Zb + (int64_t)j * n9 + i0;
+      double t = 0.0;
+      for (int a = lane; a < nrow; a += 32) t += zj[a] * rs[a];
+      t = warp_sum(t);
+      if (lane == 0) zpart[(int64_t)blockIdx.x * kz + j] = t;
     }
   }
 }
@@ -818,21 +837,28 @@ k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __r
 // for the r.z dot product.  One CTA; m = CDOF ncl <= 144.
 __global__ void __launch_bounds__(160)
 k_pcg_coarse(int nvb, int ctas_per_cluster, int m, const double* __restrict__ cpart, const double* __restrict__ Aci,
-             double* __restrict__ yc, double* scal, int init) {
+             double* __restrict__ yc, double* scal, int init, int kz, const double* __restrict__ zpart) {
   __shared__ double rc[144], yy[144];
   if (!init && scal[S_DONE] != 0.0) return;
   const int a = threadIdx.x;
-  if (a < m) {
+  const int mcl = m - kz;  // cluster unknowns first, then one unknown per deflation vector
+  if (a < mcl) {
     const int I = a / CDOF, jj = a - CDOF * I;
     const int b0 = I * ctas_per_cluster, b1 = min(nvb, b0 + ctas_per_cluster);
     double t = 0.0;
     for (int bb = b0; bb < b1; ++bb) t += cpart[bb * 9 + jj];
     rc[a] = t;
   }
+  for (int j = a >> 5; j < kz; j += 160 / 32) {  // Z_j . r: a warp sums the per-CTA partials of one vector
+    double t = 0.0;
+    for (int bb = a & 31; bb < nvb; bb += 32) t += zpart[(int64_t)bb * kz + j];
+    t = warp_sum(t);
+    if ((a & 31) == 0) rc[mcl + j] = t;
+  }
   __syncthreads();
   if (a < m) {
     double t = 0.0;
-    for (int bq = 0; bq < m; ++bq) t += Aci[a * m + bq] * rc[bq];
+    for (int bq = 0; bq < m; ++bq) t += Aci[bq * m + a] * rc[bq];  // Aci is exactly symmetric: coalesced reads
     yy[a] = t;
     yc[a] = t;
   }
@@ -849,20 +875,24 @@ k_pcg_coarse(int nvb, int ctas_per_cluster, int m, const double* __restrict__ cp
 template <bool INIT>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_pq, const double* part_rz,
-        double* scal, double tol, unsigned long long* seqp, const double* __restrict__ yc, int ctas_per_cluster) {
+        double* scal, double tol, unsigned long long* seqp, const double* __restrict__ yc, int ctas_per_cluster,
+        const double* __restrict__ Zb, int kz, int mcl, double* __restrict__ harv, int hcap,
+        double* __restrict__ hcoef) {
   __shared__ double sh[VEC_THREADS / 32];
   const int64_t i = blockIdx.x * (int64_t)VEC_ROWS + threadIdx.x;
   const bool live = threadIdx.x < VEC_ROWS && i < n9;
   const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
-  // coarse correction of this row: z_i = (Minv r)_i + (P yc)_i; its share of r.z is scal[S_RCY]
+  // coarse correction of this row: z_i = (Minv r)_i + (P yc)_i + (Z yz)_i; its share of r.z is scal[S_RCY]
   double zc = 0.0;
   if (yc && live) {
     const int comp = (int)(i % 9);
-    if (comp < CDOF) zc = yc[(blockIdx.x / ctas_per_cluster) * CDOF + comp];
+    if (mcl > 0 && comp < CDOF) zc = yc[(blockIdx.x / ctas_per_cluster) * CDOF + comp];
+    for (int j = 0; j < kz; ++j) zc += Zb[(int64_t)j * n9 + i] * yc[mcl + j];
   }
   if (INIT) {
     const double rz = sum_partials(part_rz, nparts, sh) + (yc ? scal[S_RCY] : 0.0);
     if (live) p[i] = z[i] + zc;
+    if (harv && live && hcap > 0) harv[i] = (z[i] + zc) / sqrt(rz);  // Lanczos vector 0
     if (lead) {
       scal[S_RZN] = rz;
       scal[S_RZ0] = rz;
@@ -886,6 +916,14 @@ k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_p
   const double rzn = sum_partials(part_rz, nparts, sh) + (yc ? scal[S_RCY] : 0.0);
   const double beta = rzn / scal[S_RZ];
   if (live) p[i] = (z[i] + zc) + beta * p[i];
+  if (harv) {  // harvest the Lanczos vector z_t / sqrt(r_t.z_t) and the CG coefficients of step t - 1
+    const int t = (int)scal[S_ITK] + 1;
+    if (t < hcap && live) harv[(int64_t)t * n9 + i] = (z[i] + zc) / sqrt(rzn);
+    if (lead && t <= hcap) {
+      hcoef[t - 1] = scal[S_RZ] / pq;
+      hcoef[hcap + t - 1] = beta;
+    }
+  }
   if (lead && seqp) *seqp += 1;  // next exchange uses the other mailbox half (no CTA of this kernel reads it)
   if (lead) {
     const double rel = sqrt(rzn / scal[S_RZ0]);
@@ -987,7 +1025,7 @@ k_pcg_small(int64_t n9, int64_t ncams, const double* __restrict__ H, const doubl
     __syncthreads();
     if (threadIdx.x < m) {
       double t = 0.0;
-      for (int bq = 0; bq < m; ++bq) t += Aci[threadIdx.x * m + bq] * rc[bq];
+      for (int bq = 0; bq < m; ++bq) t += Aci[bq * m + threadIdx.x] * rc[bq];  // (symmetric: coalesced)
       yy[threadIdx.x] = t;
     }
     __syncthreads();
@@ -1091,7 +1129,7 @@ k_coarse_assemble(const int32_t* __restrict__ pstart, int64_t npl, int64_t nl, c
 // Ac = P'HP - dequantised Schur part
 __global__ void __launch_bounds__(256)
 k_coarse_finish(int64_t ncams, int cams_per_cluster, int m, const double* __restrict__ H, const double* __restrict__ d,
-                const long long* __restrict__ Acq, double* __restrict__ Ac) {
+                const long long* __restrict__ Acq, double* __restrict__ Ac, int ld) {
   const int e = blockIdx.x * 256 + threadIdx.x;
   if (e >= m * m) return;
   const int row = e / m, col = e - row * m;
@@ -1101,7 +1139,7 @@ k_coarse_finish(int64_t ncams, int cams_per_cluster, int m, const double* __rest
     const int64_t c0 = (int64_t)I * cams_per_cluster, c1 = min((long long)ncams, (long long)(c0 + cams_per_cluster));
     for (int64_t c = c0; c < c1; ++c) t += H[c * 81 + a * 9 + b];
   }
-  Ac[e] = t - ((double)Acq[e] / CQ_SCALE) * (d[row] * d[col]);
+  Ac[row * ld + col] = t - ((double)Acq[e] / CQ_SCALE) * (d[row] * d[col]);  // ld > m: room for the deflation block
 }
 
 // coarse-space setup: basis vector (cluster I, component j) of P, restriction of S v, inversion of Ac
@@ -1131,35 +1169,109 @@ k_coarse_restrict(int64_t ncams, int cams_per_cluster, int m, int col, const dou
   }
 }
 
-// Aci = Ac^-1 (m <= 144, SPD) by Gauss-Jordan without pivoting on a symmetrised copy; one CTA, global memory
-__global__ void __launch_bounds__(256)
-k_coarse_invert(int m, const double* __restrict__ Ac, double* W /* m x 2m scratch */, double* __restrict__ Aci,
-                double* scal) {
-  const int n2 = 2 * m;
-  for (int e = threadIdx.x; e < m * m; e += 256) {
+// Aci = Ac^-1 (m <= 144, SPD) by in-place Gauss-Jordan without pivoting on a symmetrised copy held in shared
+// memory (m^2 doubles <= 162 KB); one CTA.  Pivot step k: row k becomes row_k / pivot with 1 / pivot in column
+// k; every other row i subtracts A[i][k] times it, its column k starting from zero.
+constexpr int INV_THREADS = 1024;
+__global__ void __launch_bounds__(INV_THREADS)
+k_coarse_invert(int m, const double* __restrict__ Ac, double* __restrict__ Aci, double* scal) {
+  extern __shared__ double Ash[];  // m x m
+  __shared__ double colk[144], rowk[144];
+  for (int e = threadIdx.x; e < m * m; e += INV_THREADS) {
     const int a = e / m, bq = e - a * m;
-    W[a * n2 + bq] = 0.5 * (Ac[a * m + bq] + Ac[bq * m + a]);
-    W[a * n2 + m + bq] = (a == bq) ? 1.0 : 0.0;
+    Ash[e] = 0.5 * (Ac[a * m + bq] + Ac[bq * m + a]);
   }
   __syncthreads();
   for (int k = 0; k < m; ++k) {
-    const double piv = W[k * n2 + k];
+    const double piv = Ash[k * m + k];
     if (!(piv > 0.0) && threadIdx.x == 0) scal[S_ERR] = 2.0;
-    __syncthreads();
-    for (int e = threadIdx.x; e < n2; e += 256) W[k * n2 + e] /= piv;
-    __syncthreads();
-    for (int e = threadIdx.x; e < m * n2; e += 256) {
-      const int a = e / n2, col = e - a * n2;
-      if (a != k && col != k) W[a * n2 + col] -= W[a * n2 + k] * W[k * n2 + col];
+    if (threadIdx.x < m) {
+      colk[threadIdx.x] = Ash[threadIdx.x * m + k];
+      rowk[threadIdx.x] = ((int)threadIdx.x == k ? 1.0 : Ash[k * m + threadIdx.x]) / piv;
     }
     __syncthreads();
-    for (int a = threadIdx.x; a < m; a += 256)
-      if (a != k) W[a * n2 + k] = 0.0;
+    for (int e = threadIdx.x; e < m * m; e += INV_THREADS) {
+      const int a = e / m, bq = e - a * m;
+      Ash[e] = (a == k) ? rowk[bq] : ((bq == k ? 0.0 : Ash[e]) - colk[a] * rowk[bq]);
+    }
     __syncthreads();
   }
-  for (int e = threadIdx.x; e < m * m; e += 256) {
+  for (int e = threadIdx.x; e < m * m; e += INV_THREADS) {
     const int a = e / m, bq = e - a * m;
-    Aci[e] = 0.5 * (W[a * n2 + m + bq] + W[bq * n2 + m + a]);
+    Aci[e] = 0.5 * (Ash[a * m + bq] + Ash[bq * m + a]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deflation vectors: the coarse space is [P | Z] with Z (n9 x kz, column-major,
+// Euclidean-orthonormal) built from Ritz vectors harvested from the PCG solves themselves.
+// ---------------------------------------------------------------------------------------------
+// Ac[(mcl + i) * ld + col] = Z_i . q  (column `col` of the Z rows of [P Z]' S [P Z]); one CTA per i
+__global__ void __launch_bounds__(256)
+k_defl_zdot(int64_t n9, const double* __restrict__ Zb, const double* __restrict__ q, double* __restrict__ Ac, int ld,
+            int mcl, int col) {
+  __shared__ double sh[8];
+  const double* zi = Zb + (int64_t)blockIdx.x * n9;
+  double t = 0.0;
+  for (int64_t a = threadIdx.x; a < n9; a += 256) t += zi[a] * q[a];
+  t = block_sum<256>(t, sh);
+  if (threadIdx.x == 0) Ac[(int64_t)(mcl + blockIdx.x) * ld + col] = t;
+}
+
+// the Z-rows x P-columns block is the transpose of the P-rows x Z-columns block (filled by k_coarse_restrict)
+__global__ void k_defl_symfill(int m, int mcl, double* __restrict__ Ac) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kz = m - mcl;
+  if (e >= kz * mcl) return;
+  const int j = e / mcl, a = e - j * mcl;
+  Ac[(mcl + j) * m + a] = Ac[a * m + mcl + j];
+}
+
+// Out (n9 x N, column-major) = In (n9 x K, column-major) * Cf (K x N, row-major), N <= 64: thread per row
+constexpr int DG_N = 64, DG_TJ = 32;
+__global__ void __launch_bounds__(128)
+k_defl_gemm(int64_t n9, int K, int N, const double* __restrict__ In, const double* __restrict__ Cf,
+            double* __restrict__ Out) {
+  __shared__ double cs[DG_TJ][DG_N];
+  const int64_t i = blockIdx.x * (int64_t)128 + threadIdx.x;
+  double acc[DG_N];
+#pragma unroll
+  for (int c = 0; c < DG_N; ++c) acc[c] = 0.0;
+  for (int j0 = 0; j0 < K; j0 += DG_TJ) {
+    const int nj = min(DG_TJ, K - j0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < DG_TJ * DG_N; e += 128) {
+      const int jj = e / DG_N, c = e - jj * DG_N;
+      cs[jj][c] = (jj < nj && c < N) ? Cf[(int64_t)(j0 + jj) * N + c] : 0.0;
+    }
+    __syncthreads();
+    if (i < n9)
+      for (int jj = 0; jj < nj; ++jj) {
+        const double v = In[(int64_t)(j0 + jj) * n9 + i];
+#pragma unroll
+        for (int c = 0; c < DG_N; ++c) acc[c] += v * cs[jj][c];
+      }
+  }
+  if (i < n9) {
+#pragma unroll
+    for (int c = 0; c < DG_N; ++c)
+      if (c < N) Out[(int64_t)c * n9 + i] = acc[c];
+  }
+}
+
+// G (N x N, row-major) = Y' Y for Y (n9 x N, column-major); one CTA per entry of the upper triangle
+__global__ void __launch_bounds__(256)
+k_defl_gram(int64_t n9, int N, const double* __restrict__ Y, double* __restrict__ G) {
+  __shared__ double sh[8];
+  const int a = blockIdx.x / N, b = blockIdx.x - a * N;
+  if (a > b) return;
+  const double *ya = Y + (int64_t)a * n9, *yb = Y + (int64_t)b * n9;
+  double t = 0.0;
+  for (int64_t e = threadIdx.x; e < n9; e += 256) t += ya[e] * yb[e];
+  t = block_sum<256>(t, sh);
+  if (threadIdx.x == 0) {
+    G[a * N + b] = t;
+    G[b * N + a] = t;
   }
 }
 

@@ -1,7 +1,7 @@
 // ba_ritz.h -- host-side small dense algebra for the PCG deflation space: eigenpairs of the Lanczos
 // tridiagonal that a PCG solve produces for free, and the selection of a well-conditioned subset of the
 // Ritz vectors (converged Ritz values come with "ghost" copies).  Header-only, no CUDA: unit-tested on
-// the CPU through ba_dbg_tridiag_smallest / ba_dbg_select_columns (tests/test_host.py).
+// the CPU through ba_dbg_tridiag_eig / ba_dbg_tridiag_smallest / ba_dbg_select_columns (tests/test_host.py).
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -24,10 +24,12 @@ inline void lanczos_tridiagonal(const double* alpha, const double* beta, int m, 
 // Eigen-decomposition of a symmetric tridiagonal matrix (implicit QL with Wilkinson shifts, the classic
 // tql2 scheme).  d: diagonal (m) -> eigenvalues ascending; e: off-diagonal (e[j] couples j, j+1);
 // V (m x m, column-major, V[i + m*j]) -> eigenvectors in columns.  Returns false if an eigenvalue fails to
-// converge in 60 sweeps.
-inline bool tridiag_eig(std::vector<double>& d, std::vector<double> e, int m, std::vector<double>& V) {
-  V.assign((size_t)m * m, 0.0);
-  for (int i = 0; i < m; ++i) V[(size_t)i + (size_t)m * i] = 1.0;
+// converge in 60 sweeps.  want_vectors = false: eigenvalues only (O(m^2) instead of O(m^3)), V left empty.
+inline bool tridiag_eig(std::vector<double>& d, std::vector<double> e, int m, std::vector<double>& V,
+                        bool want_vectors = true) {
+  V.assign(want_vectors ? (size_t)m * m : 0, 0.0);
+  if (want_vectors)
+    for (int i = 0; i < m; ++i) V[(size_t)i + (size_t)m * i] = 1.0;
   if (m == 0) return true;
   e[(size_t)m - 1] = 0.0;
   for (int l = 0; l < m; ++l) {
@@ -60,7 +62,7 @@ inline bool tridiag_eig(std::vector<double>& d, std::vector<double> e, int m, st
           p = s * r;
           d[(size_t)i + 1] = g + p;
           g = c * r - b;
-          for (int k = 0; k < m; ++k) {
+          for (int k = 0; want_vectors && k < m; ++k) {
             double* vk = &V[(size_t)k];
             f = vk[(size_t)m * (i + 1)];
             vk[(size_t)m * (i + 1)] = s * vk[(size_t)m * i] + c * f;
@@ -78,14 +80,97 @@ inline bool tridiag_eig(std::vector<double>& d, std::vector<double> e, int m, st
   std::vector<int> idx((size_t)m);
   for (int i = 0; i < m; ++i) idx[(size_t)i] = i;
   std::sort(idx.begin(), idx.end(), [&](int a, int b) { return d[(size_t)a] < d[(size_t)b]; });
-  std::vector<double> d2((size_t)m), V2((size_t)m * m);
+  std::vector<double> d2((size_t)m), V2(V.size());
   for (int j = 0; j < m; ++j) {
     d2[(size_t)j] = d[(size_t)idx[(size_t)j]];
-    std::copy(V.begin() + (size_t)m * idx[(size_t)j], V.begin() + (size_t)m * (idx[(size_t)j] + 1),
-              V2.begin() + (size_t)m * j);
+    if (want_vectors)
+      std::copy(V.begin() + (size_t)m * idx[(size_t)j], V.begin() + (size_t)m * (idx[(size_t)j] + 1),
+                V2.begin() + (size_t)m * j);
   }
   d.swap(d2);
   V.swap(V2);
+  return true;
+}
+
+// One eigenvector of the symmetric tridiagonal (d, e) for the (computed) eigenvalue theta by inverse iteration:
+// LU of T - theta I with partial pivoting (the pivot row keeps at most three entries), three solves from a
+// fixed pseudo-random start.  x (m) is returned with unit 2-norm.
+inline void tridiag_inverse_iteration(const std::vector<double>& d, const std::vector<double>& e, int m, double theta,
+                                      double* x) {
+  std::vector<double> u0((size_t)m), u1((size_t)m, 0.0), u2((size_t)m, 0.0), mult((size_t)m, 0.0);
+  std::vector<char> swapped((size_t)m, 0);
+  double tnorm = 0.0;
+  for (int i = 0; i < m; ++i)
+    tnorm = std::max(tnorm, std::fabs(d[(size_t)i]) + (i + 1 < m ? std::fabs(e[(size_t)i]) : 0.0) +
+                                (i ? std::fabs(e[(size_t)i - 1]) : 0.0));
+  const double tiny = 2.220446049250313e-16 * std::max(tnorm, 1e-300);
+  double w0 = d[0] - theta, w1 = m > 1 ? e[0] : 0.0;  // working row: entries at columns i, i+1
+  for (int i = 0; i + 1 < m; ++i) {
+    const double sub = e[(size_t)i], dia = d[(size_t)i + 1] - theta, sup = (i + 2 < m) ? e[(size_t)i + 1] : 0.0;
+    if (std::fabs(sub) > std::fabs(w0)) {  // the next row becomes the pivot row
+      swapped[(size_t)i] = 1;
+      u0[(size_t)i] = sub; u1[(size_t)i] = dia; u2[(size_t)i] = sup;
+      const double mu = w0 / sub;
+      mult[(size_t)i] = mu;
+      w0 = w1 - mu * dia;
+      w1 = -mu * sup;
+    } else {
+      if (std::fabs(w0) < tiny) w0 = tiny;
+      u0[(size_t)i] = w0; u1[(size_t)i] = w1; u2[(size_t)i] = 0.0;
+      const double mu = sub / w0;
+      mult[(size_t)i] = mu;
+      w0 = dia - mu * w1;
+      w1 = sup;
+    }
+  }
+  if (std::fabs(w0) < tiny) w0 = tiny;
+  u0[(size_t)m - 1] = w0;
+  unsigned long long lcg = 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < m; ++i) {
+    lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+    x[i] = 0.5 + (double)(lcg >> 11) * (1.0 / 9007199254740992.0);  // in [0.5, 1.5): no accidental orthogonality
+  }
+  for (int it = 0; it < 3; ++it) {
+    for (int i = 0; i + 1 < m; ++i) {
+      if (swapped[(size_t)i]) std::swap(x[i], x[i + 1]);
+      x[i + 1] -= mult[(size_t)i] * x[i];
+    }
+    for (int i = m - 1; i >= 0; --i) {
+      double t = x[i];
+      if (i + 1 < m) t -= u1[(size_t)i] * x[i + 1];
+      if (i + 2 < m) t -= u2[(size_t)i] * x[i + 2];
+      x[i] = t / u0[(size_t)i];
+    }
+    double big = 0.0;
+    for (int i = 0; i < m; ++i) big = std::max(big, std::fabs(x[i]));
+    if (!(big > 0.0) || big != big) break;
+    double n2 = 0.0;
+    for (int i = 0; i < m; ++i) {
+      x[i] /= big;
+      n2 += x[i] * x[i];
+    }
+    const double inv = 1.0 / std::sqrt(n2);
+    for (int i = 0; i < m; ++i) x[i] *= inv;
+  }
+}
+
+// The k smallest eigenpairs of the tridiagonal (d, e): evals (k) ascending, vecs (m x k, column-major).
+// Small matrices: full QL with vectors; large ones: eigenvalues by QL, vectors by inverse iteration (ghost
+// copies of a converged Ritz value then yield nearly parallel vectors, which select_orthonormal drops).
+inline bool tridiag_smallest(const std::vector<double>& d, const std::vector<double>& e, int m, int k,
+                             std::vector<double>& evals, std::vector<double>& vecs, int full_below = 160) {
+  k = std::min(k, m);
+  std::vector<double> w(d), V;
+  if (m <= full_below) {
+    if (!tridiag_eig(w, e, m, V)) return false;
+    evals.assign(w.begin(), w.begin() + k);
+    vecs.assign(V.begin(), V.begin() + (size_t)m * k);
+    return true;
+  }
+  if (!tridiag_eig(w, e, m, V, false)) return false;
+  evals.assign(w.begin(), w.begin() + k);
+  vecs.assign((size_t)m * k, 0.0);
+  for (int j = 0; j < k; ++j) tridiag_inverse_iteration(d, e, m, evals[(size_t)j], &vecs[(size_t)m * j]);
   return true;
 }
 

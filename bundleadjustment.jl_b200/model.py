@@ -147,6 +147,12 @@ class BALNLPModel:
         clusters (default 16, at most 24; 0 = plain block-Jacobi).  Changes iteration counts, not solutions."""
         _lib.check(_lib.lib().ba_set_coarse_clusters(self.handle, int(n)), self.handle)
 
+    def set_deflation(self, k: int):
+        """PCG of the LM solve: add up to ``k`` (<= 32; default 32; 0 = off) Ritz vectors harvested from the PCG
+        solves themselves to the coarse level, plus up to 16 refreshed after every solve.  Changes iteration
+        counts, not solutions."""
+        _lib.check(_lib.lib().ba_set_deflation(self.handle, int(k)), self.handle)
+
     # ---- NLPModels surface ---------------------------------------------------------------------
     def obj(self, x):
         """NLPModels.obj: identically 0 (src/BALNLPModels.jl:109)."""

@@ -94,6 +94,11 @@ BA_API int ba_sync(ba_handle* h);
  * coarse level over `n` clusters of consecutive cameras (piecewise-constant interpolation of the six pose
  * components, n <= 24; default 16; 0 = plain block-Jacobi).  Changes the iteration count, not the solution. */
 BA_API int ba_set_coarse_clusters(ba_handle* h, int n);
+/* PCG deflation: extend the coarse level by up to `k` (<= 32; default 32; 0 = off) base vectors plus up to 16
+ * refreshed ones, all harvested from the PCG solves themselves (CG is a Lanczos process: Ritz vectors of the
+ * preconditioned reduced camera system come without extra products; ba_lm.cu).  Only used
+ * for camera systems above the single-CTA threshold.  Changes the iteration count, not the solution. */
+BA_API int ba_set_deflation(ba_handle* h, int k);
 /* Profiling: with it on, the per-observation evaluation kernel (k_eval: cons!/jac_coord!/fused) is
  * bracketed by CUDA events on the handle's stream and ba_last_eval_ms returns its device time alone
  * (waits for that kernel); for roofline reporting.  Off by default: the events would sit between the
@@ -165,6 +170,10 @@ BA_API int ba_comm_ipc_disable(ba_handle* h);
  * evals ascending (m), evecs column-major (m x m). */
 BA_API int ba_dbg_tridiag_eig(const double* alpha, const double* beta, int32_t m, double* evals,
                               double* evecs_colmajor);
+/* The k smallest eigenpairs only (evecs m x k column-major); matrices larger than full_below use QL for the
+ * values and inverse iteration for the vectors. */
+BA_API int ba_dbg_tridiag_smallest(const double* alpha, const double* beta, int32_t m, int32_t k, int32_t full_below,
+                                   double* evals, double* evecs_colmajor);
 /* From the Gram matrix (n x n, row-major) of n candidate vectors in preference order keep up to k that are
  * numerically independent (remainder >= tol of their norm) and return coefficients (n x kept, row-major) that
  * orthonormalise them. */

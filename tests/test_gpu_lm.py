@@ -281,3 +281,28 @@ def test_points_seen_by_more_than_32_cameras(ba, oracle):
     st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=6)
     ref = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, oracle.default_params(ite_max=6))
     _compare_trajectories(st, ref, f_tol=1e-8)
+
+
+@pytest.mark.gpu
+def test_deflated_pcg_gives_the_same_step_in_fewer_iterations(ba):
+    """PCG deflation (ba_set_deflation): the first solve harvests Ritz vectors, the second one -- same system --
+    uses them.  Same step to PCG accuracy, at most half the iterations."""
+    from conftest import assert_rel
+    p = ba.synth.make_problem((160, 10000, 50000))       # 1440 camera rows: the multi-CTA vector kernels
+    m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    m.set_deflation(0)
+    d_ref, dr_ref, _, _, it_ref = ba.lm_step(m, p.x0, 30.0, pcg_max_iter=2000)
+    m.set_deflation(32)
+    d0, _, _, _, it0 = ba.lm_step(m, p.x0, 30.0, pcg_max_iter=2000)
+    d1, dr1, _, _, it1 = ba.lm_step(m, p.x0, 30.0, pcg_max_iter=2000)
+    d2, _, _, _, it2 = ba.lm_step(m, p.x0, 3.0, pcg_max_iter=2000)      # other damping: stale vectors + refresh
+    m.set_deflation(0)
+    d3, _, _, _, it3 = ba.lm_step(m, p.x0, 3.0, pcg_max_iter=2000)
+    m.close()
+    assert it0 == it_ref and np.array_equal(d0, d_ref)   # harvesting alone changes nothing
+    assert_rel(d1, d_ref, 1e-9, what="deflated step")
+    assert abs(dr1 - dr_ref) <= 1e-9 * abs(dr_ref)
+    assert it_ref >= 48, it_ref                           # otherwise nothing was harvested
+    assert 2 * it1 <= it_ref, (it_ref, it1)
+    assert_rel(d2, d3, 1e-9, what="deflated step, other lambda")
+    assert 2 * it2 <= it3, (it3, it2)

@@ -67,3 +67,76 @@ def test_two_gpu_lm_matches_one_gpu(ba, small_max):
     assert rel(got["x"], st.solution) <= 1e-7
     w = np.random.default_rng(1).normal(size=2 * p.nobs)
     assert rel(got["jtw"], m.jtprod_(p.x0, w)) <= 1e-11
+
+
+BIG = (160, 10000, 50000)   # 1440 camera rows: multi-CTA vector kernels, PCG long enough to harvest Ritz vectors
+
+
+def _deflated_sequence(ba, m, p):
+    out = []
+    for lam in (30.0, 30.0, 3.0):          # harvest; deflated; stale vectors + refreshed ones
+        d, dr2, _, _, it = ba.lm_step(m, p.x0, lam, pcg_max_iter=2000)
+        out.append((d, dr2, it))
+    st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=4, pcg_max_iter=2000)
+    return out, st
+
+
+def _worker_deflated(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["BAGPU_DEFLATE_MULTI"] = "1"
+    import torch
+    import torch.distributed as dist
+    import bundleadjustment.jl_b200 as ba
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = ba.synth.make_problem(BIG)
+    m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs, device=rank, rank=rank, nranks=world)
+    m.set_deflation(32)
+    ba.init_comm(m)
+    seq, st = _deflated_sequence(ba, m, p)
+    if rank == 0:
+        q.put(dict(seq=seq, f=[r["f"] for r in st.rows], acc=[r["accepted"] for r in st.rows],
+                   pcg=[r["pcg_iters"] for r in st.rows], objective=st.objective))
+    dist.barrier()
+    m.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_deflated_pcg_matches_one_gpu(ba):
+    """The deflation vectors are built from replicated data with the same arithmetic on every rank: the sharded
+    run must follow the single-GPU one (same steps to PCG accuracy, same iteration counts up to rounding)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000) + 13
+    procs = [ctx.Process(target=_worker_deflated, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    got = q.get(timeout=600)
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    p = ba.synth.make_problem(BIG)
+    m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    m.set_deflation(32)
+    seq, st = _deflated_sequence(ba, m, p)
+    m.set_deflation(0)
+    d_plain, _, _, _, it_plain = ba.lm_step(m, p.x0, 30.0, pcg_max_iter=2000)
+    m.close()
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    print("pcg iterations: plain", it_plain, "1 GPU", [s[2] for s in seq], "2 GPUs", [s[2] for s in got["seq"]],
+          "LM", [r["pcg_iters"] for r in st.rows], got["pcg"])
+    for (d2, dr2, it2), (d1, dr1, it1) in zip(got["seq"], seq):
+        assert rel(d2, d1) <= 1e-9
+        assert abs(dr2 - dr1) <= 1e-9 * abs(dr1)
+        assert abs(it2 - it1) <= max(3, 0.2 * it1), (it1, it2)
+    assert rel(got["seq"][0][0], d_plain) <= 1e-9
+    assert 2 * got["seq"][1][2] <= it_plain, (it_plain, got["seq"][1][2])      # the vectors are in use on 2 GPUs
+    assert got["acc"] == [r["accepted"] for r in st.rows]
+    assert np.allclose(got["f"], [r["f"] for r in st.rows], rtol=1e-8, atol=0)
+    assert abs(got["objective"] - st.objective) <= 1e-8 * st.objective
