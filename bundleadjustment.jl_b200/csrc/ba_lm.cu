@@ -166,9 +166,7 @@ int lm_prepare(ba_handle* h) {
     S.mc = CDOF * S.ncl;
     // deflation vectors share the coarse solve (mc + kz <= 144); small systems use the fused kernel without them
     S.kz_max = S.kz_base_max = 0;
-    // (sharded runs: the code path is rank-symmetric but has not been validated on several GPUs yet)
-    static const bool defl_multi = getenv("BAGPU_DEFLATE_MULTI") != nullptr;
-    if (h->deflate > 0 && 9 * ncams > small_rows_max() && (h->nranks == 1 || defl_multi)) {
+    if (h->deflate > 0 && 9 * ncams > small_rows_max()) {
       S.kz_max = std::min(144 - S.mc, h->deflate + DEFL_ROLL);
       S.kz_base_max = std::min(h->deflate, S.kz_max);
     }

@@ -83,7 +83,6 @@ def _deflated_sequence(ba, m, p):
 
 def _worker_deflated(rank, world, port, q):
     sys.path.insert(0, ROOT)
-    os.environ["BAGPU_DEFLATE_MULTI"] = "1"
     import torch
     import torch.distributed as dist
     import bundleadjustment.jl_b200 as ba
