@@ -324,6 +324,11 @@ def main():
         bpo = algorithmic_bytes_per_obs(p)
         # per-launch algorithmic bytes of the dominant kernel on one rank (rank 0's shard)
         achieved = bpo * nl / (k_ms * 1e-3) / 1e9
+        # secondary ceiling: FP64 FMA throughput measured on this GPU by the library's probe
+        fp64 = C.c_double(0.0)
+        fp64_peak = fp64.value if L.ba_measure_fp64_peak(local, C.byref(fp64)) == 0 else None
+        flops_obs = 180.0  # algorithmic FP64 flops per observation with the per-camera precompute (section 8d)
+        fp64_ach = flops_obs * nl / (k_ms * 1e-3) / 1e12
         out = {
             "metric": METRIC, "value": p.nobs / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
@@ -341,7 +346,10 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, world),
                          "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bpo * nl,
-                         "kernel_ms": k_ms, "bytes_per_obs": bpo, "frac_of_nominal_8TBs": achieved / 8000.0},
+                         "kernel_ms": k_ms, "bytes_per_obs": bpo, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "fp64": {"peak_TFLOPs_measured": fp64_peak, "flops_per_obs": flops_obs,
+                                  "achieved_TFLOPs": fp64_ach, "frac": fp64_ach / fp64_peak if fp64_peak else None,
+                                  "note": "secondary ceiling; ncu: FP64 pipe 21 % busy in k_eval"}},
             "clocks": clocks,
             "jac_structure": {"ms": js_ms, "GB/s": 392.0 * nl / (js_ms * 1e-3) / 1e9,
                               "bytes_per_obs": 392, "note": "rank 0 shard; 2 x 24 Int64 written + 8 B of indices read"},

@@ -54,6 +54,7 @@ SYMBOLS = {
     "ba_partition_observations": (C.c_int, [_i64, _vp, C.c_int, _vp]),
     "ba_last_error": (C.c_char_p, [_vp]),
     "ba_version": (C.c_char_p, []),
+    "ba_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "ba_set_stream": (C.c_int, [_vp, _vp]),
     "ba_alloc_pinned": (C.c_int, [C.c_uint64, C.POINTER(_vp)]),
     "ba_free_pinned": (C.c_int, [_vp]),

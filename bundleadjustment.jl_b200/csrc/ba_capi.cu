@@ -94,7 +94,55 @@ int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, 
 
 }  // namespace
 
+namespace {
+// FP64 FMA throughput probe: 8 independent chains per thread, operands from kernel arguments so that
+// nothing folds at compile time
+__global__ void __launch_bounds__(256) k_fp64_fma(double* out, int iters, double a, double b) {
+  double x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = (double)(threadIdx.x + j) * 1e-3;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = fma(x[j], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += x[j];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
 extern "C" {
+
+int ba_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return BA_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return BA_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BA_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+  double* out = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(reinterpret_cast<void**>(&out), sizeof(double) * 256 * (size_t)blocks) != cudaSuccess) return BA_ERR_CUDA;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 0.f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up; keep the fastest of the rest
+    cudaEventRecord(e0, 0);
+    k_fp64_fma<<<blocks, 256>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+  }
+  const cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (err != cudaSuccess || !(best > 0.f)) return BA_ERR_CUDA;
+  *tflops = 2.0 * 8.0 * iters * 256.0 * blocks / (best * 1e-3) / 1e12;
+  return BA_OK;
+}
 
 const char* ba_version(void) { return "bagpu 0.1 (sm_100a, fp64)"; }
 

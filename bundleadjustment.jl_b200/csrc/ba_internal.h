@@ -75,6 +75,8 @@ struct ba_lm_state {
   double* d_hcoef = nullptr;    // [alpha (hcap) | beta (hcap)] of the harvested solve
   double* d_zpart = nullptr;    // per vector-kernel CTA: kz partial dot products Z_j . r
   double* d_dsmall = nullptr;   // hcap x 64 coefficient matrix / 64 x 64 Gram matrix
+  double2* d_w4 = nullptr;      // 4 x nl: per-observation exchange of the 4-vector Schur product (coarse setup)
+  double* d_q4 = nullptr;       // 4 x n9: its results
   int pcg_graph_kz = -1;        // kz the captured PCG graph was built for
   int z_gen = 0, coarse_gen = 0;  // version of Z, and the version the current Ac^-1 was built for
   int defl_iters_first = 0;     // PCG iterations of the solve the base vectors came from

@@ -59,6 +59,7 @@ inline int64_t small_rows_max() {
 constexpr int DEFL_ROLL = 16;   // deflation vectors refreshed after every solve (on top of the base ones)
 constexpr int DEFL_CAND = 64;   // candidates per selection (= DG_N, the widest k_defl_gemm output)
 constexpr int DEFL_HCAP = 1024; // Lanczos vectors kept per solve at most
+constexpr int DEFL_NR = 4;      // vectors per pass of the multi-vector Schur product (coarse setup)
 
 }  // namespace
 
@@ -71,6 +72,12 @@ int lm_prepare(ba_handle* h) {
   }
   BA_CUDA(cudaSetDevice(h->device));
   const int64_t nl = h->nobs_l(), npl = h->npnts_l(), ncams = h->ncams;
+  const bool trace = getenv("BAGPU_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double>(now() - t).count() * 1e3;
+  };
+  const auto tp0 = now();
   // ---- point-major warp tasks: whole points, <= 32 observations; a longer point is a task of its own
   std::vector<int32_t> tstart, pstart((size_t)npl + 1, 0);
   {
@@ -128,6 +135,8 @@ int lm_prepare(ba_handle* h) {
   S.nctasks = (int64_t)tb.size();
 
   int rc;
+  const double t_host = ms_since(tp0);
+  const auto tp1 = now();
 #define ALLOC(ptr, n) if ((rc = dmalloc(h, &(ptr), (size_t)(n)))) return rc
   ALLOC(S.d_tstart, tstart.size());
   ALLOC(S.d_pstart, pstart.size());
@@ -167,7 +176,7 @@ int lm_prepare(ba_handle* h) {
     // deflation vectors share the coarse solve (mc + kz <= 144); small systems use the fused kernel without them
     S.kz_max = S.kz_base_max = 0;
     if (h->deflate > 0 && 9 * ncams > small_rows_max()) {
-      S.kz_max = std::min(144 - S.mc, h->deflate + DEFL_ROLL);
+      S.kz_max = std::min(std::min(144 - S.mc, KZ_LIMIT), h->deflate + DEFL_ROLL);
       S.kz_base_max = std::min(h->deflate, S.kz_max);
     }
     const int64_t mt = S.mc + S.kz_max;
@@ -181,6 +190,8 @@ int lm_prepare(ba_handle* h) {
       ALLOC(S.d_Z, 9 * ncams * S.kz_max);
       ALLOC(S.d_Zcand, 9 * ncams * DEFL_CAND);
       ALLOC(S.d_zpart, (int64_t)nvb * S.kz_max);
+      ALLOC(S.d_w4, DEFL_NR * nl);
+      ALLOC(S.d_q4, DEFL_NR * 9 * ncams);
     }
   }
   ALLOC(S.d_x, h->nvar());
@@ -193,6 +204,8 @@ int lm_prepare(ba_handle* h) {
 #undef ALLOC
   BA_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&S.h_scal), S_COUNT * sizeof(double), cudaHostAllocDefault));
   for (auto& e : S.ev) BA_CUDA(cudaEventCreate(&e));
+  const double t_alloc = ms_since(tp1);
+  const auto tp2 = now();
   auto up = [&](void* d, const void* s, size_t bytes) {
     return bytes ? cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
   };
@@ -211,6 +224,9 @@ int lm_prepare(ba_handle* h) {
   BA_CUDA(cudaMemsetAsync(S.d_scal, 0, S_COUNT * sizeof(double), h->stream));
   BA_CUDA(cudaMemsetAsync(S.d_delta, 0, sizeof(double) * (size_t)h->nvar(), h->stream));
   BA_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+  if (trace)
+    fprintf(stderr, "[bagpu] lm_prepare: schedules on the host %.1f ms, device allocations %.1f ms, uploads %.1f ms\n",
+            t_host, t_alloc, ms_since(tp2));
   S.ready = true;
   return BA_OK;
 }
@@ -239,7 +255,7 @@ void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,
                   S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
-                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_Z, S.d_Zcand, S.d_harv, S.d_hcoef, S.d_zpart, S.d_dsmall, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
+                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_Z, S.d_Zcand, S.d_harv, S.d_hcoef, S.d_zpart, S.d_dsmall, S.d_w4, S.d_q4, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
   for (void* p : ptrs) cudaFree(p);
   if (S.h_scal) cudaFreeHost(S.h_scal);
   if (S.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph));
@@ -366,12 +382,63 @@ struct Solver {
           k_coarse_restrict<<<S.ncl, 288, 0, s>>>(ncams, cpc, m, col, q, S.d_Ac);
           if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
         }
-      for (int j = 0; j < S.kz; ++j) {  // columns S Z_j: P rows by restriction, Z rows by dot products
-        BA_CUDA(cudaMemcpyAsync(p, S.d_Z + (int64_t)j * n9, sizeof(double) * (size_t)n9, cudaMemcpyDeviceToDevice, s));
-        if ((rc = s_product(false))) return rc;
-        if (S.ncl > 0) k_coarse_restrict<<<S.ncl, 288, 0, s>>>(ncams, cpc, m, S.mc + j, q, S.d_Ac);
-        k_defl_zdot<<<S.kz, 256, 0, s>>>(n9, S.d_Z, q, S.d_Ac, m, S.mc, S.mc + j);
-        if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
+      // columns S Z_j: P rows by restriction, Z rows by dot products.  DEFL_NR vectors share one pass over the
+      // J blocks (k_point_solve_multi / k_cam_pass_multi); a remainder goes through the single-vector product.
+      auto z_columns = [&](bool multi) -> int {
+        int j = 0;
+        for (; multi && j + DEFL_NR <= S.kz; j += DEFL_NR) {
+          const double* zj = S.d_Z + (int64_t)j * n9;
+          if (S.ntasks)
+            k_point_solve_multi<DEFL_NR><<<nblk(S.ntasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
+                S.d_tstart, S.ntasks, h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, zj, n9, S.d_Vinv, S.d_w4);
+          if (S.nctasks)
+            k_cam_pass_multi<DEFL_NR><<<nblk(S.nctasks, PT_THREADS / 32), PT_THREADS, 0, s>>>(
+                S.d_ctask_beg, S.d_ctask_end, S.nctasks, S.d_ctask_cam, S.d_cam_t0, S.d_cam_cnt, S.d_cperm, S.d_pntc, nl,
+                h->d_camtab, S.d_x4, S.d_w4, S.d_taskpart, S.d_q4, n9);
+          if (S.nempty)
+            for (int r = 0; r < DEFL_NR; ++r)
+              k_zero_cams<<<nblk((int64_t)S.nempty * 9, 256), 256, 0, s>>>(S.d_empty_cams, (int)S.nempty, 9,
+                                                                          S.d_q4 + (int64_t)r * n9, nullptr, nullptr, n9);
+          if ((rc = check())) return rc;
+          if ((rc = allreduce_sum(h, S.d_q4, (size_t)(DEFL_NR * n9)))) return rc;
+          k_defl_hq<<<nblk(DEFL_NR * n9, 256), 256, 0, s>>>(n9, DEFL_NR, S.d_H, zj, n9, S.d_q4);
+          for (int r = 0; r < DEFL_NR; ++r) {
+            const double* qr = S.d_q4 + (int64_t)r * n9;
+            if (S.ncl > 0) k_coarse_restrict<<<S.ncl, 288, 0, s>>>(ncams, cpc, m, S.mc + j + r, qr, S.d_Ac);
+            k_defl_zdot<<<S.kz, 256, 0, s>>>(n9, S.d_Z, qr, S.d_Ac, m, S.mc, S.mc + j + r);
+          }
+        }
+        for (; j < S.kz; ++j) {
+          BA_CUDA(cudaMemcpyAsync(p, S.d_Z + (int64_t)j * n9, sizeof(double) * (size_t)n9, cudaMemcpyDeviceToDevice, s));
+          if ((rc = s_product(false))) return rc;
+          if (S.ncl > 0) k_coarse_restrict<<<S.ncl, 288, 0, s>>>(ncams, cpc, m, S.mc + j, q, S.d_Ac);
+          k_defl_zdot<<<S.kz, 256, 0, s>>>(n9, S.d_Z, q, S.d_Ac, m, S.mc, S.mc + j);
+          if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
+        }
+        return check();
+      };
+      const bool single_only = getenv("BAGPU_DEFL_SINGLE") != nullptr;
+      if ((rc = z_columns(!single_only))) return rc;
+      if (S.kz > 0 && getenv("BAGPU_DEFL_CHECK") && !single_only) {
+        // cross-check: the same columns vector by vector must agree to rounding
+        std::vector<double> a((size_t)m * m), bref((size_t)m * m);
+        BA_CUDA(cudaMemcpyAsync(a.data(), S.d_Ac, a.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        BA_CUDA(cudaStreamSynchronize(s));
+        if ((rc = z_columns(false))) return rc;
+        BA_CUDA(cudaMemcpyAsync(bref.data(), S.d_Ac, bref.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        BA_CUDA(cudaStreamSynchronize(s));
+        double worst = 0.0, big = 0.0;
+        for (int row = 0; row < m; ++row)
+          for (int col = S.mc; col < m; ++col) {
+            worst = std::max(worst, std::fabs(a[(size_t)row * m + col] - bref[(size_t)row * m + col]));
+            big = std::max(big, std::fabs(bref[(size_t)row * m + col]));
+          }
+        fprintf(stderr, "[bagpu] coarse setup check: multi-vector vs single-vector columns differ by %.3e (max entry %.3e)\n",
+                worst, big);
+        if (!(worst <= 1e-11 * big)) {
+          h->err = "multi-vector Schur product disagrees with the single-vector one";
+          return BA_ERR_NUMERIC;
+        }
       }
       if (S.kz > 0 && S.mc > 0) k_defl_symfill<<<nblk((int64_t)S.kz * S.mc, 256), 256, 0, s>>>(m, S.mc, S.d_Ac);
     }
@@ -489,7 +556,7 @@ struct Solver {
     k_pcg_xr<INIT><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, b, S.d_Minv, p, q, xc, r, z, ppq, prz, S.d_scal,
                                                S.ncl > 0 ? S.d_cpart : nullptr, S.d_Z, S.kz, S.d_zpart);
     if (coarse)
-      k_pcg_coarse<<<1, 160, 0, s>>>(nvb, S.ctas_per_cluster, m, S.d_cpart, S.d_Aci, S.d_yc, S.d_scal, INIT ? 1 : 0,
+      k_pcg_coarse<<<1, COARSE_THREADS, 0, s>>>(nvb, S.ctas_per_cluster, m, S.d_cpart, S.d_Aci, S.d_yc, S.d_scal, INIT ? 1 : 0,
                                      S.kz, S.d_zpart);
     k_pcg_p<INIT><<<nvb, VEC_THREADS, 0, s>>>(n9, nvb, z, p, ppq, prz, S.d_scal, tol,
                                               (!INIT && p2p) ? h->p2p.d_seq : nullptr, coarse ? S.d_yc : nullptr,

@@ -668,6 +668,7 @@ constexpr int VEC_THREADS = 256;
 constexpr int CDOF = 6;  // coarse unknowns per camera cluster: the pose components (r, t); adding k1, k2, f to the
                        // coarse space does not reduce PCG iterations further (prototype: 165 vs 166)
 constexpr int VEC_ROWS = 252;  // 28 cameras x 9 rows per CTA
+constexpr int KZ_LIMIT = 48;   // deflation vectors at most (32 base + 16 refreshed)
 
 __device__ __forceinline__ double row9(const double* __restrict__ M, const double* v, int64_t i) {
   const int64_t c = i / 9;
@@ -820,12 +821,26 @@ k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i0 = blockIdx.x * (int64_t)VEC_ROWS;
     const int nrow = (int)min((long long)VEC_ROWS, (long long)(n9 - i0));
-    for (int j = warp; j < kz; j += VEC_THREADS / 32) {
-      const double* zj = Zb + (int64_t)j * n9 + i0;
-      double t = 0.0;
-      for (int a = lane; a < nrow; a += 32) t += zj[a] * rs[a];
-      t = warp_sum(t);
-      if (lane == 0) zpart[(int64_t)blockIdx.x * kz + j] = t;
+    constexpr int NW = VEC_THREADS / 32;
+    double t[KZ_LIMIT / NW];  // the warp's vectors (j = warp, warp + 8, ...) advance together: independent loads
+#pragma unroll
+    for (int u = 0; u < KZ_LIMIT / NW; ++u) t[u] = 0.0;
+#pragma unroll 4
+    for (int a = lane; a < nrow; a += 32) {
+      const double ra = rs[a];
+#pragma unroll
+      for (int u = 0; u < KZ_LIMIT / NW; ++u) {
+        const int j = warp + NW * u;
+        if (j < kz) t[u] += Zb[(int64_t)j * n9 + i0 + a] * ra;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < KZ_LIMIT / NW; ++u) {
+      const int j = warp + NW * u;
+      if (j < kz) {  // warp-uniform
+        const double tt = warp_sum(t[u]);
+        if (lane == 0) zpart[(int64_t)blockIdx.x * kz + j] = tt;
+      }
     }
   }
 }
@@ -835,38 +850,55 @@ k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __r
 // cluster), Ac = P' S P.
 // rc = P' r from the per-CTA partials (a CTA never straddles clusters), yc = Ac^-1 rc, and r.(P yc) = rc.yc
 // for the r.z dot product.  One CTA; m = CDOF ncl <= 144.
-__global__ void __launch_bounds__(160)
+constexpr int COARSE_THREADS = 1024, COARSE_GROUPS = COARSE_THREADS / 144;  // 7 groups of 144 threads
+__global__ void __launch_bounds__(COARSE_THREADS)
 k_pcg_coarse(int nvb, int ctas_per_cluster, int m, const double* __restrict__ cpart, const double* __restrict__ Aci,
              double* __restrict__ yc, double* scal, int init, int kz, const double* __restrict__ zpart) {
-  __shared__ double rc[144], yy[144];
+  __shared__ double rc[144], yy[144], part[COARSE_GROUPS][144];
   if (!init && scal[S_DONE] != 0.0) return;
-  const int a = threadIdx.x;
+  const int t = threadIdx.x, lane = t & 31;
   const int mcl = m - kz;  // cluster unknowns first, then one unknown per deflation vector
-  if (a < mcl) {
-    const int I = a / CDOF, jj = a - CDOF * I;
+  if (t < mcl) {
+    const int I = t / CDOF, jj = t - CDOF * I;
     const int b0 = I * ctas_per_cluster, b1 = min(nvb, b0 + ctas_per_cluster);
-    double t = 0.0;
-    for (int bb = b0; bb < b1; ++bb) t += cpart[bb * 9 + jj];
-    rc[a] = t;
+    double v = 0.0;
+    for (int bb = b0; bb < b1; ++bb) v += cpart[bb * 9 + jj];
+    rc[t] = v;
   }
-  for (int j = a >> 5; j < kz; j += 160 / 32) {  // Z_j . r: a warp sums the per-CTA partials of one vector
-    double t = 0.0;
-    for (int bb = a & 31; bb < nvb; bb += 32) t += zpart[(int64_t)bb * kz + j];
-    t = warp_sum(t);
-    if ((a & 31) == 0) rc[mcl + j] = t;
-  }
-  __syncthreads();
-  if (a < m) {
-    double t = 0.0;
-    for (int bq = 0; bq < m; ++bq) t += Aci[bq * m + a] * rc[bq];  // Aci is exactly symmetric: coalesced reads
-    yy[a] = t;
-    yc[a] = t;
+  for (int j = t >> 5; j < kz; j += COARSE_THREADS / 32) {  // Z_j . r: a warp sums the per-CTA partials of one vector
+    double v = 0.0;
+    for (int bb = lane; bb < nvb; bb += 32) v += zpart[(int64_t)bb * kz + j];
+    v = warp_sum(v);
+    if (lane == 0) rc[mcl + j] = v;
   }
   __syncthreads();
-  if (a == 0) {
-    double t = 0.0;
-    for (int bq = 0; bq < m; ++bq) t += rc[bq] * yy[bq];
-    scal[S_RCY] = t;
+  // yc = Aci rc: the m columns are split over 7 thread groups (Aci is exactly symmetric, so group g reads rows
+  // of its column range: coalesced), partial sums added in group order
+  const int g = t / 144, a = t - 144 * g;
+  if (g < COARSE_GROUPS) {
+    const int chunk = (m + COARSE_GROUPS - 1) / COARSE_GROUPS;
+    const int q0 = g * chunk, q1 = min(m, q0 + chunk);
+    double v = 0.0;
+    if (a < m) {
+#pragma unroll 8
+      for (int bq = q0; bq < q1; ++bq) v += Aci[bq * m + a] * rc[bq];
+    }
+    part[g][a] = v;
+  }
+  __syncthreads();
+  if (t < m) {
+    double v = 0.0;
+#pragma unroll
+    for (int gg = 0; gg < COARSE_GROUPS; ++gg) v += part[gg][t];
+    yy[t] = v;
+    yc[t] = v;
+  }
+  __syncthreads();
+  if (t < 32) {  // r.(coarse correction) = rc.yc
+    double v = 0.0;
+    for (int bq = t; bq < m; bq += 32) v += rc[bq] * yy[bq];
+    v = warp_sum(v);
+    if (t == 0) scal[S_RCY] = v;
   }
 }
 
@@ -887,6 +919,7 @@ k_pcg_p(int64_t n9, int nparts, const double* z, double* p, const double* part_p
   if (yc && live) {
     const int comp = (int)(i % 9);
     if (mcl > 0 && comp < CDOF) zc = yc[(blockIdx.x / ctas_per_cluster) * CDOF + comp];
+#pragma unroll 16
     for (int j = 0; j < kz; ++j) zc += Zb[(int64_t)j * n9 + i] * yc[mcl + j];
   }
   if (INIT) {
@@ -1203,7 +1236,176 @@ k_coarse_invert(int m, const double* __restrict__ Ac, double* __restrict__ Aci, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Deflation vectors (DESIGN.md section 9): the coarse space is [P | Z] with Z (n9 x kz, column-major,
+// Schur product for NR vectors at once (setup of the deflation block of the coarse matrix: S Z_j for all j).
+// The J blocks -- the bulk of the traffic of the point-major pass -- and the recomputed camera parts of the
+// camera-major pass are shared by the NR right-hand sides.  Same arithmetic per vector as k_point_solve<0> /
+// k_cam_pass<2>; no done-flag, no mailbox: the sum over ranks goes through NCCL once per NR vectors.
+// ---------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(PT_THREADS, 4)
+k_point_solve_multi(const int32_t* __restrict__ tstart, int64_t ntasks, const int32_t* __restrict__ cam_idx,
+                    const int32_t* __restrict__ pnt_idx, int64_t pnt0, int64_t nl, const double2* __restrict__ Jp,
+                    const double* __restrict__ vcam, int64_t vstride, const double* __restrict__ Vinv,
+                    double2* __restrict__ w_out /* NR planes of nl */) {
+  __shared__ double vst[(PT_THREADS / 32) * 288];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t task = blockIdx.x * (int64_t)(PT_THREADS / 32) + warp;
+  double* vrow = vst + warp * 288;
+  if (task >= ntasks) return;  // (no block-wide barrier below)
+  auto second_half = [&](int64_t k, const PtLane& L, double T0, double T1, double T2, int r) {
+    const double i00 = L.vi[0], i01 = L.vi[1], i02 = L.vi[2], i11 = L.vi[3], i12 = L.vi[4], i22 = L.vi[5];
+    const double u0 = (i00 * T0 + i01 * T1) + i02 * T2, u1 = (i01 * T0 + i11 * T1) + i12 * T2,
+                 u2 = (i02 * T0 + i12 * T1) + i22 * T2;
+    w_out[(int64_t)r * nl + k] =
+        make_double2((L.A0.x * u0 + L.A1.x * u1) + L.A2.x * u2, (L.A0.y * u0 + L.A1.y * u1) + L.A2.y * u2);
+  };
+  const int64_t t0 = tstart[task], t1 = tstart[task + 1];
+  if (t1 - t0 <= 32) {
+    const int64_t k = t0 + lane;
+    const bool valid = k < t1;
+    int c = 0, p = -1;
+    if (valid) {
+      c = __ldg(cam_idx + k);
+      p = (int)(__ldg(pnt_idx + k) - pnt0);
+    }
+    PtLane L;
+    pt_load<0>(L, valid, k, p, nl, Jp, nullptr, Vinv, nullptr);
+    const int pprev = __shfl_up_sync(0xffffffffu, p, 1);
+    const bool head = (lane == 0) || (p != pprev);
+    const unsigned hm = __ballot_sync(0xffffffffu, head);
+    const int seg0 = 31 - __clz(hm & (0xffffffffu >> (31 - lane)));
+    const unsigned above = (lane == 31) ? 0u : (hm >> (lane + 1));
+    const int tail = above ? lane + __ffs(above) - 1 : 31;
+    for (int r = 0; r < NR; ++r) {
+      __syncwarp();  // every lane is done with the previous vector's rows
+      warp_stage_vec9(vcam + (int64_t)r * vstride, c, lane, vrow);
+      pt_first(L, vrow, lane);
+      double s0 = L.t0, s1 = L.t1, s2 = L.t2;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double a = shfl_up_d(s0, d), b = shfl_up_d(s1, d), cc = shfl_up_d(s2, d);
+        if (lane - d >= seg0) {
+          s0 += a;
+          s1 += b;
+          s2 += cc;
+        }
+      }
+      const double T0 = shfl_d(s0, tail), T1 = shfl_d(s1, tail), T2 = shfl_d(s2, tail);
+      if (valid) second_half(k, L, T0, T1, T2, r);
+    }
+  } else {
+    // one point with more than 32 observations (rare): vector by vector, as k_point_solve does
+    const int64_t p = __ldg(pnt_idx + t0) - pnt0;
+    for (int r = 0; r < NR; ++r) {
+      double T0 = 0.0, T1 = 0.0, T2 = 0.0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t base = t0; base < t1; base += 32) {
+          const int64_t k = base + lane;
+          const bool valid = k < t1;
+          const int c = valid ? __ldg(cam_idx + k) : 0;
+          PtLane L;
+          pt_load<0>(L, valid, k, p, nl, Jp, nullptr, Vinv, nullptr);
+          __syncwarp();
+          warp_stage_vec9(vcam + (int64_t)r * vstride, c, lane, vrow);
+          pt_first(L, vrow, lane);
+          if (pass == 0) {
+            T0 += warp_sum(L.t0);
+            T1 += warp_sum(L.t1);
+            T2 += warp_sum(L.t2);
+          } else if (valid) {
+            second_half(k, L, T0, T1, T2, r);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(PT_THREADS, 3)
+k_cam_pass_multi(const int32_t* __restrict__ tbeg, const int32_t* __restrict__ tend, int64_t nctasks,
+                 const int32_t* __restrict__ task_cam, const int32_t* __restrict__ cam_t0,
+                 int32_t* __restrict__ cam_cnt, const int32_t* __restrict__ cperm, const int32_t* __restrict__ pntc,
+                 int64_t nl, const double* __restrict__ camtab, const double2* __restrict__ x4,
+                 const double2* __restrict__ w /* NR planes of nl */, double* taskpart /* nctasks x 9 NR */,
+                 double* __restrict__ out /* NR x n9 */, int64_t n9) {
+  constexpr int NACC = 9 * NR;
+  const int lane = threadIdx.x & 31;
+  const int64_t task = blockIdx.x * (int64_t)(PT_THREADS / 32) + (threadIdx.x >> 5);
+  if (task >= nctasks) return;
+  const int c = task_cam[task];
+  double cam[14];
+  {
+    const double2* src = reinterpret_cast<const double2*>(camtab + (int64_t)c * CAM_REC);  // warp-uniform
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const double2 t = __ldg(src + i);
+      cam[2 * i] = t.x;
+      cam[2 * i + 1] = t.y;
+    }
+  }
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+  const int e = tend[task];
+  for (int pos = tbeg[task] + lane; pos < e; pos += 32) {
+    const int k = __ldg(cperm + pos);
+    const int p = __ldg(pntc + pos);
+    const double2 xa = __ldg(x4 + 2 * (int64_t)p), xb = __ldg(x4 + 2 * (int64_t)p + 1);
+    double2 wk[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) wk[r] = w[(int64_t)r * nl + k];
+    const double X[3] = {xa.x, xa.y, xb.x};
+    ObsBlock o;
+    eval_block<false>(X, cam, 0.0, 0.0, o);  // camera part only
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const double bx = nan0(o.B[j]), by = nan0(o.B[9 + j]);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r * 9 + j] += bx * wk[r].x + by * wk[r].y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = warp_sum(acc[i]);
+  const int tb0 = cam_t0[c], nt = cam_t0[c + 1] - tb0;
+  if (nt == 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) out[(int64_t)(i / 9) * n9 + (int64_t)c * 9 + (i % 9)] = acc[i];
+    }
+    return;
+  }
+  int last = 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) taskpart[task * NACC + i] = acc[i];
+    __threadfence();
+    last = (atomicAdd(cam_cnt + c, 1) == nt - 1);
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {
+    __threadfence();
+    for (int j = lane; j < NACC; j += 32) {
+      double s = 0.0;
+      for (int t = 0; t < nt; ++t) s += __ldcg(taskpart + (int64_t)(tb0 + t) * NACC + j);
+      out[(int64_t)(j / 9) * n9 + (int64_t)c * 9 + (j % 9)] = s;
+    }
+    if (lane == 0) cam_cnt[c] = 0;
+  }
+}
+
+// q_r = H v_r - q_r for NR vectors (v_r = v + r vstride, q_r = q + r n9): finishes S v_r
+__global__ void __launch_bounds__(256)
+k_defl_hq(int64_t n9, int nr, const double* __restrict__ H, const double* __restrict__ v, int64_t vstride,
+          double* __restrict__ q) {
+  const int64_t e = blockIdx.x * (int64_t)256 + threadIdx.x;
+  if (e >= n9 * nr) return;
+  const int64_t r = e / n9, i = e - r * n9;
+  q[e] = row9(H, v + r * vstride, i) - q[e];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deflation vectors (DESIGN.md section 5): the coarse space is [P | Z] with Z (n9 x kz, column-major,
 // Euclidean-orthonormal) built from Ritz vectors harvested from the PCG solves themselves.
 // ---------------------------------------------------------------------------------------------
 // Ac[(mcl + i) * ld + col] = Z_i . q  (column `col` of the Z rows of [P Z]' S [P Z]); one CTA per i

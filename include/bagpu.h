@@ -60,6 +60,9 @@ BA_API int ba_shard_range(const ba_handle* h, int64_t* obs0, int64_t* obs1, int6
 BA_API int ba_partition_observations(int64_t nobs, const int64_t* pnt_idx_1based, int nranks, int64_t* cuts);
 BA_API const char* ba_last_error(const ba_handle* h);
 BA_API const char* ba_version(void);
+/* FP64 FMA throughput of `device` in TFLOP/s, measured with a register-resident FMA kernel (the secondary ceiling
+ * of this path next to HBM bandwidth; not part of the reference's surface). */
+BA_API int ba_measure_fp64_peak(int device, double* tflops);
 /* Run this handle's work on an existing stream (cudaStream_t passed as void*), e.g. the
  * caller's current stream so that its own CUDA events bracket the kernels. */
 BA_API int ba_set_stream(ba_handle* h, void* cuda_stream);

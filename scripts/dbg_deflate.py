@@ -38,7 +38,7 @@ def run(k):
 
 
 results = {}
-for k in ([int(child)] if child else [0, 32, 0, 32]):
+for k in ([int(child)] if child else [0, 32]):
     try:
         results[k] = run(k)
     except Exception as e:  # noqa: BLE001

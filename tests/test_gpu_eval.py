@@ -233,3 +233,11 @@ def test_jtprod_camera_part_is_reproducible(ba):
     for _ in range(3):
         b = m.jtprod_(p.x0, w)
         assert np.array_equal(a[3 * p.npnts:], b[3 * p.npnts:])
+
+
+@pytest.mark.gpu
+def test_fp64_peak_probe_is_sane(ba):
+    import ctypes as C
+    v = C.c_double()
+    assert ba._lib.lib().ba_measure_fp64_peak(0, C.byref(v)) == 0
+    assert 5.0 < v.value < 200.0, v.value          # B200: a few tens of TFLOP/s

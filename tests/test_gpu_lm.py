@@ -284,9 +284,11 @@ def test_points_seen_by_more_than_32_cameras(ba, oracle):
 
 
 @pytest.mark.gpu
-def test_deflated_pcg_gives_the_same_step_in_fewer_iterations(ba):
+def test_deflated_pcg_gives_the_same_step_in_fewer_iterations(ba, monkeypatch):
     """PCG deflation (ba_set_deflation): the first solve harvests Ritz vectors, the second one -- same system --
-    uses them.  Same step to PCG accuracy, at most half the iterations."""
+    uses them.  Same step to PCG accuracy, at most half the iterations.  BAGPU_DEFL_CHECK makes the library
+    verify its 4-vector Schur product (coarse setup) against the single-vector one and fail on a mismatch."""
+    monkeypatch.setenv("BAGPU_DEFL_CHECK", "1")
     from conftest import assert_rel
     p = ba.synth.make_problem((160, 10000, 50000))       # 1440 camera rows: the multi-CTA vector kernels
     m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)

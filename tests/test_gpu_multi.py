@@ -83,6 +83,7 @@ def _deflated_sequence(ba, m, p):
 
 def _worker_deflated(rank, world, port, q):
     sys.path.insert(0, ROOT)
+    os.environ["BAGPU_DEFL_CHECK"] = "1"   # the library cross-checks its 4-vector Schur product (coarse setup)
     import torch
     import torch.distributed as dist
     import bundleadjustment.jl_b200 as ba
