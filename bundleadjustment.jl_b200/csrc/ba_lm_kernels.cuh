@@ -770,6 +770,42 @@ k_pcg_q(int64_t n9, const double* __restrict__ H, const double* p, double* q, do
   if (threadIdx.x == 0) part_pq[blockIdx.x] = pq;
 }
 
+// Dot products of this warp's NU deflation vectors (j = warp, warp + 8, ...) with the CTA's slice of r (rs, in
+// shared memory).  All NU x 8 loads of a lane are independent and unpredicated (row indices are clamped, the
+// clamped rows get a zero weight) so that they are in flight together.
+template <int NU, bool FULL>
+__device__ __forceinline__ void warp_zdot_rows(const double* __restrict__ zb, int64_t n9, int nrow, const double* rs,
+                                               double* __restrict__ zp) {
+  constexpr int NW = VEC_THREADS / 32, NB = (VEC_ROWS + 31) / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* zu[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) zu[u] = zb + (int64_t)(warp + NW * u) * n9;
+  double t[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) t[u] = 0.0;
+#pragma unroll
+  for (int bt = 0; bt < NB; ++bt) {
+    const int a = lane + 32 * bt;
+    // a full CTA (252 rows) only clamps in its last batch: the other row offsets are compile-time constants
+    const int ac = (FULL && bt < NB - 1) ? a : min(a, nrow - 1);
+    const double ra = (a < nrow) ? rs[ac] : 0.0;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) t[u] += zu[u][ac] * ra;
+  }
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const double tt = warp_sum(t[u]);
+    if (lane == 0) zp[warp + NW * u] = tt;
+  }
+}
+template <int NU>
+__device__ __forceinline__ void warp_zdot(const double* __restrict__ zb /* Z + first row of the CTA */, int64_t n9,
+                                          int kz, int nrow, const double* rs, double* __restrict__ zp) {
+  if (nrow == VEC_ROWS) warp_zdot_rows<NU, true>(zb, n9, nrow, rs, zp);
+  else warp_zdot_rows<NU, false>(zb, n9, nrow, rs, zp);
+}
+
 // K7d: alpha = r.z / p.q; xc += alpha p; r -= alpha q; z = Minv r; per-CTA partials of r.z.
 // INIT: r = b, xc = 0 instead of the update.
 template <bool INIT>
@@ -817,30 +853,21 @@ k_pcg_xr(int64_t n9, int nparts, const double* __restrict__ b, const double* __r
       cpart[blockIdx.x * 9 + threadIdx.x] = t;
     }
   }
-  if (kz > 0) {  // restriction to the deflation vectors: this CTA's slice of Z_j . r, one warp per vector
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (kz > 0) {  // restriction to the deflation vectors: this CTA's slice of Z_j . r
+    const int warp = threadIdx.x >> 5;
     const int64_t i0 = blockIdx.x * (int64_t)VEC_ROWS;
     const int nrow = (int)min((long long)VEC_ROWS, (long long)(n9 - i0));
-    constexpr int NW = VEC_THREADS / 32;
-    double t[KZ_LIMIT / NW];  // the warp's vectors (j = warp, warp + 8, ...) advance together: independent loads
-#pragma unroll
-    for (int u = 0; u < KZ_LIMIT / NW; ++u) t[u] = 0.0;
-#pragma unroll 4
-    for (int a = lane; a < nrow; a += 32) {
-      const double ra = rs[a];
-#pragma unroll
-      for (int u = 0; u < KZ_LIMIT / NW; ++u) {
-        const int j = warp + NW * u;
-        if (j < kz) t[u] += Zb[(int64_t)j * n9 + i0 + a] * ra;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < KZ_LIMIT / NW; ++u) {
-      const int j = warp + NW * u;
-      if (j < kz) {  // warp-uniform
-        const double tt = warp_sum(t[u]);
-        if (lane == 0) zpart[(int64_t)blockIdx.x * kz + j] = tt;
-      }
+    const int nu = (kz - warp + VEC_THREADS / 32 - 1) / (VEC_THREADS / 32);  // vectors of this warp (uniform)
+    double* zp = zpart + (int64_t)blockIdx.x * kz;
+    const double* zb = Zb + i0;
+    switch (nu) {
+      case 6: warp_zdot<6>(zb, n9, kz, nrow, rs, zp); break;
+      case 5: warp_zdot<5>(zb, n9, kz, nrow, rs, zp); break;
+      case 4: warp_zdot<4>(zb, n9, kz, nrow, rs, zp); break;
+      case 3: warp_zdot<3>(zb, n9, kz, nrow, rs, zp); break;
+      case 2: warp_zdot<2>(zb, n9, kz, nrow, rs, zp); break;
+      case 1: warp_zdot<1>(zb, n9, kz, nrow, rs, zp); break;
+      default: break;
     }
   }
 }
