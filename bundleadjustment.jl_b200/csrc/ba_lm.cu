@@ -644,7 +644,9 @@ struct Solver {
       if ((rc = coarse_setup())) return rc;
       return pcg(tol, maxit, iters);
     }
-    if (S.kz_max > 0 && S.h_scal[S_DONE] == 1.0 && (rc = defl_update(*iters))) return rc;
+    // (a solve stopped by the iteration limit has harvested just as valid Lanczos vectors as a converged one --
+    //  and is the one that needs the deflation most)
+    if (S.kz_max > 0 && S.h_scal[S_DONE] != 2.0 && (rc = defl_update(*iters))) return rc;
     if (S.h_scal[S_DONE] == 2.0) {
       h->err = "PCG breakdown (non-finite or non-positive curvature in the reduced camera system)";
       return BA_ERR_NUMERIC;

@@ -87,6 +87,12 @@ function NLPModels.jtprod!(nlp::BALGPUModel, x::Vector{Float64}, v::Vector{Float
   return Jtv
 end
 
+# PCG preconditioner knobs of the device solve (no counterpart in the reference; they change iteration counts only)
+set_coarse_clusters!(nlp::BALGPUModel, n::Integer) =
+  check(nlp, ccall((:ba_set_coarse_clusters, libbagpu), Cint, (Ptr{Cvoid}, Cint), nlp.handle, n))
+set_deflation!(nlp::BALGPUModel, k::Integer) =
+  check(nlp, ccall((:ba_set_deflation, libbagpu), Cint, (Ptr{Cvoid}, Cint), nlp.handle, k))
+
 # ba_lm_params / ba_lm_stats / ba_lm_row of include/bagpu.h (isbits structs, same field order)
 struct BALMParams
   restol::Float64; satol::Float64; srtol::Float64; oatol::Float64; ortol::Float64; atol::Float64; rtol::Float64
