@@ -128,10 +128,11 @@ int ba_comm_init(ba_handle* h, const uint8_t id128[128]) {
   }
   // NCCL sets up channels / protocols lazily inside the first collective of each size class (tens to hundreds
   // of ms): pay that here, at the message sizes the solver uses, not in the first LM iteration
-  const size_t sizes[3] = {8, 9 * (size_t)h->ncams, 54 * (size_t)h->ncams};
+  // (scalars, one camera vector, the four vectors of the coarse setup, the per-camera accumulators)
+  const size_t sizes[4] = {8, 9 * (size_t)h->ncams, 36 * (size_t)h->ncams, 54 * (size_t)h->ncams};
   double* warm = nullptr;
-  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&warm), std::max<size_t>(sizes[2], 8) * sizeof(double)));
-  BA_CUDA(cudaMemsetAsync(warm, 0, std::max<size_t>(sizes[2], 8) * sizeof(double), h->stream));
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&warm), std::max<size_t>(sizes[3], 8) * sizeof(double)));
+  BA_CUDA(cudaMemsetAsync(warm, 0, std::max<size_t>(sizes[3], 8) * sizeof(double), h->stream));
   int wrc = BA_OK;
   for (int rep = 0; rep < 2 && !wrc; ++rep)
     for (size_t n : sizes)
