@@ -303,6 +303,18 @@ def main():
     # ---- LM leg: full Levenberg-Marquardt iterations per second on the same problem ----------------------
     lm = None
     if args.lm_iters > 0:
+        lm_warm = None
+        if world == 1:
+            # untimed warm-up (the contract's W): a 3-iteration solve of a small synthetic problem whose camera
+            # system is above the single-CTA threshold, so that every LM kernel is loaded before the timed call;
+            # nothing of the timed problem is precomputed -- its schedules (lm_prepare) are built inside the timing
+            pw = ba.synth.make_problem((160, 10000, 50000))
+            mw = ba.BALNLPModel(pw.cam_idx, pw.pnt_idx, pw.pt2d, pw.x0, pw.ncams, pw.npnts, pw.nobs, device=local)
+            try:
+                ba.Levenberg_Marquardt(mw, "LDL", "AMD", "None", False, ite_max=2, pcg_max_iter=args.pcg_max_iter)
+                lm_warm = "one 3-iteration solve of a (160, 10000, 50000) synthetic problem on its own handle"
+            finally:
+                mw.close()
         ba.init_comm(m)
         barrier()
         t0 = time.perf_counter()
@@ -316,7 +328,7 @@ def main():
         lm = {"metric": "LM iters/s", "value": st.iter / float(t.item()), "iters": st.iter,
               "pcg_iters": st.pcg_iters, "objective0": st.rows[0]["f"] if st.rows else None,
               "objective": st.objective, "status": st.status, "timings_ms": st.timings_ms,
-              "e2e": "x0 host -> solution host through Levenberg_Marquardt()"}
+              "e2e": "x0 host -> solution host through Levenberg_Marquardt()", "warmup": lm_warm}
 
     if rank == 0:
         clocks = sampler.summary()  # sampled every 100 ms from warm-up to the end of the last leg
