@@ -1,6 +1,6 @@
 // ba_lm.cu -- device-resident Levenberg-Marquardt (K5-K8): block JtJ / Jtr assembly, Schur
-// complement onto the reduced camera system, PCG (block-Jacobi + a coarse level over camera clusters),
-// back-substitution, and the LM loop.
+// complement onto the reduced camera system, PCG (block-Jacobi + a coarse level over camera clusters and
+// deflation vectors harvested from the PCG solves themselves), back-substitution, and the LM loop.
 //
 // Reference semantics: src/lm.jl:15-418 (control flow, kept decision for decision) with the damped
 // solve  (J'J + lambda I) delta = -J'r  that src/lm.jl:61-100,138-152,175-229 obtains from
@@ -21,6 +21,8 @@
 // reproducible run to run and no FP64 atomics are used.  The camera-sized vector updates of PCG are
 // a few small multi-CTA kernels (one fused CTA for up to 128 cameras); its dot products are per-CTA partials
 // summed in fixed order.  Eight PCG iterations form one CUDA graph; convergence is decided on the device.
+// The coarse level solves with [P | Z]' S [P | Z]: P = cluster indicators of the pose components, Z = Ritz
+// vectors of the preconditioned system taken from the Lanczos process that CG is (defl_update, ba_ritz.h).
 // Sharded over ranks (one process per GPU), the sum over ranks inside the PCG iteration is fused into the
 // kernel that consumes it and read from the peers' IPC-mapped memory over NVLink (ba_comm.cu); the
 // per-LM-iteration collectives use NCCL.
