@@ -154,21 +154,104 @@ inline void tridiag_inverse_iteration(const std::vector<double>& d, const std::v
   }
 }
 
-// The k smallest eigenpairs of the tridiagonal (d, e): evals (k) ascending, vecs (m x k, column-major).
-// Small matrices: full QL with vectors; large ones: eigenvalues by QL, vectors by inverse iteration (ghost
-// copies of a converged Ritz value then yield nearly parallel vectors, which select_orthonormal drops).
-inline bool tridiag_smallest(const std::vector<double>& d, const std::vector<double>& e, int m, int k,
-                             std::vector<double>& evals, std::vector<double>& vecs, int full_below = 160) {
+// Sturm counts: cnt[s] = number of eigenvalues of the tridiagonal (d, e2 = squared off-diagonal) smaller than
+// x[s], by the LDL' pivot recurrence q_i = (d_i - x) - e2_{i-1} / q_{i-1}.  NS shifts advance together so that
+// the divisions -- the whole cost -- are independent and pipeline.
+template <int NS>
+inline void sturm_counts(const double* d, const double* e2, int m, const double* x, int* cnt, double pivmin) {
+  double q[NS];
+  for (int s = 0; s < NS; ++s) {
+    q[s] = d[0] - x[s];
+    cnt[s] = q[s] < 0.0;
+  }
+  for (int i = 1; i < m; ++i) {
+    const double di = d[i], ei = e2[i - 1];
+    for (int s = 0; s < NS; ++s) {
+      double qq = q[s];
+      if (std::fabs(qq) < pivmin) qq = -pivmin;
+      qq = (di - x[s]) - ei / qq;
+      cnt[s] += qq < 0.0;
+      q[s] = qq;
+    }
+  }
+}
+
+// The k smallest eigenvalues (ascending, with multiplicity) by multisection on the Sturm count: each pass cuts
+// the bracket of eigenvalue j into NS + 1 parts.  O(k m log(1/eps)) instead of the O(m^2) of a full QL sweep,
+// and indifferent to the ghost copies a long CG run leaves in T.
+inline void tridiag_smallest_values(const std::vector<double>& d, const std::vector<double>& e, int m, int k,
+                                    std::vector<double>& evals) {
+  constexpr int NS = 8;
   k = std::min(k, m);
-  std::vector<double> w(d), V;
+  evals.assign((size_t)k, 0.0);
+  if (m == 0) return;
+  std::vector<double> e2((size_t)std::max(m - 1, 1), 0.0);
+  double gl = d[0], gu = d[0], emax = 0.0;
+  for (int i = 0; i < m; ++i) {
+    const double r = (i ? std::fabs(e[(size_t)i - 1]) : 0.0) + (i + 1 < m ? std::fabs(e[(size_t)i]) : 0.0);
+    gl = std::min(gl, d[(size_t)i] - r);
+    gu = std::max(gu, d[(size_t)i] + r);
+    if (i + 1 < m) {
+      e2[(size_t)i] = e[(size_t)i] * e[(size_t)i];
+      emax = std::max(emax, e2[(size_t)i]);
+    }
+  }
+  const double tnorm = std::max(std::fabs(gl), std::fabs(gu));
+  const double eps = 2.220446049250313e-16;
+  const double pivmin = std::max(2.2250738585072014e-308 * std::max(emax, 1.0), 1e-300);
+  gl -= 2.0 * eps * tnorm * m + 2.0 * pivmin;  // Gershgorin bounds, widened by the rounding of the recurrence
+  gu += 2.0 * eps * tnorm * m + 2.0 * pivmin;
+  // The recurrence resolves eigenvalues to about eps |T| in absolute terms: stop there.  Upper ends found while
+  // bracketing eigenvalue j are kept for the later ones (ub), so that the common part of the search
+  // -- from |T| down to the scale of the small cluster -- is done once.  (Single-threaded on purpose: every rank
+  // of a sharded run must get the same bits, whatever cores it may use.)
+  const double atol = 4.0 * eps * tnorm + 2.0 * pivmin;
+  auto chunk = [&](int j0, int j1) {
+    std::vector<double> ub((size_t)(j1 - j0), gu);
+    double lo_prev = gl;
+    for (int j = j0; j < j1; ++j) {
+      double lo = lo_prev, hi = ub[(size_t)(j - j0)];  // count(lo) <= j < count(hi)
+      for (int pass = 0; pass < 64 && hi - lo > atol; ++pass) {
+        double x[NS];
+        int cnt[NS];
+        const double h = (hi - lo) / (NS + 1);
+        for (int s = 0; s < NS; ++s) x[s] = lo + h * (s + 1);
+        sturm_counts<NS>(d.data(), e2.data(), m, x, cnt, pivmin);
+        double nlo = lo, nhi = hi;
+        for (int s = NS - 1; s >= 0; --s)  // count(x) > j' makes x an upper end for every eigenvalue j' < count(x)
+          for (int jj = std::min(cnt[s], j1) - 1; jj > j && ub[(size_t)(jj - j0)] > x[s]; --jj) ub[(size_t)(jj - j0)] = x[s];
+        for (int s = 0; s < NS; ++s) {
+          if (cnt[s] <= j) nlo = x[s];  // counts are monotone in x: the last such shift is the new lower end
+          else {
+            nhi = x[s];
+            break;
+          }
+        }
+        if (nlo == lo && nhi == hi) break;  // no progress: the bracket is at rounding level
+        lo = nlo;
+        hi = nhi;
+      }
+      evals[(size_t)j] = 0.5 * (lo + hi);
+      lo_prev = lo;
+    }
+  };
+  chunk(0, k);
+}
+
+// The k smallest eigenpairs of the tridiagonal (d, e): evals (k) ascending, vecs (m x k, column-major).
+// Small matrices: full QL with vectors; larger ones: eigenvalues by multisection, vectors by inverse iteration
+// (ghost copies of a converged Ritz value then yield nearly parallel vectors, which select_orthonormal drops).
+inline bool tridiag_smallest(const std::vector<double>& d, const std::vector<double>& e, int m, int k,
+                             std::vector<double>& evals, std::vector<double>& vecs, int full_below = 64) {
+  k = std::min(k, m);
   if (m <= full_below) {
+    std::vector<double> w(d), V;
     if (!tridiag_eig(w, e, m, V)) return false;
     evals.assign(w.begin(), w.begin() + k);
     vecs.assign(V.begin(), V.begin() + (size_t)m * k);
     return true;
   }
-  if (!tridiag_eig(w, e, m, V, false)) return false;
-  evals.assign(w.begin(), w.begin() + k);
+  tridiag_smallest_values(d, e, m, k, evals);
   vecs.assign((size_t)m * k, 0.0);
   for (int j = 0; j < k; ++j) tridiag_inverse_iteration(d, e, m, evals[(size_t)j], &vecs[(size_t)m * j]);
   return true;
