@@ -620,11 +620,288 @@ BAO_API int bao_lm_step(const int64_t *cam_idx, const int64_t *pnt_idx, const do
   return rc;
 }
 
-/* src/lm.jl:15-418 */
-BAO_API int bao_lm_solve(const int64_t *cam_idx, const int64_t *pnt_idx, const double *pt2d,
+
+/* ------------------------------------------------------------------------------------
+ * Schur-ordered exact solve of the damped normal equations (test infrastructure).
+ *
+ * The reference solves  [[I J];[J' -lambda I]] [dr; d] = [-r; 0]  (src/lm.jl:68-100,175-229) with an
+ * LDL' under a fill-reducing ordering (AMD src/lm.jl:85 / Metis :87).  On a bundle-adjustment
+ * Jacobian such an ordering eliminates the residual rows and the 3x3 point blocks first and is left
+ * with the dense reduced camera system; this is that elimination order written out:
+ *     V_p = sum A'A + lambda I,  U_c = sum B'B + lambda I,  W_cp = B_k'A_k   (J_k = [A_k | B_k])
+ *     S = U - W V^-1 W',   S dc = -(J'r)_c + W V^-1 (J'r)_p,   dp = -V^-1 ((J'r)_p + W' dc)
+ * with a dense Cholesky of S.  Same linear system, different pivot order: the result differs from
+ * the natural-order LDL' above by rounding only (checked in tests/test_oracle.py).  It exists
+ * because the natural-order factorisation fills in far too much beyond ~50 cameras.
+ * vals/rows/cols are the reference's COO Jacobian (jac_coord!/jac_structure!), so nothing here
+ * depends on how the Jacobian was computed.
+ * ---------------------------------------------------------------------------------- */
+static void inv3_sym(const double *v /* 00 01 02 11 12 22 */, double *o /* 3x3 row-major */) {
+  double a = v[0], b = v[1], c = v[2], d = v[3], e = v[4], f = v[5];
+  double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  double det = (a * c00 + b * c01) + c * c02;
+  o[0] = c00 / det; o[1] = o[3] = c01 / det; o[2] = o[6] = c02 / det;
+  o[4] = (a * f - c * c) / det; o[5] = o[7] = (b * c - a * e) / det; o[8] = (a * d - b * b) / det;
+}
+
+/* observation lists per point (any observation order): pstart (npnts+1), plist (nobs) */
+static void point_lists(const int64_t *pnt_idx, int64_t nobs, int64_t npnts, int64_t *pstart, int64_t *plist) {
+  for (int64_t p = 0; p <= npnts; ++p) pstart[p] = 0;
+  for (int64_t k = 0; k < nobs; ++k) pstart[pnt_idx[k]] += 1;
+  for (int64_t p = 0; p < npnts; ++p) pstart[p + 1] += pstart[p];
+  int64_t *w = (int64_t *)malloc((size_t)(npnts > 0 ? npnts : 1) * sizeof(int64_t));
+  for (int64_t p = 0; p < npnts; ++p) w[p] = pstart[p];
+  for (int64_t k = 0; k < nobs; ++k) plist[w[pnt_idx[k] - 1]++] = k;
+  free(w);
+}
+
+/* S (n9 x n9, row-major, both triangles), b (n9), Vinv (9 per point), hp (3 per point: V^-1 (J'r)_p).
+ * jtr = J'r (nvar).  Threads own whole camera rows of S (no atomics, fixed summation order). */
+BAO_API void bao_schur_system(const int64_t *cam_idx, const int64_t *pnt_idx, const double *vals,
+                              const double *jtr, int64_t ncams, int64_t npnts, int64_t nobs, double lambda,
+                              int nthreads, double *S, double *b, double *Vinv, double *hp) {
+  int64_t n9 = 9 * ncams;
+  int64_t *pstart = (int64_t *)malloc((size_t)(npnts + 1) * sizeof(int64_t));
+  int64_t *plist = (int64_t *)malloc((size_t)(nobs > 0 ? nobs : 1) * sizeof(int64_t));
+  point_lists(pnt_idx, nobs, npnts, pstart, plist);
+  if (nthreads < 1) nthreads = 1;
+  memset(S, 0, (size_t)n9 * (size_t)n9 * sizeof(double));
+  /* point blocks */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+#endif
+  for (int64_t p = 0; p < npnts; ++p) {
+    double v[6] = {lambda, 0, 0, lambda, 0, lambda};
+    for (int64_t q = pstart[p]; q < pstart[p + 1]; ++q) {
+      const double *a1 = vals + plist[q] * 24, *a2 = a1 + 12;
+      v[0] += a1[0] * a1[0] + a2[0] * a2[0]; v[1] += a1[0] * a1[1] + a2[0] * a2[1];
+      v[2] += a1[0] * a1[2] + a2[0] * a2[2]; v[3] += a1[1] * a1[1] + a2[1] * a2[1];
+      v[4] += a1[1] * a1[2] + a2[1] * a2[2]; v[5] += a1[2] * a1[2] + a2[2] * a2[2];
+    }
+    double *vi = Vinv + p * 9;
+    inv3_sym(v, vi);
+    const double *g = jtr + p * 3;
+    for (int i = 0; i < 3; ++i) hp[p * 3 + i] = (vi[i * 3] * g[0] + vi[i * 3 + 1] * g[1]) + vi[i * 3 + 2] * g[2];
+  }
+  /* camera rows: thread t owns the cameras c with c % nthreads == t */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nthreads)
+#endif
+  for (int t = 0; t < nthreads; ++t) {
+    for (int64_t c = t; c < ncams; c += nthreads) {
+      for (int j = 0; j < 9; ++j) {
+        S[(9 * c + j) * n9 + 9 * c + j] = lambda;
+        b[9 * c + j] = -jtr[3 * npnts + 9 * c + j];
+      }
+    }
+    for (int64_t p = 0; p < npnts; ++p) {
+      const double *vi = Vinv + p * 9;
+      for (int64_t q1 = pstart[p]; q1 < pstart[p + 1]; ++q1) {
+        int64_t k1 = plist[q1], c1 = cam_idx[k1] - 1;
+        if (c1 % nthreads != t) continue;
+        const double *r1 = vals + k1 * 24, *r2 = r1 + 12;
+        /* U_c1 += B'B */
+        for (int i = 0; i < 9; ++i)
+          for (int j = 0; j < 9; ++j)
+            S[(9 * c1 + i) * n9 + 9 * c1 + j] += r1[3 + i] * r1[3 + j] + r2[3 + i] * r2[3 + j];
+        /* Y = (B'A) V^-1  (9x3) */
+        double Y[27];
+        for (int i = 0; i < 9; ++i) {
+          double e0 = r1[3 + i] * r1[0] + r2[3 + i] * r2[0], e1 = r1[3 + i] * r1[1] + r2[3 + i] * r2[1],
+                 e2 = r1[3 + i] * r1[2] + r2[3 + i] * r2[2];
+          for (int m = 0; m < 3; ++m) Y[i * 3 + m] = (e0 * vi[m] + e1 * vi[3 + m]) + e2 * vi[6 + m];
+        }
+        /* b_c1 += W V^-1 (J'r)_p = Y (J'r)_p */
+        const double *g = jtr + p * 3;
+        for (int i = 0; i < 9; ++i) b[9 * c1 + i] += (Y[i * 3] * g[0] + Y[i * 3 + 1] * g[1]) + Y[i * 3 + 2] * g[2];
+        for (int64_t q2 = pstart[p]; q2 < pstart[p + 1]; ++q2) {
+          int64_t k2 = plist[q2], c2 = cam_idx[k2] - 1;
+          const double *s1 = vals + k2 * 24, *s2 = s1 + 12;
+          for (int j = 0; j < 9; ++j) {
+            double e0 = s1[3 + j] * s1[0] + s2[3 + j] * s2[0], e1 = s1[3 + j] * s1[1] + s2[3 + j] * s2[1],
+                   e2 = s1[3 + j] * s1[2] + s2[3 + j] * s2[2];
+            for (int i = 0; i < 9; ++i)
+              S[(9 * c1 + i) * n9 + 9 * c2 + j] -= (Y[i * 3] * e0 + Y[i * 3 + 1] * e1) + Y[i * 3 + 2] * e2;
+          }
+        }
+      }
+    }
+  }
+  free(pstart); free(plist);
+}
+
+/* dp = -(hp + V^-1 W' dc) for every point; delta = [dp; dc] */
+BAO_API void bao_schur_backsub(const int64_t *cam_idx, const int64_t *pnt_idx, const double *vals, int64_t ncams,
+                               int64_t npnts, int64_t nobs, const double *Vinv, const double *hp, const double *dc,
+                               int nthreads, double *delta) {
+  int64_t *pstart = (int64_t *)malloc((size_t)(npnts + 1) * sizeof(int64_t));
+  int64_t *plist = (int64_t *)malloc((size_t)(nobs > 0 ? nobs : 1) * sizeof(int64_t));
+  point_lists(pnt_idx, nobs, npnts, pstart, plist);
+  if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+#endif
+  for (int64_t p = 0; p < npnts; ++p) {
+    double w[3] = {0, 0, 0}; /* W' dc = sum A'(B dc) */
+    for (int64_t q = pstart[p]; q < pstart[p + 1]; ++q) {
+      int64_t k = plist[q];
+      const double *r1 = vals + k * 24, *r2 = r1 + 12, *d = dc + (cam_idx[k] - 1) * 9;
+      double y1 = 0, y2 = 0;
+      for (int j = 0; j < 9; ++j) { y1 += r1[3 + j] * d[j]; y2 += r2[3 + j] * d[j]; }
+      for (int m = 0; m < 3; ++m) w[m] += r1[m] * y1 + r2[m] * y2;
+    }
+    const double *vi = Vinv + p * 9;
+    for (int i = 0; i < 3; ++i)
+      delta[p * 3 + i] = -(hp[p * 3 + i] + ((vi[i * 3] * w[0] + vi[i * 3 + 1] * w[1]) + vi[i * 3 + 2] * w[2]));
+  }
+  memcpy(delta + 3 * npnts, dc, (size_t)(9 * ncams) * sizeof(double));
+  free(pstart); free(plist);
+}
+
+/* Dense Cholesky solve S x = b in place (lower triangle of S used and overwritten; b -> x).
+ * Right-looking, blocked by 64 columns; the trailing update runs in axpy form over a transposed
+ * copy of the panel so that it vectorises without reassociating sums.  Returns -1 on a
+ * non-positive pivot (the SQDException of src/ldl_aux.jl:199). */
+BAO_API int bao_chol_solve(int64_t n, double *S, double *b, int nthreads) {
+  const int64_t NB = 64;
+  if (nthreads < 1) nthreads = 1;
+  double *Pt = (double *)malloc((size_t)NB * (size_t)(n > 0 ? n : 1) * sizeof(double));
+  int bad = 0;
+  for (int64_t k0 = 0; k0 < n && !bad; k0 += NB) {
+    int64_t kb = (n - k0 < NB) ? n - k0 : NB, k1 = k0 + kb;
+    for (int64_t j = k0; j < k1; ++j) { /* diagonal block, unblocked */
+      double d = S[j * n + j];
+      for (int64_t q = k0; q < j; ++q) d -= S[j * n + q] * S[j * n + q];
+      if (!(d > 0)) { bad = 1; break; }
+      d = sqrt(d);
+      S[j * n + j] = d;
+      for (int64_t i = j + 1; i < k1; ++i) {
+        double s = S[i * n + j];
+        for (int64_t q = k0; q < j; ++q) s -= S[i * n + q] * S[j * n + q];
+        S[i * n + j] = s / d;
+      }
+    }
+    if (bad) break;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+#endif
+    for (int64_t i = k1; i < n; ++i) { /* panel: rows below the block */
+      double *row = S + i * n;
+      for (int64_t j = k0; j < k1; ++j) {
+        double s = row[j];
+        for (int64_t q = k0; q < j; ++q) s -= row[q] * S[j * n + q];
+        row[j] = s / S[j * n + j];
+        Pt[(j - k0) * n + i] = row[j];
+      }
+    }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nthreads)
+#endif
+    for (int64_t i = k1; i < n; ++i) { /* trailing update, lower triangle */
+      double *row = S + i * n;
+      for (int64_t q = 0; q < kb; ++q) {
+        const double a = row[k0 + q];
+        const double *pt = Pt + q * n;
+        for (int64_t j = k1; j <= i; ++j) row[j] -= a * pt[j];
+      }
+    }
+  }
+  free(Pt);
+  if (bad) return -1;
+  for (int64_t i = 0; i < n; ++i) { /* L y = b */
+    double s = b[i];
+    for (int64_t q = 0; q < i; ++q) s -= S[i * n + q] * b[q];
+    b[i] = s / S[i * n + i];
+  }
+  for (int64_t i = n - 1; i >= 0; --i) { /* L' x = y (axpy form: rows of L) */
+    b[i] /= S[i * n + i];
+    const double xi = b[i];
+    for (int64_t q = 0; q < i; ++q) b[q] -= S[i * n + q] * xi;
+  }
+  return 0;
+}
+
+/* threaded J v for the COO Jacobian of jac_structure! (two rows per observation) */
+static void jprod_obs(const int64_t *cam_idx, const int64_t *pnt_idx, const double *vals, const double *v,
+                      int64_t npnts, int64_t nobs, int nthreads, double *Jv) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+#endif
+  for (int64_t k = 0; k < nobs; ++k) {
+    const double *r1 = vals + k * 24, *r2 = r1 + 12;
+    const double *X = v + (pnt_idx[k] - 1) * 3, *Cc = v + 3 * npnts + (cam_idx[k] - 1) * 9;
+    double y1 = 0, y2 = 0;
+    for (int j = 0; j < 3; ++j) { y1 += r1[j] * X[j]; y2 += r2[j] * X[j]; }
+    for (int j = 0; j < 9; ++j) { y1 += r1[3 + j] * Cc[j]; y2 += r2[3 + j] * Cc[j]; }
+    Jv[2 * k] = y1; Jv[2 * k + 1] = y2;
+  }
+}
+
+/* workspace of the Schur solve inside the LM loop */
+typedef struct {
+  int64_t ncams, npnts, nobs;
+  double *S, *b, *Vinv, *hp, *Jd;
+} bao_schur_ws;
+
+static bao_schur_ws *schur_ws_new(int64_t ncams, int64_t npnts, int64_t nobs) {
+  bao_schur_ws *W = (bao_schur_ws *)calloc(1, sizeof(bao_schur_ws));
+  int64_t n9 = 9 * ncams;
+  W->ncams = ncams; W->npnts = npnts; W->nobs = nobs;
+  W->S = (double *)malloc((size_t)n9 * (size_t)n9 * sizeof(double));
+  W->b = (double *)malloc((size_t)n9 * sizeof(double));
+  W->Vinv = (double *)malloc((size_t)(9 * npnts) * sizeof(double));
+  W->hp = (double *)malloc((size_t)(3 * npnts) * sizeof(double));
+  W->Jd = (double *)malloc((size_t)(2 * nobs) * sizeof(double));
+  return W;
+}
+static void schur_ws_free(bao_schur_ws *W) {
+  if (!W) return;
+  free(W->S); free(W->b); free(W->Vinv); free(W->hp); free(W->Jd); free(W);
+}
+/* delta (nvar) and dr = -(r + J delta) (nequ), the two halves of the augmented solution */
+static int schur_solve(bao_schur_ws *W, const int64_t *cam_idx, const int64_t *pnt_idx, const double *vals,
+                       const double *r, const double *jtr, double lambda, int nt, double *delta, double *dr) {
+  bao_schur_system(cam_idx, pnt_idx, vals, jtr, W->ncams, W->npnts, W->nobs, lambda, nt, W->S, W->b, W->Vinv, W->hp);
+  if (bao_chol_solve(9 * W->ncams, W->S, W->b, nt)) return -1;
+  bao_schur_backsub(cam_idx, pnt_idx, vals, W->ncams, W->npnts, W->nobs, W->Vinv, W->hp, W->b, nt, delta);
+  jprod_obs(cam_idx, pnt_idx, vals, delta, W->npnts, W->nobs, nt, W->Jd);
+  for (int64_t i = 0; i < 2 * W->nobs; ++i) dr[i] = -(r[i] + W->Jd[i]);
+  return 0;
+}
+
+BAO_API int bao_lm_step_schur(const int64_t *cam_idx, const int64_t *pnt_idx, const double *pt2d,
+                              int64_t ncams, int64_t npnts, int64_t nobs, const double *x, double lambda,
+                              int nthreads, double *delta, double *dr2_out, double *jtr_out) {
+  int64_t nequ = 2 * nobs, nvar = 9 * ncams + 3 * npnts, nnzj = 24 * nobs;
+  int64_t *rows = (int64_t *)malloc((size_t)nnzj * sizeof(int64_t));
+  int64_t *cols = (int64_t *)malloc((size_t)nnzj * sizeof(int64_t));
+  double *vals = (double *)malloc((size_t)nnzj * sizeof(double));
+  double *r = (double *)malloc((size_t)nequ * sizeof(double));
+  double *dr = (double *)malloc((size_t)nequ * sizeof(double));
+  double *jtr = (double *)malloc((size_t)nvar * sizeof(double));
+  if (nthreads < 1) nthreads = 1;
+  bao_cons(cam_idx, pnt_idx, pt2d, x, r, nobs, npnts, nthreads);
+  bao_jac_structure(cam_idx, pnt_idx, nobs, npnts, rows, cols);
+  bao_jac_coord(cam_idx, pnt_idx, x, vals, nobs, npnts, nthreads);
+  bao_mul_sparse(cols, rows, vals, r, nnzj, jtr, nvar);
+  if (jtr_out) memcpy(jtr_out, jtr, (size_t)nvar * sizeof(double));
+  bao_schur_ws *W = schur_ws_new(ncams, npnts, nobs);
+  int rc = schur_solve(W, cam_idx, pnt_idx, vals, r, jtr, lambda, nthreads, delta, dr);
+  if (!rc) {
+    double n = norm2v(dr, nequ);
+    *dr2_out = n * n / 2;
+  }
+  schur_ws_free(W);
+  free(rows); free(cols); free(vals); free(r); free(dr); free(jtr);
+  return rc;
+}
+
+/* src/lm.jl:15-418; solver 0 = LDL' of the augmented matrix in natural order (src/ldl_aux.jl),
+ * 1 = the same system by the Schur-ordered dense Cholesky above */
+BAO_API int bao_lm_solve_ex(const int64_t *cam_idx, const int64_t *pnt_idx, const double *pt2d,
                          int64_t ncams, int64_t npnts, int64_t nobs, double *x /* in: x0, out: solution */,
                          const bao_lm_params *prm, bao_lm_stats *st, bao_lm_row *log,
-                         int64_t log_cap) {
+                         int64_t log_cap, int solver) {
   int64_t nequ = 2 * nobs, nvar = 9 * ncams + 3 * npnts, nnzj = 24 * nobs;
   int nt = prm->nthreads > 0 ? prm->nthreads : 1;
   int ntj = nt < 3 ? nt : 3; /* jac_coord! self-limits to 3 threads, BALNLPModels.jl:167-168 */
@@ -652,8 +929,9 @@ BAO_API int bao_lm_solve(const int64_t *cam_idx, const int64_t *pnt_idx, const d
   double norm_Jtr = norm2v(Jtr, nvar);
   double lambda = fmax(prm->lambda, 1e10 / norm_Jtr);
   /* :68-100 */
-  bao_aug *G = aug_build(nequ, nvar, nnzj, rows, cols, NULL);
-  aug_set(G, vals, lambda);
+  bao_aug *G = solver == 0 ? aug_build(nequ, nvar, nnzj, rows, cols, NULL) : NULL;
+  bao_schur_ws *W = solver == 0 ? NULL : schur_ws_new(ncams, npnts, nobs);
+  if (G) aug_set(G, vals, lambda);
 
   double norm_delta = 0, dr2 = 0;
   double eps_first_order = prm->atol + prm->rtol * norm_Jtr; /* :107 */
@@ -664,9 +942,14 @@ BAO_API int bao_lm_solve(const int64_t *cam_idx, const int64_t *pnt_idx, const d
   while (!(small_step || first_order || small_residual || small_obj_change || tired || fail || fail2)) {
     iter += 1;
     /* :175-180, :227-229 */
-    if (aug_solve(G, r)) { fail2 = 1; continue; } /* SQDException surfaces as an exception */
-    memcpy(dr, G->b, (size_t)nequ * sizeof(double));
-    memcpy(delta, G->b + nequ, (size_t)nvar * sizeof(double));
+    if (G) {
+      if (aug_solve(G, r)) { fail2 = 1; continue; } /* SQDException surfaces as an exception */
+      memcpy(dr, G->b, (size_t)nequ * sizeof(double));
+      memcpy(delta, G->b + nequ, (size_t)nvar * sizeof(double));
+    } else if (schur_solve(W, cam_idx, pnt_idx, vals, r, Jtr, lambda, nt, delta, dr)) {
+      fail2 = 1;
+      continue;
+    }
     { double n = norm2v(dr, nequ); dr2 = n * n / 2; }
     /* :251-254 */
     for (int64_t i = 0; i < nvar; ++i) x_suiv[i] = x[i] + delta[i];
@@ -706,7 +989,7 @@ BAO_API int bao_lm_solve(const int64_t *cam_idx, const int64_t *pnt_idx, const d
     if (!step_accepted) {
       /* :306-325 */
       lambda = fmax(lambda, 1 / norm_delta) * pow(prm->nu_m, (double)(ntimes + 1));
-      aug_set(G, vals, lambda);
+      if (G) aug_set(G, vals, lambda);
     } else {
       /* :328-338 */
       if (ntimes > 0) lambda /= pow(prm->nu_d, (double)(ntimes - 1));
@@ -720,7 +1003,7 @@ BAO_API int bao_lm_solve(const int64_t *cam_idx, const int64_t *pnt_idx, const d
       memcpy(r, r_suiv, (size_t)nequ * sizeof(double));
       norm_r = norm_rsuiv;
       obj = obj_suiv;
-      aug_set(G, vals, lambda);
+      if (G) aug_set(G, vals, lambda);
       bao_mul_sparse(cols, rows, vals, r, nnzj, Jtr, nvar);
       /* :374-379 */
       norm_Jtr = norm2v(Jtr, nvar);
@@ -740,10 +1023,17 @@ BAO_API int bao_lm_solve(const int64_t *cam_idx, const int64_t *pnt_idx, const d
   else if (fail2) status = 6;
   else if (tired) status = 7;
   st->status = status; st->iter = iter; st->objective = obj; st->dual_feas = norm_Jtr;
-  st->lambda_final = lambda; st->nrows = nlog; st->ldl_nnz = bao_ldl_nnz(G->sym);
+  st->lambda_final = lambda; st->nrows = nlog; st->ldl_nnz = G ? bao_ldl_nnz(G->sym) : 0;
   aug_free(G);
+  schur_ws_free(W);
   free(x_suiv); free(r); free(r_suiv); free(delta); free(dr); free(Jtr); free(rows); free(cols); free(vals);
   return 0;
+}
+
+BAO_API int bao_lm_solve(const int64_t *cam_idx, const int64_t *pnt_idx, const double *pt2d,
+                         int64_t ncams, int64_t npnts, int64_t nobs, double *x, const bao_lm_params *prm,
+                         bao_lm_stats *st, bao_lm_row *log, int64_t log_cap) {
+  return bao_lm_solve_ex(cam_idx, pnt_idx, pt2d, ncams, npnts, nobs, x, prm, st, log, log_cap, 0);
 }
 
 /* Generic entry used by tests: solve a CSC upper-stored SQD system with permutation P. */

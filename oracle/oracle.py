@@ -76,6 +76,17 @@ def lib():
         L.bao_lm_solve.argtypes = [_i64p, _i64p, _f64p, C.c_int64, C.c_int64, C.c_int64, _f64p,
                                    C.POINTER(LMParams), C.POINTER(LMStats), C.c_void_p, C.c_int64]
         L.bao_lm_solve.restype = C.c_int
+        L.bao_lm_solve_ex.argtypes = L.bao_lm_solve.argtypes + [C.c_int]
+        L.bao_lm_solve_ex.restype = C.c_int
+        L.bao_lm_step_schur.argtypes = [_i64p, _i64p, _f64p, C.c_int64, C.c_int64, C.c_int64, _f64p, C.c_double,
+                                        C.c_int, _f64p, C.POINTER(C.c_double), C.c_void_p]
+        L.bao_lm_step_schur.restype = C.c_int
+        L.bao_schur_system.argtypes = [_i64p, _i64p, _f64p, _f64p, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                                       C.c_int, _f64p, _f64p, _f64p, _f64p]
+        L.bao_schur_backsub.argtypes = [_i64p, _i64p, _f64p, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p, _f64p,
+                                        C.c_int, _f64p]
+        L.bao_chol_solve.argtypes = [C.c_int64, _f64p, _f64p, C.c_int]
+        L.bao_chol_solve.restype = C.c_int
         L.bao_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -195,15 +206,62 @@ class LMResult:
     ldl_nnz: int
 
 
-def lm_solve(cam_idx, pnt_idx, pt2d, ncams, npnts, x0, params: LMParams | None = None, log_cap=512) -> LMResult:
-    """Levenberg_Marquardt(model, :LDL, <natural order>, :None, linesearch) (src/lm.jl:15-418)."""
+def lm_step_schur(cam_idx, pnt_idx, pt2d, ncams, npnts, x, lam, want_jtr=False, nthreads=None, dense="auto"):
+    """The same damped solve as lm_step, eliminated in the order a fill-reducing permutation (AMD/Metis,
+    src/lm.jl:85-87) takes on a BA Jacobian: residual rows, 3x3 point blocks, then a dense Cholesky of the
+    reduced camera system.  Finishes at every BASELINE.json size up to Venice-1778 (S is 16002^2 there).
+    dense = "c" (oracle's own blocked Cholesky), "scipy" (LAPACK dpotrf, faster for big S) or "auto"."""
+    nobs = len(cam_idx)
+    nvar = 9 * ncams + 3 * npnts
+    nt = nthreads or max_threads()
+    cam_idx, pnt_idx, pt2d, x = _i64(cam_idx), _i64(pnt_idx), _f64(pt2d), _f64(x)
+    if dense == "auto":
+        dense = "scipy" if ncams > 400 else "c"
+    if dense == "c":
+        delta = np.empty(nvar)
+        dr2 = C.c_double()
+        jtr = np.empty(nvar) if want_jtr else None
+        rc = lib().bao_lm_step_schur(cam_idx, pnt_idx, pt2d, ncams, npnts, nobs, x, float(lam), nt, delta,
+                                     C.byref(dr2), None if jtr is None else jtr.ctypes.data_as(C.c_void_p))
+        if rc:
+            raise ArithmeticError("non-positive pivot in the reduced camera system")
+        return (delta, dr2.value, jtr) if want_jtr else (delta, dr2.value)
+    import scipy.linalg as sla
+    r = cons(cam_idx, pnt_idx, pt2d, x, npnts, nt)
+    vals = jac_coord(cam_idx, pnt_idx, x, npnts, nt)
+    rows, cols = jac_structure(cam_idx, pnt_idx, npnts)
+    jtr = mul_sparse(cols, rows, vals, r, nvar)
+    del rows, cols
+    n9 = 9 * ncams
+    S, b = np.empty((n9, n9)), np.empty(n9)
+    Vinv, hp = np.empty(9 * npnts), np.empty(3 * npnts)
+    lib().bao_schur_system(cam_idx, pnt_idx, vals, jtr, ncams, npnts, nobs, float(lam), nt, S.reshape(-1), b,
+                           Vinv, hp)
+    cf = sla.cho_factor(S, lower=True, overwrite_a=True, check_finite=False)
+    dc = sla.cho_solve(cf, b, check_finite=False)
+    del S, cf
+    delta = np.empty(nvar)
+    lib().bao_schur_backsub(cam_idx, pnt_idx, vals, ncams, npnts, nobs, Vinv, hp, _f64(dc), nt, delta)
+    v = vals.reshape(nobs, 2, 12)
+    Jd = np.einsum("kij,kj->ki", v[:, :, :3], delta[: 3 * npnts].reshape(-1, 3)[pnt_idx - 1]) + \
+        np.einsum("kij,kj->ki", v[:, :, 3:], delta[3 * npnts:].reshape(-1, 9)[cam_idx - 1])
+    dr = Jd.reshape(-1) + r
+    dr2 = float(np.linalg.norm(dr)) ** 2 / 2
+    return (delta, dr2, jtr) if want_jtr else (delta, dr2)
+
+
+def lm_solve(cam_idx, pnt_idx, pt2d, ncams, npnts, x0, params: LMParams | None = None, log_cap=512,
+             solver="ldl") -> LMResult:
+    """Levenberg_Marquardt(model, :LDL, <order>, :None, linesearch) (src/lm.jl:15-418).  solver="ldl": LDL' of the
+    augmented matrix in natural order (src/ldl_aux.jl; small problems only); "schur": the same system in the
+    elimination order of a fill-reducing permutation (points first, dense Cholesky of the camera system)."""
     nobs = len(cam_idx)
     p = params or default_params()
     st = LMStats()
     rows = (LMRow * log_cap)()
     x = _f64(x0).copy()
-    lib().bao_lm_solve(_i64(cam_idx), _i64(pnt_idx), _f64(pt2d), ncams, npnts, nobs, x, C.byref(p), C.byref(st),
-                       C.cast(rows, C.c_void_p), log_cap)
+    lib().bao_lm_solve_ex(_i64(cam_idx), _i64(pnt_idx), _f64(pt2d), ncams, npnts, nobs, x, C.byref(p), C.byref(st),
+                          C.cast(rows, C.c_void_p), log_cap, {"ldl": 0, "schur": 1}[solver])
     log = [dict(iter=r.iter, f=r.f, df=r.df, dfeas=r.dfeas, lam=r.lam, delta_norm=r.delta_norm, rho=r.rho,
                 accepted=bool(r.accepted), acc_str=bool(r.acc_str)) for r in rows[: st.nrows]]
     return LMResult(STATUS[st.status], st.iter, st.objective, st.dual_feas, st.lambda_final, x, log, st.ldl_nnz)

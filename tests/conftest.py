@@ -35,6 +35,32 @@ def assert_rel(a, b, tol=TOL, scale=None, what=""):
     return worst
 
 
+def rel_errors(a, b):
+    """(norm-wise, floor-wise as in assert_rel, worst entry-wise) relative errors of a against b over the finite
+    entries.  The entry-wise figure has no floor: entries that are small through cancellation show up there."""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    fin = np.isfinite(b) & np.isfinite(a)
+    d, bb = np.abs(a[fin] - b[fin]), np.abs(b[fin])
+    nrm = float(np.linalg.norm(a[fin] - b[fin]) / max(np.linalg.norm(b[fin]), 1e-300))
+    floor = float((d / (bb + bb.max() + 1e-300)).max()) if d.size else 0.0
+    nz = bb > 0
+    entry = float((d[nz] / bb[nz]).max()) if nz.any() else 0.0
+    return nrm, floor, entry
+
+
+def parity_report(name, **numbers):
+    """Print the achieved errors of a parity test (pytest -rP / -s shows them) and append them to
+    gpurun_out/parity_report.jsonl when that directory exists (copied to profiles/ for the record)."""
+    import json
+    line = json.dumps(dict(test=name, **numbers))
+    print("[parity] " + line)
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(line + "\n")
+
+
 def assert_jac_rel(vals, ref, tol=TOL, what="jac"):
     """Jacobian values: judged per column slot (24 slots per observation), because columns differ by
     many orders of magnitude (f*rho^4 for k2 against ~1e3 for the rotation)."""

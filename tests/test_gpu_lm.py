@@ -39,6 +39,60 @@ def test_lm_step_matches_ldl_oracle(ba, oracle, shape, lam):
     assert 0 < iters < 1000
 
 
+def _first_lambda(m, p):
+    # lambda of the first LM iteration: max(30, 1e10 / ||J'r||) (src/lm.jl:59)
+    g = m.jtprod_(p.x0, m.cons(p.x0))
+    return max(30.0, 1e10 / float(np.linalg.norm(g)))
+
+
+@pytest.mark.parametrize("shape,lam", [("trafalgar-257", 30.0), ("trafalgar-257", 1e3), ("trafalgar-257", "first"),
+                                        ("dubrovnik-356", 30.0), ("dubrovnik-356", 1e3),
+                                        ("venice-1778", 30.0), ("venice-1778", 1e3)])
+def test_lm_step_matches_schur_oracle_at_baseline_sizes(ba, oracle, shape, lam):
+    """The damped solve at the BASELINE.json sizes against an independent exact solver: the oracle's own
+    jac_coord values, points eliminated, dense Cholesky (LAPACK) of the reduced camera system -- the pivot
+    order AMD/Metis give the reference's LDL' on a BA Jacobian (oracle.lm_step_schur)."""
+    from conftest import parity_report, rel_errors
+    p = ba.synth.make_problem(shape)
+    m = _model(ba, p)
+    if lam == "first":
+        lam = _first_lambda(m, p)
+    d_ref, dr2_ref, jtr_ref = oracle.lm_step_schur(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, lam,
+                                                   want_jtr=True)
+    d, dr2, obj, jtr, iters = ba.lm_step(m, p.x0, lam, pcg_tol=1e-13, pcg_max_iter=4000, want_jtr=True)
+    m.close()
+    npt = 3 * p.npnts
+    ep, ec, ej = rel_errors(d[:npt], d_ref[:npt]), rel_errors(d[npt:], d_ref[npt:]), rel_errors(jtr, jtr_ref)
+    parity_report("lm_step_vs_schur_oracle", shape=shape, lam=lam, solver_iters=int(iters),
+                  points=dict(norm=ep[0], floor=ep[1], entry=ep[2]), cameras=dict(norm=ec[0], floor=ec[1], entry=ec[2]),
+                  jtr=dict(norm=ej[0], floor=ej[1], entry=ej[2]), dr2=abs(dr2 - dr2_ref) / dr2_ref)
+    assert ep[0] <= TOL and ec[0] <= TOL, "LM step (norm-wise): points %.2e cameras %.2e" % (ep[0], ec[0])
+    assert ep[1] <= TOL and ec[1] <= TOL
+    assert abs(dr2 - dr2_ref) <= TOL * dr2_ref
+    assert ej[0] <= TOL
+
+
+@pytest.mark.parametrize("shape", ["trafalgar-257", "dubrovnik-356", "venice-1778"])
+def test_lm_first_iterations_match_schur_oracle(ba, oracle, shape):
+    """Three LM iterations (f, lambda, accept/reject, ||J'r||, ||delta||) at the BASELINE.json sizes against the
+    oracle's src/lm.jl loop with the Schur-ordered exact solve."""
+    from conftest import parity_report
+    p = ba.synth.make_problem(shape)
+    m = _model(ba, p)
+    st = ba.Levenberg_Marquardt(ba.FeasibilityResidual(m), "LDL", "AMD", "None", False, ite_max=2, pcg_max_iter=4000)
+    m.close()
+    ref = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0,
+                          oracle.default_params(ite_max=2, nthreads=oracle.max_threads()), solver="schur")
+    worst = dict(f=0.0, lam=0.0, dfeas=0.0, delta_norm=0.0)
+    for a, b in zip(st.rows, ref.log):
+        for k in worst:
+            worst[k] = max(worst[k], abs(a[k] - b[k]) / abs(b[k]))
+    parity_report("lm_trajectory_vs_schur_oracle", shape=shape, iters=int(st.iter), **worst,
+                  objective=abs(st.objective - ref.objective) / ref.objective,
+                  solution=_rel(st.solution, ref.solution))
+    _compare_trajectories(st, ref, f_tol=1e-9)
+
+
 def test_lm_step_small_lambda_is_conditioning_limited(ba, oracle):
     p = ba.synth.make_problem((9, 300, 1500))
     m = _model(ba, p)

@@ -255,3 +255,51 @@ def test_ldl_oracle_agrees_with_an_independent_sparse_solver(oracle, ba):
     delta, dr2 = oracle.lm_step(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, lam)
     assert np.linalg.norm(delta - xr[m:]) <= 1e-9 * np.linalg.norm(xr[m:])
     assert abs(dr2 - 0.5 * float(xr[:m] @ xr[:m])) <= 1e-10 * dr2
+
+
+@pytest.mark.parametrize("shape,lam", [((7, 60, 260), 30.0), ((9, 300, 1500), 1e3), ((12, 400, 2000), 0.5)])
+def test_schur_ordered_solve_equals_natural_order_ldl(oracle, shape, lam):
+    """The Schur-ordered exact solve (points eliminated first, dense Cholesky of the camera system: the pivot
+    order a fill-reducing permutation gives src/ldl_aux.jl on a BA Jacobian) is the same linear solve as the
+    natural-order LDL' restated from src/ldl_aux.jl: steps agree to rounding.  It is what the GPU tests use as
+    the checker at the BASELINE.json sizes, where the natural order fills in too much."""
+    import bundleadjustment.jl_b200.synth as synth
+    p = synth.make_problem(shape)
+    d0, dr0, j0 = oracle.lm_step(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, lam, want_jtr=True)
+    for dense in ("c", "scipy"):
+        d1, dr1, j1 = oracle.lm_step_schur(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, lam, want_jtr=True,
+                                           dense=dense)
+        assert np.array_equal(j0, j1)
+        assert np.linalg.norm(d1 - d0) <= 1e-10 * np.linalg.norm(d0)
+        assert abs(dr1 - dr0) <= 1e-12 * dr0
+    # any observation order (the lists per point are built by a counting sort)
+    perm = np.random.default_rng(1).permutation(p.nobs)
+    d2, dr2 = oracle.lm_step_schur(p.cam_idx[perm], p.pnt_idx[perm], p.pt2d.reshape(-1, 2)[perm].ravel(), p.ncams,
+                                   p.npnts, p.x0, lam, dense="c")
+    assert np.linalg.norm(d2 - d0) <= 1e-10 * np.linalg.norm(d0)
+
+
+def test_lm_loop_with_schur_solver_follows_the_ldl_trajectory(oracle):
+    import bundleadjustment.jl_b200.synth as synth
+    p = synth.make_problem((9, 300, 1500))
+    a = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0)
+    b = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0,
+                        oracle.default_params(nthreads=2), solver="schur")
+    assert a.status == b.status and a.iter == b.iter
+    assert [r["accepted"] for r in a.log] == [r["accepted"] for r in b.log]
+    for ra, rb in zip(a.log, b.log):
+        assert abs(ra["f"] - rb["f"]) <= 1e-9 * ra["f"] and abs(ra["lam"] - rb["lam"]) <= 1e-9 * ra["lam"]
+    assert abs(a.objective - b.objective) <= 1e-9 * a.objective
+
+
+def test_oracle_dense_cholesky(oracle):
+    rng = np.random.default_rng(3)
+    n = 150
+    A = rng.normal(size=(n, n))
+    S = A @ A.T + n * np.eye(n)
+    b = rng.normal(size=n)
+    x = b.copy()
+    assert oracle.lib().bao_chol_solve(n, S.copy().reshape(-1), x, 3) == 0
+    assert np.linalg.norm(S @ x - b) <= 1e-12 * np.linalg.norm(b)
+    S[5, 5] = -1.0
+    assert oracle.lib().bao_chol_solve(n, S.copy().reshape(-1), b.copy(), 1) == -1
