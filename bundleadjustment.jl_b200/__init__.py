@@ -8,7 +8,8 @@ The directory name carries a dot, so import it as ``bundleadjustment.jl_b200`` (
 from . import _lib
 from ._lib import BAError
 from .model import BALNLPModel, FeasibilityResidual, NLPModelMeta, Counters, name
-from .lm import Levenberg_Marquardt, GenericExecutionStats, default_params, lm_step
+from . import lm
+from .lm import Levenberg_Marquardt, GenericExecutionStats, default_params, lm_step, last_solve_info
 from . import synth
 from .dist import init_comm
 

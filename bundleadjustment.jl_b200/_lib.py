@@ -11,6 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BAGPU_LIB", os.path.join(HERE, "libbagpu.so"))  # BAGPU_LIB: A/B builds
 
 BA_OK, BA_ERR_ARG, BA_ERR_CUDA, BA_ERR_UNSORTED, BA_ERR_COMM, BA_ERR_NUMERIC = range(6)
+SOLVERS = {"auto": 0, "pcg": 1, "exact": 2}  # BA_SOLVER_*
+SOLVER_NAMES = {v: k for k, v in SOLVERS.items()}
 _CODE = {1: "bad argument", 2: "CUDA failure", 3: "observations not point-major", 4: "NCCL failure",
          5: "numeric breakdown"}
 
@@ -26,20 +28,22 @@ class LMParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("restol", "satol", "srtol", "oatol", "ortol", "atol", "rtol",
                                           "nu_d", "nu_m", "lam", "delta_d")] + \
                [("ite_max", C.c_int64), ("linesearch", C.c_int32), ("pcg_max_iter", C.c_int32),
-                ("pcg_tol", C.c_double)]
+                ("pcg_tol", C.c_double), ("solver", C.c_int32), ("reserved", C.c_int32)]
 
 
 class LMRow(C.Structure):
     """ba_lm_row: one log_row of src/lm.jl:304."""
     _fields_ = [("iter", C.c_int64)] + [(n, C.c_double) for n in ("f", "df", "dfeas", "lam", "delta_norm", "rho")] + \
-               [("accepted", C.c_int32), ("acc_str", C.c_int32), ("pcg_iters", C.c_int32), ("ntimes", C.c_int32)]
+               [("accepted", C.c_int32), ("acc_str", C.c_int32), ("pcg_iters", C.c_int32), ("ntimes", C.c_int32),
+                ("solver", C.c_int32), ("converged", C.c_int32), ("solve_rel", C.c_double)]
 
 
 class LMStats(C.Structure):
     _fields_ = [("status", C.c_int32), ("pad", C.c_int32), ("iter", C.c_int64), ("objective", C.c_double),
                 ("dual_feas", C.c_double), ("lambda_final", C.c_double), ("elapsed_s", C.c_double),
                 ("pcg_iters_total", C.c_int64), ("t_eval_ms", C.c_double), ("t_assemble_ms", C.c_double),
-                ("t_pcg_ms", C.c_double), ("t_backsub_ms", C.c_double)]
+                ("t_pcg_ms", C.c_double), ("t_backsub_ms", C.c_double), ("capped_solves", C.c_int64),
+                ("worst_solve_rel", C.c_double), ("t_prepare_ms", C.c_double)]
 
 
 ITER_CB = C.CFUNCTYPE(None, C.POINTER(LMRow), C.c_void_p)
@@ -73,6 +77,9 @@ SYMBOLS = {
     "ba_sync": (C.c_int, [_vp]),
     "ba_set_coarse_clusters": (C.c_int, [_vp, C.c_int]),
     "ba_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "ba_set_solver": (C.c_int, [_vp, C.c_int]),
+    "ba_last_solve_info": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_f64), C.POINTER(_i32)]),
+    "ba_dbg_chol": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ba_last_eval_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ba_lm_default_params": (None, [C.POINTER(LMParams)]),
     "ba_lm_step": (C.c_int, [_vp, _vp, _f64, _f64, _i32, _vp, C.POINTER(_f64), C.POINTER(_f64), _vp,

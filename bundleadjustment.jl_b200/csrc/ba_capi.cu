@@ -48,6 +48,9 @@ int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, 
   h->ncams = ncams; h->npnts = npnts; h->nobs = nobs; h->rank = rank; h->nranks = nranks;
   if (const char* e = getenv("BAGPU_COARSE")) h->coarse_clusters = atoi(e);
   if (const char* e = getenv("BAGPU_DEFLATE")) h->deflate = std::max(0, std::min(32, atoi(e)));
+  if (const char* e = getenv("BAGPU_SOLVER"))
+    h->solver = !strcmp(e, "pcg") ? BA_SOLVER_PCG : (!strcmp(e, "exact") ? BA_SOLVER_EXACT : BA_SOLVER_AUTO);
+  if (const char* e = getenv("BAGPU_EXACT_REFINE")) h->exact_refine = std::max(0, std::min(8, atoi(e)));
   bool sorted = true;
   for (int64_t k = 0; k < nobs; ++k) {
     if (cam[k] < 1 || cam[k] > ncams || pnt[k] < 1 || pnt[k] > npnts)
@@ -244,6 +247,26 @@ int ba_set_deflation(ba_handle* h, int k) {
     ba::lm_release(h);  // buffers, harvested vectors and the captured PCG graph depend on it
     h->deflate = k;
   }
+  return BA_OK;
+}
+
+int ba_set_solver(ba_handle* h, int solver) {
+  if (!h || solver < BA_SOLVER_AUTO || solver > BA_SOLVER_EXACT) return fail(h, BA_ERR_ARG, "unknown solver");
+  if (solver != h->solver) {
+    BA_CUDA(cudaSetDevice(h->device));
+    if (h->stream) BA_CUDA(cudaStreamSynchronize(h->stream));
+    ba::lm_release(h);  // the dense matrix / PCG buffers are allocated per mode; rebuilt on next use
+    h->solver = solver;
+  }
+  return BA_OK;
+}
+
+int ba_last_solve_info(const ba_handle* h, int32_t* solver, int32_t* converged, double* rel, int32_t* iters) {
+  if (!h) return BA_ERR_ARG;
+  if (solver) *solver = h->lm.last_solver;
+  if (converged) *converged = h->lm.last_converged;
+  if (rel) *rel = h->lm.last_rel;
+  if (iters) *iters = h->lm.last_iters;
   return BA_OK;
 }
 

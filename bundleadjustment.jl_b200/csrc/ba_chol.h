@@ -1,0 +1,45 @@
+// ba_chol.h -- dense Cholesky of the reduced camera system on the device (ba_chol.cu).
+//
+// Stands in for what ldl_factorize / ldl_solve! deliver on the camera block once the points are
+// eliminated (src/ldl_aux.jl:122-201 numeric factorisation, :4-42 the three solve sweeps): an exact
+// factorisation, here of the explicitly assembled Schur complement.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+struct ba_handle;
+
+namespace ba {
+
+constexpr int CHOL_TILE = 128;  // block size of the factorisation; matrices are padded to a multiple of it
+
+inline int64_t chol_padded(int64_t n) { return (n + CHOL_TILE - 1) / CHOL_TILE * CHOL_TILE; }
+
+// Workspace of one factorisation: the matrix itself is owned by the caller.
+struct chol_plan {
+  int64_t cn = 0;            // padded order (multiple of CHOL_TILE)
+  double* d_Dinv = nullptr;  // cn/128 blocks of 128 x 128: inverses of the diagonal blocks of L (lower, row-major)
+  float* d_Dinv32 = nullptr; // the same in FP32 (mixed-precision factor)
+  double* d_y = nullptr;     // cn: forward-substitution result
+  double* d_w = nullptr;     // cn: right-hand side being consumed
+  int* d_info = nullptr;     // 0 ok, j + 1 = first non-positive pivot
+  cudaStream_t side = nullptr;   // panel stream (look-ahead)
+  cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_join = nullptr;
+  void* solve_graph = nullptr;   // cudaGraphExec_t of the 2 cn/128 substitution steps
+  const void* solve_graph_A = nullptr;
+  bool attrs_set = false;
+};
+
+int chol_plan_init(ba_handle* h, chol_plan& P, int64_t cn);
+void chol_plan_release(chol_plan& P);
+// A (cn x cn, row-major, leading dimension cn, lower triangle) <- L with A = L L'.  Returns BA_OK and leaves
+// *info_host = 0, or the 1-based index of the first non-positive pivot (BA_ERR_NUMERIC).
+int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info_host);
+// x <- (L L')^-1 b for one right-hand side (b and x: cn doubles on the device, may alias).
+int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, double* x, cudaStream_t s);
+
+// FP32 factor of an FP64 matrix (mixed precision, src/lm.jl:92-98,165-173 facto_type): A32 (cn x cn) <- chol(float(A)).
+int chol_factor32(ba_handle* h, chol_plan& P, float* A32, cudaStream_t s, int* info_host);
+int chol_solve32(ba_handle* h, chol_plan& P, const float* L32, const double* b, double* x, cudaStream_t s);
+
+}  // namespace ba

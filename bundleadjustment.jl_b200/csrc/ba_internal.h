@@ -6,6 +6,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/bagpu.h"
+#include "ba_chol.h"
 
 struct ncclComm;
 
@@ -80,6 +81,18 @@ struct ba_lm_state {
   int pcg_graph_kz = -1;        // kz the captured PCG graph was built for
   int z_gen = 0, coarse_gen = 0;  // version of Z, and the version the current Ac^-1 was built for
   int defl_iters_first = 0;     // PCG iterations of the solve the base vectors came from
+  // ---- exact solve: explicit reduced camera system + dense Cholesky (ba_chol.cu) ---------------------
+  bool exact = false;         // decided in lm_prepare from ba_handle::solver and the problem size
+  int64_t cn = 0;             // 9 ncams padded to a multiple of 128
+  double* d_S = nullptr;      // cn x cn row-major: fixed-point sums, then the scaled matrix, then its factor L
+  double* d_Yh = nullptr;     // 27 per local observation: D_c^-1 (B'A) L_p
+  double* d_cd = nullptr;     // 9 ncams: sqrt(diag(U + lambda I)), the Jacobi scaling
+  double* d_ex = nullptr;     // 2 vectors of cn: scaled right-hand side / residual, scaled solution
+  ba::chol_plan chol;
+  bool attrs_set = false;     // cudaFuncSetAttribute is per device: done once per handle
+  // outcome of the last damped solve (ba_last_solve_info)
+  int last_solver = 0, last_converged = 0, last_iters = 0;
+  double last_rel = 0.0;
   // ---- iterates -------------------------------------------------------------------------------
   double* d_x = nullptr;      // current iterate (nvar; only this rank's point slice + cameras are live)
   double* d_xt = nullptr;     // trial iterate
@@ -133,6 +146,8 @@ struct ba_handle {
   bool profile = false;
   int coarse_clusters = 16;  // two-level PCG preconditioner: target number of camera clusters (0 = off)
   int deflate = 32;          // PCG deflation: base Ritz vectors wanted (0 = off)
+  int solver = BA_SOLVER_AUTO;  // damped solve: auto / PCG / exact (ba_set_solver)
+  int exact_refine = 1;      // refinement steps of the exact solve (matrix-free FP64 residual)
   ba_lm_state lm;
   ncclComm* comm = nullptr;
   ba_p2p_state p2p;

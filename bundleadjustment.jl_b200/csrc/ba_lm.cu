@@ -58,6 +58,18 @@ inline int64_t small_rows_max() {
   static const int64_t v = getenv("BAGPU_VEC_SMALL_MAX") ? atoll(getenv("BAGPU_VEC_SMALL_MAX")) : 1152;
   return v;
 }
+inline bool trace_on() {
+  static const bool v = getenv("BAGPU_TRACE") != nullptr;
+  return v;
+}
+inline int64_t exact_auto_cams() {
+  static const int64_t v = getenv("BAGPU_EXACT_AUTO_CAMS") ? atoll(getenv("BAGPU_EXACT_AUTO_CAMS")) : 2048;
+  return v;
+}
+inline double exact_max_bytes() {
+  static const double v = (getenv("BAGPU_EXACT_MAX_GB") ? atof(getenv("BAGPU_EXACT_MAX_GB")) : 16.0) * 1e9;
+  return v;
+}
 constexpr int DEFL_ROLL = 16;   // deflation vectors refreshed after every solve (on top of the base ones)
 constexpr int DEFL_CAND = 64;   // candidates per selection (= DG_N, the widest k_defl_gemm output)
 constexpr int DEFL_HCAP = 1024; // Lanczos vectors kept per solve at most
@@ -203,7 +215,31 @@ int lm_prepare(ba_handle* h) {
   S.npart = 4 * (int64_t)std::max<int64_t>(nblk(std::max(nl, npl), PT_THREADS), 1024);
   ALLOC(S.d_part, S.npart + 16);  // + scratch for the four step norms
   ALLOC(S.d_scal, S_COUNT);
+  // exact solve: auto = up to EXACT_AUTO_CAMS cameras (the factorisation is n^3/3 flops on a replicated matrix)
+  S.exact = h->solver == BA_SOLVER_EXACT || (h->solver == BA_SOLVER_AUTO && ncams <= exact_auto_cams());
+  S.cn = chol_padded(9 * ncams);
+  if (S.exact && ncams > 0) {
+    if ((double)S.cn * (double)S.cn * 8.0 > exact_max_bytes()) {
+      if (h->solver == BA_SOLVER_EXACT) {
+        h->err = "BA_SOLVER_EXACT: the dense reduced camera system does not fit (raise BAGPU_EXACT_MAX_GB or use PCG)";
+        return BA_ERR_ARG;
+      }
+      S.exact = false;
+    }
+  } else {
+    S.exact = false;
+  }
+  if (S.exact) {
+    ALLOC(S.d_S, S.cn * S.cn);
+    ALLOC(S.d_Yh, 27 * nl);
+    ALLOC(S.d_cd, 9 * ncams);
+    ALLOC(S.d_ex, 2 * S.cn);
+    if ((rc = chol_plan_init(h, S.chol, S.cn))) return rc;
+  }
 #undef ALLOC
+  // opt-in shared-memory sizes are per device: set them for this handle's device
+  BA_CUDA(cudaFuncSetAttribute(k_coarse_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 144 * 8));
+  BA_CUDA(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 144 * 8));
   BA_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&S.h_scal), S_COUNT * sizeof(double), cudaHostAllocDefault));
   for (auto& e : S.ev) BA_CUDA(cudaEventCreate(&e));
   const double t_alloc = ms_since(tp1);
@@ -257,8 +293,9 @@ void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,
                   S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
-                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_Z, S.d_Zcand, S.d_harv, S.d_hcoef, S.d_zpart, S.d_dsmall, S.d_w4, S.d_q4, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal};
+                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_Z, S.d_Zcand, S.d_harv, S.d_hcoef, S.d_zpart, S.d_dsmall, S.d_w4, S.d_q4, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal, S.d_S, S.d_Yh, S.d_cd, S.d_ex};
   for (void* p : ptrs) cudaFree(p);
+  chol_plan_release(S.chol);
   if (S.h_scal) cudaFreeHost(S.h_scal);
   if (S.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(S.pcg_graph));
   for (auto& e : S.ev)
@@ -343,8 +380,65 @@ struct Solver {
     if ((rc = cam_pass<1>(S.d_Cr))) return rc;
     k_cam_finish<<<nblk(ncams, 64), 64, 0, s>>>(ncams, lambda, S.d_Ug, S.d_Cr, S.d_H, S.d_Minv, b, S.d_scal);
     if ((rc = check())) return rc;
-    return coarse_setup();
+    return S.exact ? exact_factor(lambda) : coarse_setup();
   }
+  // Exact solve, factor phase: assemble the Jacobi-scaled reduced camera system explicitly (fixed-point sums of
+  // the off-diagonal blocks: order-independent, summed over ranks as integers) and factorise it (ba_chol.cu).
+  int exact_factor(double lambda) {
+    int rc;
+    const int64_t cn = S.cn;
+    k_exact_diag<<<nblk(n9, 256), 256, 0, s>>>(n9, lambda, S.d_Ug, S.d_cd);
+    k_exact_y<<<nblk(nl, PT_THREADS), PT_THREADS, 0, s>>>(h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_Vinv, S.d_cd,
+                                                          S.d_Yh);
+    BA_CUDA(cudaMemsetAsync(S.d_S, 0, sizeof(double) * (size_t)(cn * cn), s));
+    if ((rc = check())) return rc;
+    if (nl > 0)
+      k_exact_assemble<<<(unsigned)std::min<int64_t>(nblk(nl, 8), 148 * 16), 256, 0, s>>>(
+          S.d_pstart, h->d_pnt, h->pnt0, h->d_cam, nl, S.d_Yh, reinterpret_cast<unsigned long long*>(S.d_S), cn);
+    if ((rc = check())) return rc;
+    if ((rc = allreduce_sum_i64(h, reinterpret_cast<long long*>(S.d_S), (size_t)(cn * cn)))) return rc;
+    k_exact_finish<<<dim3(nblk(cn, 256), (unsigned)cn), 256, 0, s>>>(n9, cn, S.d_H, S.d_Cr, S.d_cd, S.d_S);
+    if ((rc = check())) return rc;
+    int info = 0;
+    rc = chol_factor(h, S.chol, S.d_S, s, &info);  // synchronises (pivot check)
+    if (rc) return rc;
+    if ((rc = read_scalars())) return rc;
+    if (S.h_scal[S_ERR] != 0.0) {
+      h->err = "Schur diagonal block not positive definite";
+      return BA_ERR_NUMERIC;
+    }
+    return BA_OK;
+  }
+  // Exact solve, solve phase: xc = D^-1 (L L')^-1 D^-1 b, then `exact_refine` refinement steps with the FP64
+  // residual b - S xc of the matrix-free product (the same operator PCG applies).  No host round trip: the
+  // residual norm of the direct solve is left in S_REL for the next read of the scalars.
+  int exact_solve(int* iters) {
+    int rc;
+    const int64_t cn = S.cn;
+    double* rs = S.d_ex;        // scaled right-hand side / residual
+    double* xs = S.d_ex + cn;   // scaled solution / correction
+    const bool p2p = h->nranks > 1 && h->p2p.ready;
+    k_exact_scale<<<nblk(cn, 256), 256, 0, s>>>(n9, cn, b, S.d_cd, rs);
+    if ((rc = chol_solve(h, S.chol, S.d_S, rs, xs, s))) return rc;
+    k_exact_unscale<<<nblk(n9, 256), 256, 0, s>>>(n9, xs, S.d_cd, xc, 0);
+    const int steps = std::max(0, h->exact_refine);
+    for (int it = 0; it < steps; ++it) {
+      BA_CUDA(cudaMemcpyAsync(p, xc, sizeof(double) * (size_t)n9, cudaMemcpyDeviceToDevice, s));
+      BA_CUDA(cudaMemsetAsync(S.d_scal + S_DONE, 0, sizeof(double), s));  // the product kernels honour S_DONE
+      if ((rc = s_product(false))) return rc;
+      if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
+      k_exact_resid<<<1, RED_THREADS, 0, s>>>(n9, cn, b, q, S.d_cd, rs, S.d_scal, it == 0 ? 1 : 0);
+      if ((rc = chol_solve(h, S.chol, S.d_S, rs, xs, s))) return rc;
+      k_exact_unscale<<<nblk(n9, 256), 256, 0, s>>>(n9, xs, S.d_cd, xc, 1);
+    }
+    *iters = steps;
+    S.last_solver = BA_SOLVER_EXACT;
+    S.last_converged = 1;
+    S.last_iters = steps;
+    S.last_rel = -1.0;  // filled from S_REL at the next read of the scalars
+    return check();
+  }
+  int solve(double tol, int maxit, int* iters) { return S.exact ? exact_solve(iters) : pcg(tol, maxit, iters); }
   // Ac = [P Z]' S [P Z], then Ac^-1.  P block: direct assembly in one pass over the points (k_coarse_assemble;
   // BAGPU_COARSE_PRODUCTS=1: column by column with CDOF ncl applications of S, the cross-check).  Z block
   // (deflation vectors, dense): one application of S per vector.
@@ -361,11 +455,6 @@ struct Solver {
       k_coarse_diag<<<nblk(mcl, 64), 64, 0, s>>>(ncams, cpc, mcl, S.d_H, S.d_cdiag);
       BA_CUDA(cudaMemsetAsync(S.d_Acq, 0, sizeof(long long) * (size_t)(mcl * mcl), s));
       const size_t smem = sizeof(unsigned long long) * (size_t)(mcl * mcl);
-      static bool attr_set = false;
-      if (!attr_set) {
-        BA_CUDA(cudaFuncSetAttribute(k_coarse_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 144 * 8));
-        attr_set = true;
-      }
       const unsigned grid = (unsigned)std::min<int64_t>(nblk(npl, 256), 148 * 2);
       k_coarse_assemble<<<grid, 256, smem, s>>>(S.d_pstart, npl, nl, h->d_cam, S.d_Jp, S.d_Vinv, cpc, mcl, S.d_cdiag,
                                                 reinterpret_cast<unsigned long long*>(S.d_Acq));
@@ -443,11 +532,6 @@ struct Solver {
         }
       }
       if (S.kz > 0 && S.mc > 0) k_defl_symfill<<<nblk((int64_t)S.kz * S.mc, 256), 256, 0, s>>>(m, S.mc, S.d_Ac);
-    }
-    static bool inv_attr_set = false;
-    if (!inv_attr_set) {
-      BA_CUDA(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 144 * 8));
-      inv_attr_set = true;
     }
     k_coarse_invert<<<1, INV_THREADS, sizeof(double) * (size_t)(m * m), s>>>(m, S.d_Ac, S.d_Aci, S.d_scal);
     S.coarse_gen = S.z_gen;
@@ -636,7 +720,27 @@ struct Solver {
       if (S.h_scal[S_DONE] != 0.0 || launched >= maxit) break;
     }
     *iters = (int)S.h_scal[S_ITERS];
-    if (S.kz > 0 && (S.h_scal[S_DONE] == 2.0 || S.h_scal[S_ERR] == 2.0)) {
+    S.last_solver = BA_SOLVER_PCG;
+    S.last_converged = S.h_scal[S_DONE] == 1.0;
+    S.last_iters = *iters;
+    S.last_rel = S.h_scal[S_REL];
+    if (S.h_scal[S_ERR] == 3.0) {
+      // a peer never published its partial sum (k_pcg_q wait timed out): a communication failure, not a numeric
+      // one -- leave the deflation state alone and say so
+      h->err = "peer-memory exchange timed out (a rank is missing or stalled)";
+      return BA_ERR_COMM;
+    }
+    if (S.h_scal[S_CBAD] != 0.0) {
+      // the coarse matrix was not positive definite: the device zeroed its inverse, so this solve ran (correctly)
+      // with plain block-Jacobi.  Nearly dependent deflation vectors are the usual cause: drop them for good.
+      if (trace_on()) fprintf(stderr, "[bagpu] coarse matrix not positive definite: solve ran without the coarse level\n");
+      BA_CUDA(cudaMemsetAsync(S.d_scal + S_CBAD, 0, sizeof(double), s));
+      if (S.kz > 0) {
+        S.kz = S.kz_base = S.kz_max = 0;
+        S.z_gen += 1;
+      }
+    }
+    if (S.kz > 0 && S.h_scal[S_DONE] == 2.0) {
       // the extended coarse matrix lost definiteness (nearly dependent vectors): drop the deflation vectors
       // for good, rebuild the cluster level and solve again
       S.kz = S.kz_base = S.kz_max = 0;
@@ -728,6 +832,8 @@ void ba_lm_default_params(ba_lm_params* p) {
   p->linesearch = 0;
   p->pcg_max_iter = 1000;
   p->pcg_tol = 1e-13;
+  p->solver = BA_SOLVER_AUTO;
+  p->reserved = 0;
 }
 
 int ba_lm_step(ba_handle* h, const double* x, double lambda, double pcg_tol, int32_t pcg_max_iter, double* delta,
@@ -746,12 +852,13 @@ int ba_lm_step(ba_handle* h, const double* x, double lambda, double pcg_tol, int
   if ((rc = sv.build(S.d_x))) return rc;
   if ((rc = sv.factor(lambda))) return rc;
   int it = 0;
-  rc = sv.pcg(pcg_tol, pcg_max_iter, &it);
+  rc = sv.solve(pcg_tol, pcg_max_iter, &it);
   if (pcg_iters) *pcg_iters = it;
   if (rc) return rc;
   if ((rc = sv.backsub(false))) return rc;
   if ((rc = ba::allreduce_sum(h, S.d_scal + ba::S_DR2, 1))) return rc;
   if ((rc = sv.read_scalars())) return rc;
+  if (S.last_rel < 0.0) S.last_rel = S.h_scal[ba::S_REL];
   if (S.h_scal[ba::S_ERR] != 0.0) {
     h->err = "Schur diagonal block not positive definite";
     return BA_ERR_NUMERIC;
@@ -783,16 +890,19 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
   if (prm_in) prm = *prm_in; else ba_lm_default_params(&prm);
   static const bool trace = getenv("BAGPU_TRACE") != nullptr;  // per-iteration phase times on stderr
   const auto wall_prep = std::chrono::steady_clock::now();
-  int rc = lm_prepare(h);
-  if (rc) return rc;
+  int rc;
+  if (prm.solver != BA_SOLVER_AUTO && prm.solver != h->solver && (rc = ba_set_solver(h, prm.solver))) return rc;
+  const bool was_ready = h->lm.ready;
+  if ((rc = lm_prepare(h))) return rc;
   BA_CUDA(cudaSetDevice(h->device));
   Solver sv(h);
   ba_lm_state& S = h->lm;
   const auto wall0 = std::chrono::steady_clock::now();
   if (trace)
     fprintf(stderr, "[bagpu] lm_prepare %.1f ms\n", std::chrono::duration<double>(wall0 - wall_prep).count() * 1e3);
-  double t_eval = 0, t_asm = 0, t_pcg = 0, t_back = 0;
-  int64_t pcg_total = 0;
+  const double t_prepare = was_ready ? 0.0 : std::chrono::duration<double>(wall0 - wall_prep).count() * 1e3;
+  double t_eval = 0, t_asm = 0, t_pcg = 0, t_back = 0, worst_rel = 0;
+  int64_t pcg_total = 0, capped = 0;
   auto rec = [&](int i) { cudaEventRecord(S.ev[i], h->stream); };
   auto lap = [&](int a, int b) {
     float ms = 0;
@@ -825,12 +935,17 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
     // damped solve (stands in for ldl_factorize + ldl_solve!, src/lm.jl:175-180,227-229)
     rec(0);
     if (need_factor) {
-      if ((rc = sv.factor(lambda))) return rc;
+      rc = sv.factor(lambda);
+      if (rc == BA_ERR_NUMERIC) {  // non-positive pivot: the SQDException of src/ldl_aux.jl:199 -> status exception
+        fail2 = true;
+        continue;
+      }
+      if (rc) return rc;
       need_factor = false;
     }
     rec(1);
     int pit = 0;
-    rc = sv.pcg(prm.pcg_tol, prm.pcg_max_iter, &pit);
+    rc = sv.solve(prm.pcg_tol, prm.pcg_max_iter, &pit);
     pcg_total += pit;
     if (rc == BA_ERR_NUMERIC || S.h_scal[S_ERR] != 0.0) {  // like SQDException / NaN step: status exception
       fail2 = true;
@@ -845,10 +960,18 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
     rec(4);
     BA_CUDA(cudaEventSynchronize(S.ev[4]));
     t_asm += lap(0, 1); t_pcg += lap(1, 2); t_back += lap(2, 3); t_eval += lap(3, 4);
-    if (trace)
-      fprintf(stderr, "[bagpu] iter %lld: factor %.2f ms, pcg %.2f ms (%d iterations, %d deflation vectors), backsub %.2f ms, "
-              "trial %.2f ms, wall %.1f ms\n", (long long)iter, lap(0, 1), lap(1, 2), pit, S.kz, lap(2, 3), lap(3, 4),
+    if (S.last_rel < 0.0) S.last_rel = S.h_scal[S_REL];  // exact solve: left on the device, read by trial()
+    if (!S.last_converged) capped += 1;
+    if (S.last_rel > worst_rel) worst_rel = S.last_rel;
+    if (trace) {
+      fprintf(stderr, "[bagpu] iter %lld: factor %.2f ms, %s %.2f ms (%d iterations, %d deflation vectors, residual %.1e), "
+              "backsub %.2f ms, trial %.2f ms, wall %.1f ms\n", (long long)iter, lap(0, 1), S.exact ? "exact solve" : "pcg",
+              lap(1, 2), pit, S.kz, S.last_rel, lap(2, 3), lap(3, 4),
               std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count() * 1e3);
+      if (!S.last_converged)
+        fprintf(stderr, "[bagpu] iter %lld: PCG stopped at pcg_max_iter = %d with relative residual %.2e > pcg_tol = %.1e: "
+                "the step is inexact\n", (long long)iter, (int)prm.pcg_max_iter, S.last_rel, prm.pcg_tol);
+    }
     dr2 = sq_to_half_norm2(S.h_scal[S_DR2]);
     double norm_rsuiv = sqrt(S.h_scal[S_TR2]);
     double obj_suiv = norm_rsuiv * norm_rsuiv / 2;
@@ -883,6 +1006,7 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
       row.iter = iter; row.f = obj; row.df = old_obj - obj; row.dfeas = norm_Jtr; row.lambda = lambda;
       row.delta_norm = norm_delta; row.rho = ared / pred; row.accepted = step_accepted; row.acc_str = acc_str;
       row.pcg_iters = pit; row.ntimes = ntimes;
+      row.solver = S.last_solver; row.converged = S.last_converged; row.solve_rel = S.last_rel;
       cb(&row, user);
     }
     if (!step_accepted) {
@@ -931,6 +1055,7 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
     st->elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
     st->pcg_iters_total = pcg_total;
     st->t_eval_ms = t_eval; st->t_assemble_ms = t_asm; st->t_pcg_ms = t_pcg; st->t_backsub_ms = t_back;
+    st->capped_solves = capped; st->worst_solve_rel = worst_rel; st->t_prepare_ms = t_prepare;
   }
   return BA_OK;
 }

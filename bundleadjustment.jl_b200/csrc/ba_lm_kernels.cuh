@@ -29,6 +29,8 @@ enum {
   S_XC2,      // sum (x + delta)_c^2
   S_RZ = 16, S_RZ0, S_PQ, S_DONE, S_ITERS, S_REL, S_ERR, S_RZN, S_RCY,
   S_ITK,      // S_ITERS as it was when the current PCG iteration started (read by every CTA of k_pcg_p)
+  S_CBAD,     // the coarse matrix [P Z]'S[P Z] had a non-positive pivot: its inverse was replaced by zero, i.e. the
+              // solves run with plain block-Jacobi (not an error: the preconditioner never changes the solution)
   S_COUNT = 32
 };
 
@@ -1242,9 +1244,11 @@ k_coarse_invert(int m, const double* __restrict__ Ac, double* __restrict__ Aci, 
     Ash[e] = 0.5 * (Ac[a * m + bq] + Ac[bq * m + a]);
   }
   __syncthreads();
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
   for (int k = 0; k < m; ++k) {
     const double piv = Ash[k * m + k];
-    if (!(piv > 0.0) && threadIdx.x == 0) scal[S_ERR] = 2.0;
+    if (!(piv > 0.0) && threadIdx.x == 0) bad = 1;
     if (threadIdx.x < m) {
       colk[threadIdx.x] = Ash[threadIdx.x * m + k];
       rowk[threadIdx.x] = ((int)threadIdx.x == k ? 1.0 : Ash[k * m + threadIdx.x]) / piv;
@@ -1256,10 +1260,14 @@ k_coarse_invert(int m, const double* __restrict__ Ac, double* __restrict__ Aci, 
     }
     __syncthreads();
   }
+  // lost definiteness (rounding of the fixed-point sums at tiny lambda, nearly dependent deflation vectors):
+  // a zero "inverse" switches the coarse level off for the solves that use it
+  const bool zero = bad != 0;
   for (int e = threadIdx.x; e < m * m; e += INV_THREADS) {
     const int a = e / m, bq = e - a * m;
-    Aci[e] = 0.5 * (Ash[a * m + bq] + Ash[bq * m + a]);
+    Aci[e] = zero ? 0.0 : 0.5 * (Ash[a * m + bq] + Ash[bq * m + a]);
   }
+  if (zero && threadIdx.x == 0) scal[S_CBAD] = 1.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1501,6 +1509,172 @@ k_defl_gram(int64_t n9, int N, const double* __restrict__ Y, double* __restrict_
   if (threadIdx.x == 0) {
     G[a * N + b] = t;
     G[b * N + a] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact solve: the reduced camera system assembled explicitly,
+//     S~ = D^-1 (U + lambda I - W (V + lambda I)^-1 W') D^-1,   D = sqrt(diag(U + lambda I))
+// (the Jacobi scaling is the camera part of the reference's column normalisation, src/lma_aux.jl:143-178), for
+// the dense Cholesky of ba_chol.cu.  Off-diagonal blocks: per point, every pair of its observations contributes
+// Yh_k1 Yh_k2' with Yh_k = D_c^-1 (B_k'A_k) L_p, (V_p + lambda I)^-1 = L_p L_p'.  |Yh_k1[i] . Yh_k2[j]| <= 1 and so
+// is every partial sum (Cauchy-Schwarz against diag(W V^-1 W') <= diag(U)), hence the sums are accumulated in
+// 64-bit fixed point (scale 2^61: resolution 4e-19, no overflow): integer addition is associative, so the
+// atomics -- and the allreduce over ranks -- give bit-identical results in any order.  Diagonal blocks come from
+// the ordered FP64 sums of the camera pass (H - Cr).
+// ---------------------------------------------------------------------------------------------
+constexpr double EX_SCALE = 2305843009213693952.0;  // 2^61
+
+// cd[i] = sqrt(U_ii + lambda) for the n9 camera unknowns
+__global__ void __launch_bounds__(256)
+k_exact_diag(int64_t n9, double lambda, const double* __restrict__ Ug, double* __restrict__ cd) {
+  const int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x;
+  if (i >= n9) return;
+  const int64_t c = i / 9;
+  const int j = (int)(i - 9 * c);
+  cd[i] = sqrt(Ug[c * NV + sym9(j, j)] + lambda);
+}
+
+// Yh_k (9 x 3, row-major, 27 doubles per observation) = D_c^-1 (B_k' A_k) L_p; thread per observation
+__global__ void __launch_bounds__(PT_THREADS)
+k_exact_y(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx, int64_t pnt0, int64_t nl,
+          const double2* __restrict__ Jp, const double* __restrict__ Vinv, const double* __restrict__ cd,
+          double* __restrict__ Yh) {
+  __shared__ double st[PT_THREADS * 27];
+  const int64_t k = blockIdx.x * (int64_t)PT_THREADS + threadIdx.x;
+  if (k < nl) {
+    const int64_t p = __ldg(pnt_idx + k) - pnt0;
+    const int c = __ldg(cam_idx + k);
+    const double* vi = Vinv + p * 6;
+    // Cholesky of the symmetric 3 x 3 inverse: Vinv = L L'
+    const double l00 = sqrt(vi[0]), l10 = vi[1] / l00, l20 = vi[2] / l00;
+    const double l11 = sqrt(vi[3] - l10 * l10), l21 = (vi[4] - l20 * l10) / l11;
+    const double l22 = sqrt(vi[5] - (l20 * l20 + l21 * l21));
+    const double2 a0 = Jp[k], a1 = Jp[nl + k], a2 = Jp[2 * nl + k];
+    double* o = st + threadIdx.x * 27;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double2 b = Jp[(int64_t)(3 + i) * nl + k];
+      const double e0 = b.x * a0.x + b.y * a0.y, e1 = b.x * a1.x + b.y * a1.y, e2 = b.x * a2.x + b.y * a2.y;
+      const double di = 1.0 / __ldg(cd + (int64_t)c * 9 + i);
+      o[i * 3 + 0] = ((e0 * l00 + e1 * l10) + e2 * l20) * di;
+      o[i * 3 + 1] = (e1 * l11 + e2 * l21) * di;
+      o[i * 3 + 2] = (e2 * l22) * di;
+    }
+  }
+  __syncthreads();
+  // coalesced store of the block's 128 x 27 doubles
+  const int64_t base = blockIdx.x * (int64_t)PT_THREADS * 27;
+  const int64_t lim = nl * 27;
+  for (int e = threadIdx.x; e < PT_THREADS * 27; e += PT_THREADS)
+    if (base + e < lim) Yh[base + e] = st[e];
+}
+
+// one warp per observation k1: its pairs (k1, k2), k2 earlier in the same point
+__global__ void __launch_bounds__(256)
+k_exact_assemble(const int32_t* __restrict__ pstart, const int32_t* __restrict__ pnt_idx, int64_t pnt0,
+                 const int32_t* __restrict__ cam_idx, int64_t nl, const double* __restrict__ Yh,
+                 unsigned long long* __restrict__ Sq, int64_t ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = blockIdx.x * (int64_t)8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  const int la = lane < 27 ? lane : 0;
+  for (int64_t k1 = warp0; k1 < nl; k1 += nwarps) {
+    const int64_t p = __ldg(pnt_idx + k1) - pnt0;
+    const int k0 = __ldg(pstart + p);
+    if (k0 >= k1) continue;
+    const int c1 = __ldg(cam_idx + k1);
+    const double y1 = __ldg(Yh + k1 * 27 + la);
+    for (int64_t k2 = k0; k2 < k1; ++k2) {
+      const int c2 = __ldg(cam_idx + k2);
+      const double y2 = __ldg(Yh + k2 * 27 + la);
+      const bool swap = c1 < c2;
+      const double yr = swap ? y2 : y1, yc = swap ? y1 : y2;  // row / column camera
+      const int cr = swap ? c2 : c1, cc = swap ? c1 : c2;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int e = la + 27 * u, i = e / 9, j = e - 9 * i;
+        double v = __shfl_sync(0xffffffffu, yr, i * 3) * __shfl_sync(0xffffffffu, yc, j * 3);
+        v += __shfl_sync(0xffffffffu, yr, i * 3 + 1) * __shfl_sync(0xffffffffu, yc, j * 3 + 1);
+        v += __shfl_sync(0xffffffffu, yr, i * 3 + 2) * __shfl_sync(0xffffffffu, yc, j * 3 + 2);
+        bool live = lane < 27;
+        if (cr == cc) {  // the same camera twice on one point (not in BAL files): symmetric part, lower triangle
+          double v2 = __shfl_sync(0xffffffffu, yc, i * 3) * __shfl_sync(0xffffffffu, yr, j * 3);
+          v2 += __shfl_sync(0xffffffffu, yc, i * 3 + 1) * __shfl_sync(0xffffffffu, yr, j * 3 + 1);
+          v2 += __shfl_sync(0xffffffffu, yc, i * 3 + 2) * __shfl_sync(0xffffffffu, yr, j * 3 + 2);
+          v += v2;
+          live = live && i >= j;
+        }
+        if (live) {
+          const long long q = __double2ll_rn(v * EX_SCALE);
+          atomicAdd(Sq + ((int64_t)cr * 9 + i) * ld + (int64_t)cc * 9 + j, (unsigned long long)q);
+        }
+      }
+    }
+  }
+}
+
+// fixed point -> double over the lower triangle, diagonal blocks added, identity on the padding; in place
+__global__ void __launch_bounds__(256)
+k_exact_finish(int64_t n9, int64_t cn, const double* __restrict__ H, const double* __restrict__ Cr,
+               const double* __restrict__ cd, double* S) {
+  const int64_t r = blockIdx.y;
+  const int64_t c = blockIdx.x * (int64_t)256 + threadIdx.x;
+  if (c > r || c >= cn) return;
+  double* sp = S + r * cn + c;
+  if (r >= n9) {
+    *sp = (r == c) ? 1.0 : 0.0;
+    return;
+  }
+  const long long q = *reinterpret_cast<const long long*>(sp);
+  double v = -((double)q / EX_SCALE);
+  const int64_t br = r / 9, bc = c / 9;
+  if (br == bc) {
+    const int i = (int)(r - 9 * br), j = (int)(c - 9 * bc);  // j <= i
+    v += (H[br * 81 + i * 9 + j] - Cr[br * NV + sym9(j, i)]) / (cd[r] * cd[c]);
+  }
+  *sp = v;
+}
+
+// out[i] = in[i] / cd[i] (i < n9), 0 on the padding
+__global__ void __launch_bounds__(256)
+k_exact_scale(int64_t n9, int64_t cn, const double* __restrict__ in, const double* __restrict__ cd,
+              double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x;
+  if (i < cn) out[i] = (i < n9) ? in[i] / cd[i] : 0.0;
+}
+
+// x (+)= xs / cd: the unscaled solution (or its correction)
+__global__ void __launch_bounds__(256)
+k_exact_unscale(int64_t n9, const double* __restrict__ xs, const double* __restrict__ cd, double* __restrict__ x,
+                int accumulate) {
+  const int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x;
+  if (i < n9) x[i] = (accumulate ? x[i] : 0.0) + xs[i] / cd[i];
+}
+
+// r = b - q (q = S x from the matrix-free product), rs = r / cd for the next correction;
+// scal[S_RZN] = sum r^2, scal[S_RZ0] = sum b^2, first step: scal[S_REL] = ||r|| / ||b|| (one CTA, fixed order)
+__global__ void __launch_bounds__(RED_THREADS)
+k_exact_resid(int64_t n9, int64_t cn, const double* __restrict__ b, const double* __restrict__ q,
+              const double* __restrict__ cd, double* __restrict__ rs, double* __restrict__ scal, int first) {
+  __shared__ double sh[RED_THREADS / 32];
+  double r2 = 0.0, b2 = 0.0;
+  for (int64_t i = threadIdx.x; i < cn; i += RED_THREADS) {
+    double rv = 0.0;
+    if (i < n9) {
+      const double bi = b[i];
+      rv = bi - q[i];
+      r2 += rv * rv;
+      b2 += bi * bi;
+      rv /= cd[i];
+    }
+    rs[i] = rv;
+  }
+  r2 = block_sum<RED_THREADS>(r2, sh);
+  b2 = block_sum<RED_THREADS>(b2, sh);
+  if (threadIdx.x == 0) {
+    scal[S_RZN] = r2;
+    scal[S_RZ0] = b2;
+    if (first) scal[S_REL] = sqrt(r2 / b2);  // residual of the direct solve, before any refinement
   }
 }
 

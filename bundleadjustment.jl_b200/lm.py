@@ -37,6 +37,8 @@ class GenericExecutionStats:
     pcg_iters: int = 0
     lambda_final: float = 0.0
     timings_ms: dict = field(default_factory=dict)
+    capped_solves: int = 0          # damped solves that stopped at pcg_max_iter (their steps are inexact)
+    worst_solve_rel: float = 0.0    # largest relative residual a damped solve stopped at
 
 
 def default_params(**kw) -> _lib.LMParams:
@@ -52,7 +54,7 @@ def default_params(**kw) -> _lib.LMParams:
 def Levenberg_Marquardt(model, facto="LDL", perm="AMD", normalize="None", linesearch=False, *, x=None,
                         restol=None, satol=None, srtol=None, oatol=None, ortol=None, atol=None, rtol=None,
                         nu_d=3.0, nu_m=3.0, lam=30.0, delta_d=2.0, ite_max=200, max_time=3600,
-                        pcg_tol=None, pcg_max_iter=None, verbose=False) -> GenericExecutionStats:
+                        pcg_tol=None, pcg_max_iter=None, solver=None, verbose=False) -> GenericExecutionStats:
     """Levenberg_Marquardt(model, facto, perm, normalize, linesearch; x, tolerances, νd, νm, λ, δd, ite_max).
 
     ``model`` is a ``FeasibilityResidual`` (as in src/main.jl:27-30) or the ``BALNLPModel`` itself.
@@ -66,6 +68,8 @@ def Levenberg_Marquardt(model, facto="LDL", perm="AMD", normalize="None", linese
         raise TypeError("model must be a BALNLPModel or its FeasibilityResidual")
     p = default_params(nu_d=nu_d, nu_m=nu_m, lam=lam, delta_d=delta_d, ite_max=int(ite_max),
                        linesearch=1 if linesearch else 0)
+    if solver is not None:  # "auto" | "pcg" | "exact": how the damped system is solved (include/bagpu.h BA_SOLVER_*)
+        p.solver = _lib.SOLVERS[solver]
     for k, v in dict(restol=restol, satol=satol, srtol=srtol, oatol=oatol, ortol=ortol, atol=atol, rtol=rtol,
                      pcg_tol=pcg_tol, pcg_max_iter=pcg_max_iter).items():
         if v is not None:
@@ -78,7 +82,8 @@ def Levenberg_Marquardt(model, facto="LDL", perm="AMD", normalize="None", linese
     def _cb(rowp, _user):
         r = rowp.contents
         d = dict(iter=r.iter, f=r.f, df=r.df, dfeas=r.dfeas, lam=r.lam, delta_norm=r.delta_norm, rho=r.rho,
-                 accepted=bool(r.accepted), acc_str=bool(r.acc_str), pcg_iters=r.pcg_iters, ntimes=r.ntimes)
+                 accepted=bool(r.accepted), acc_str=bool(r.acc_str), pcg_iters=r.pcg_iters, ntimes=r.ntimes,
+                 solver=_lib.SOLVER_NAMES.get(r.solver, "?"), converged=bool(r.converged), solve_rel=r.solve_rel)
         rows.append(d)
         if verbose:  # the 8 columns of log_row (src/lm.jl:120-121,304)
             print("%5d  %9.2e  %9.2e  %9.2e  %9.2e  %9.2e  %9.2e  %s" % (
@@ -98,7 +103,8 @@ def Levenberg_Marquardt(model, facto="LDL", perm="AMD", normalize="None", linese
         elapsed_time=elapsed, dual_feas=st.dual_feas, rows=rows, pcg_iters=int(st.pcg_iters_total),
         lambda_final=st.lambda_final,
         timings_ms=dict(eval=st.t_eval_ms, assemble=st.t_assemble_ms, pcg=st.t_pcg_ms, backsub=st.t_backsub_ms,
-                        device_total=st.elapsed_s * 1e3))
+                        device_total=st.elapsed_s * 1e3, prepare=st.t_prepare_ms),
+        capped_solves=int(st.capped_solves), worst_solve_rel=st.worst_solve_rel)
 
 
 def lm_step(nlp: BALNLPModel, x, lam, pcg_tol=1e-13, pcg_max_iter=500, want_jtr=False):
@@ -113,3 +119,28 @@ def lm_step(nlp: BALNLPModel, x, lam, pcg_tol=1e-13, pcg_max_iter=500, want_jtr=
                                None if jtr is None else jtr.ctypes.data_as(C.c_void_p), C.byref(it))
     _lib.check(rc, nlp.handle)
     return delta, dr2.value, obj.value, jtr, it.value
+
+
+def last_solve_info(nlp: BALNLPModel) -> dict:
+    """Outcome of the last damped solve on this model (ba_last_solve_info): which solver ran, whether it
+    converged, the relative residual it stopped at, its iteration count."""
+    sv, cv, it, rel = C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+    _lib.check(_lib.lib().ba_last_solve_info(nlp.handle, C.byref(sv), C.byref(cv), C.byref(rel), C.byref(it)))
+    return dict(solver=_lib.SOLVER_NAMES.get(sv.value, "?"), converged=bool(cv.value), rel=rel.value, iters=it.value)
+
+
+def dbg_chol(A, b, device=0, want_L=False):
+    """Factor and solve a dense SPD system with the library's device Cholesky (ba_dbg_chol).
+    Returns (x, L or None, factor_ms, solve_ms)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    n = A.shape[0]
+    x = np.empty(n)
+    Lo = np.empty((n, n)) if want_L else None
+    f, s = C.c_float(), C.c_float()
+    rc = _lib.lib().ba_dbg_chol(device, n, A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                x.ctypes.data_as(C.c_void_p), None if Lo is None else Lo.ctypes.data_as(C.c_void_p),
+                                C.byref(f), C.byref(s))
+    if rc:
+        raise _lib.BAError(rc, "ba_dbg_chol")
+    return x, Lo, f.value, s.value

@@ -147,6 +147,11 @@ class BALNLPModel:
         clusters (default 16, at most 24; 0 = plain block-Jacobi).  Changes iteration counts, not solutions."""
         _lib.check(_lib.lib().ba_set_coarse_clusters(self.handle, int(n)), self.handle)
 
+    def set_solver(self, solver: str):
+        """How the damped LM system is solved: "auto" (exact up to 2048 cameras, PCG above), "pcg" (matrix-free
+        preconditioned CG) or "exact" (explicit reduced camera system + dense FP64 Cholesky + refinement)."""
+        _lib.check(_lib.lib().ba_set_solver(self.handle, _lib.SOLVERS[solver]), self.handle)
+
     def set_deflation(self, k: int):
         """PCG of the LM solve: add up to ``k`` (<= 32; default 32; 0 = off) Ritz vectors harvested from the PCG
         solves themselves to the coarse level, plus up to 16 refreshed after every solve.  Changes iteration

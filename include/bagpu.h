@@ -37,8 +37,16 @@ enum {
   BA_ERR_CUDA = 2,      /* CUDA runtime failure, see ba_last_error */
   BA_ERR_UNSORTED = 3,  /* LM entry points need point-major observation order (BAL file order) */
   BA_ERR_COMM = 4,      /* NCCL failure / communicator not initialised */
-  BA_ERR_NUMERIC = 5    /* PCG breakdown (non-finite or non-positive curvature) */
+  BA_ERR_NUMERIC = 5    /* PCG breakdown (non-finite or non-positive curvature), non-positive Cholesky pivot */
 };
+
+/* How the damped system (J'J + lambda I) delta = -J'r is solved once the points are eliminated.  The reference's
+ * facto x perm choices (src/lm.jl:15-19: :LDL / :QR with AMD / Metis) all give the exact solution of that system;
+ * BA_SOLVER_EXACT is their counterpart: the reduced camera system assembled explicitly and factorised by a dense
+ * FP64 Cholesky (what ldl_factorize + ldl_solve!, src/ldl_aux.jl:122-201,4-42, amount to after the ordering has
+ * eliminated residual rows and points) plus refinement steps with the matrix-free FP64 residual.  BA_SOLVER_PCG is
+ * the matrix-free preconditioned CG (stopped at pcg_tol).  AUTO: exact up to 2048 cameras, PCG above. */
+enum { BA_SOLVER_AUTO = 0, BA_SOLVER_PCG = 1, BA_SOLVER_EXACT = 2 };
 
 /* ---- model lifetime: BALNLPModel(filename) ctor, src/BALNLPModels.jl:91-106 ---------------- */
 /* Copies indices and pt2d to the device (caller buffers are not retained).  device = CUDA
@@ -102,6 +110,14 @@ BA_API int ba_set_coarse_clusters(ba_handle* h, int n);
  * preconditioned reduced camera system come without extra products; ba_lm.cu).  Only used
  * for camera systems above the single-CTA threshold.  Changes the iteration count, not the solution. */
 BA_API int ba_set_deflation(ba_handle* h, int k);
+/* Choose the damped solve (BA_SOLVER_*); takes effect from the next LM call on.  Env BAGPU_SOLVER=pcg|exact
+ * sets the default of new handles. */
+BA_API int ba_set_solver(ba_handle* h, int solver);
+/* Outcome of the last damped solve on this handle: solver used (BA_SOLVER_PCG / BA_SOLVER_EXACT), whether it
+ * converged (PCG: reached pcg_tol before pcg_max_iter; exact: factorisation succeeded), the relative residual
+ * it stopped at (PCG: sqrt(r'M^-1 r / r0'M^-1 r0); exact: ||b - S x|| / ||b|| of the direct solve, measured
+ * matrix-free before the refinement step) and its iteration count (PCG iterations / refinement steps). */
+BA_API int ba_last_solve_info(const ba_handle* h, int32_t* solver, int32_t* converged, double* rel, int32_t* iters);
 /* Profiling: with it on, the per-observation evaluation kernel (k_eval: cons!/jac_coord!/fused) is
  * bracketed by CUDA events on the handle's stream and ba_last_eval_ms returns its device time alone
  * (waits for that kernel); for roofline reporting.  Off by default: the events would sit between the
@@ -117,6 +133,8 @@ typedef struct ba_lm_params {
   int32_t linesearch;                                    /* positional arg, src/lm.jl:19 */
   int32_t pcg_max_iter;                                  /* cap per damped solve */
   double pcg_tol;  /* stop when sqrt(r'M^-1 r / r0'M^-1 r0) <= pcg_tol */
+  int32_t solver;  /* BA_SOLVER_*; AUTO = the handle's setting (ba_set_solver) */
+  int32_t reserved;
 } ba_lm_params;
 
 typedef struct ba_lm_row { /* one log_row of src/lm.jl:304, plus solver counters */
@@ -124,8 +142,11 @@ typedef struct ba_lm_row { /* one log_row of src/lm.jl:304, plus solver counters
   double f, df, dfeas, lambda, delta_norm, rho;
   int32_t accepted; /* branch taken at src/lm.jl:306 */
   int32_t acc_str;  /* the logged "acc"/"rej" string rule of src/lm.jl:260 */
-  int32_t pcg_iters;
+  int32_t pcg_iters; /* PCG iterations (refinement steps of the exact solve) */
   int32_t ntimes;   /* back-tracking halvings, src/lm.jl:262-295 */
+  int32_t solver;   /* BA_SOLVER_PCG / BA_SOLVER_EXACT */
+  int32_t converged; /* 0: the solve stopped at pcg_max_iter with solve_rel > pcg_tol (the step is inexact) */
+  double solve_rel; /* relative residual the solve stopped at (see ba_last_solve_info) */
 } ba_lm_row;
 
 typedef struct ba_lm_stats {
@@ -136,6 +157,9 @@ typedef struct ba_lm_stats {
   double objective, dual_feas, lambda_final, elapsed_s;
   int64_t pcg_iters_total;
   double t_eval_ms, t_assemble_ms, t_pcg_ms, t_backsub_ms; /* CUDA-event phase totals */
+  int64_t capped_solves;   /* damped solves that hit pcg_max_iter before pcg_tol (their steps are inexact) */
+  double worst_solve_rel;  /* largest solve_rel over the iterations */
+  double t_prepare_ms;     /* one-off schedule construction + allocations (first LM call on a handle) */
 } ba_lm_stats;
 
 typedef void (*ba_iter_cb)(const ba_lm_row* row, void* user);
@@ -167,6 +191,12 @@ BA_API int ba_comm_ipc_import(ba_handle* h, const uint8_t* handles64_by_rank);
 /* Return to NCCL for that exchange, e.g. when ba_comm_ipc_import failed on some rank (peer access
  * unavailable): every rank must take the same path, so call it on all ranks or on none. */
 BA_API int ba_comm_ipc_disable(ba_handle* h);
+
+/* Debug / benchmark entry of the dense FP64 Cholesky used by BA_SOLVER_EXACT: factorises the caller's SPD matrix
+ * (n x n, row-major, host) on `device`, solves A x = b, optionally returns L (n x n row-major, lower triangle
+ * live) and the device times of the two phases.  Not part of the reference's surface. */
+BA_API int ba_dbg_chol(int device, int64_t n, const double* A_rowmajor, const double* b, double* x, double* L_out,
+                       float* factor_ms, float* solve_ms);
 
 /* ---- host-only helpers of the PCG deflation space (no GPU; exported so that they can be unit-tested) ------ */
 /* Eigenpairs of the Lanczos tridiagonal defined by the CG coefficients alpha[0..m), beta[0..m-1):

@@ -14,19 +14,26 @@ from conftest import TOL, small_problem
 pytestmark = pytest.mark.gpu
 
 
-def _model(ba, p, **kw):
-    return ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs, **kw)
+def _model(ba, p, solver=None, **kw):
+    m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs, **kw)
+    if solver is not None:
+        m.set_solver(solver)   # "pcg": matrix-free PCG; "exact": explicit Schur complement + dense Cholesky
+    return m
+
+
+SOLVERS = ["pcg", "exact"]
 
 
 def _rel(a, b):
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
+@pytest.mark.parametrize("solver", SOLVERS)
 @pytest.mark.parametrize("shape,lam", [((9, 300, 1500), 30.0), ((9, 300, 1500), 1e3), ("ladybug-49", 30.0),
                                         ("ladybug-49", 419.0)])
-def test_lm_step_matches_ldl_oracle(ba, oracle, shape, lam):
+def test_lm_step_matches_ldl_oracle(ba, oracle, shape, lam, solver):
     p = ba.synth.make_problem(shape)
-    m = _model(ba, p)
+    m = _model(ba, p, solver)
     d_ref, dr2_ref, jtr_ref = oracle.lm_step(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, lam, want_jtr=True)
     d, dr2, obj, jtr, iters = ba.lm_step(m, p.x0, lam, pcg_tol=1e-13, pcg_max_iter=1000, want_jtr=True)
     npt = 3 * p.npnts
@@ -37,6 +44,9 @@ def test_lm_step_matches_ldl_oracle(ba, oracle, shape, lam):
     assert abs(obj - 0.5 * float(r @ r)) <= 1e-12 * obj
     assert _rel(jtr, jtr_ref) <= TOL
     assert 0 < iters < 1000
+    info = ba.lm.last_solve_info(m)
+    assert info["solver"] == solver and info["converged"] and info["iters"] == iters
+    assert info["rel"] <= (1e-13 if solver == "pcg" else 1e-9)
 
 
 def _first_lambda(m, p):
@@ -45,25 +55,41 @@ def _first_lambda(m, p):
     return max(30.0, 1e10 / float(np.linalg.norm(g)))
 
 
+_SCHUR_CACHE = {}
+
+
+def _schur_ref(oracle, p, shape, lam):
+    key = (shape, lam)
+    if key not in _SCHUR_CACHE:
+        if len(_SCHUR_CACHE) > 2:
+            _SCHUR_CACHE.clear()
+        _SCHUR_CACHE[key] = oracle.lm_step_schur(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, lam,
+                                                 want_jtr=True)
+    return _SCHUR_CACHE[key]
+
+
 @pytest.mark.parametrize("shape,lam", [("trafalgar-257", 30.0), ("trafalgar-257", 1e3), ("trafalgar-257", "first"),
                                         ("dubrovnik-356", 30.0), ("dubrovnik-356", 1e3),
                                         ("venice-1778", 30.0), ("venice-1778", 1e3)])
-def test_lm_step_matches_schur_oracle_at_baseline_sizes(ba, oracle, shape, lam):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_lm_step_matches_schur_oracle_at_baseline_sizes(ba, oracle, shape, lam, solver):
     """The damped solve at the BASELINE.json sizes against an independent exact solver: the oracle's own
     jac_coord values, points eliminated, dense Cholesky (LAPACK) of the reduced camera system -- the pivot
     order AMD/Metis give the reference's LDL' on a BA Jacobian (oracle.lm_step_schur)."""
     from conftest import parity_report, rel_errors
     p = ba.synth.make_problem(shape)
-    m = _model(ba, p)
+    m = _model(ba, p, solver)
     if lam == "first":
         lam = _first_lambda(m, p)
-    d_ref, dr2_ref, jtr_ref = oracle.lm_step_schur(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, lam,
-                                                   want_jtr=True)
+    d_ref, dr2_ref, jtr_ref = _schur_ref(oracle, p, shape, lam)
     d, dr2, obj, jtr, iters = ba.lm_step(m, p.x0, lam, pcg_tol=1e-13, pcg_max_iter=4000, want_jtr=True)
+    info = ba.lm.last_solve_info(m)
     m.close()
+    assert info["solver"] == solver and info["converged"]
     npt = 3 * p.npnts
     ep, ec, ej = rel_errors(d[:npt], d_ref[:npt]), rel_errors(d[npt:], d_ref[npt:]), rel_errors(jtr, jtr_ref)
-    parity_report("lm_step_vs_schur_oracle", shape=shape, lam=lam, solver_iters=int(iters),
+    parity_report("lm_step_vs_schur_oracle", shape=shape, lam=lam, solver=solver, solver_iters=int(iters),
+                  solve_rel=info["rel"],
                   points=dict(norm=ep[0], floor=ep[1], entry=ep[2]), cameras=dict(norm=ec[0], floor=ec[1], entry=ec[2]),
                   jtr=dict(norm=ej[0], floor=ej[1], entry=ej[2]), dr2=abs(dr2 - dr2_ref) / dr2_ref)
     assert ep[0] <= TOL and ec[0] <= TOL, "LM step (norm-wise): points %.2e cameras %.2e" % (ep[0], ec[0])
@@ -72,30 +98,41 @@ def test_lm_step_matches_schur_oracle_at_baseline_sizes(ba, oracle, shape, lam):
     assert ej[0] <= TOL
 
 
+_TRAJ_CACHE = {}
+
+
 @pytest.mark.parametrize("shape", ["trafalgar-257", "dubrovnik-356", "venice-1778"])
-def test_lm_first_iterations_match_schur_oracle(ba, oracle, shape):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_lm_first_iterations_match_schur_oracle(ba, oracle, shape, solver):
     """Three LM iterations (f, lambda, accept/reject, ||J'r||, ||delta||) at the BASELINE.json sizes against the
     oracle's src/lm.jl loop with the Schur-ordered exact solve."""
     from conftest import parity_report
     p = ba.synth.make_problem(shape)
     m = _model(ba, p)
-    st = ba.Levenberg_Marquardt(ba.FeasibilityResidual(m), "LDL", "AMD", "None", False, ite_max=2, pcg_max_iter=4000)
+    st = ba.Levenberg_Marquardt(ba.FeasibilityResidual(m), "LDL", "AMD", "None", False, ite_max=2, pcg_max_iter=4000,
+                                solver=solver)
     m.close()
-    ref = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0,
-                          oracle.default_params(ite_max=2, nthreads=oracle.max_threads()), solver="schur")
+    assert all(r["solver"] == solver and r["converged"] for r in st.rows) and st.capped_solves == 0
+    if shape not in _TRAJ_CACHE:
+        _TRAJ_CACHE.clear()
+        _TRAJ_CACHE[shape] = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0,
+                                             oracle.default_params(ite_max=2, nthreads=oracle.max_threads()),
+                                             solver="schur")
+    ref = _TRAJ_CACHE[shape]
     worst = dict(f=0.0, lam=0.0, dfeas=0.0, delta_norm=0.0)
     for a, b in zip(st.rows, ref.log):
         for k in worst:
             worst[k] = max(worst[k], abs(a[k] - b[k]) / abs(b[k]))
-    parity_report("lm_trajectory_vs_schur_oracle", shape=shape, iters=int(st.iter), **worst,
+    parity_report("lm_trajectory_vs_schur_oracle", shape=shape, solver=solver, iters=int(st.iter), **worst,
                   objective=abs(st.objective - ref.objective) / ref.objective,
                   solution=_rel(st.solution, ref.solution))
     _compare_trajectories(st, ref, f_tol=1e-9)
 
 
-def test_lm_step_small_lambda_is_conditioning_limited(ba, oracle):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_lm_step_small_lambda_is_conditioning_limited(ba, oracle, solver):
     p = ba.synth.make_problem((9, 300, 1500))
-    m = _model(ba, p)
+    m = _model(ba, p, solver)
     d_ref, dr2_ref = oracle.lm_step(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, 1e-2)
     d, dr2, _, _, _ = ba.lm_step(m, p.x0, 1e-2, pcg_tol=1e-13, pcg_max_iter=2000)
     assert _rel(d, d_ref) <= 1e-7          # cond * eps territory for both solvers
@@ -132,10 +169,11 @@ def _compare_trajectories(st, ref, f_tol=1e-9, loose=1.0):
     assert _rel(st.solution, ref.solution) <= 1e-6 * loose
 
 
+@pytest.mark.parametrize("solver", SOLVERS)
 @pytest.mark.parametrize("shape", [(9, 300, 1500), (12, 400, 2000)])
-def test_lm_trajectory_matches_oracle(ba, oracle, shape):
+def test_lm_trajectory_matches_oracle(ba, oracle, shape, solver):
     p = ba.synth.make_problem(shape)
-    m = _model(ba, p)
+    m = _model(ba, p, solver)
     st = ba.Levenberg_Marquardt(ba.FeasibilityResidual(m), "LDL", "AMD", "None", False)
     ref = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0)
     _compare_trajectories(st, ref)
@@ -143,10 +181,11 @@ def test_lm_trajectory_matches_oracle(ba, oracle, shape):
     assert st.pcg_iters > 0 and st.timings_ms["pcg"] > 0
 
 
-def test_lm_ladybug_shape_trajectory(ba, oracle):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_lm_ladybug_shape_trajectory(ba, oracle, solver):
     # BASELINE.json configs[0]: LadyBug problem-49-7776 shape (31,843 observations)
     p = ba.synth.make_problem("ladybug-49")
-    m = _model(ba, p)
+    m = _model(ba, p, solver)
     st = ba.Levenberg_Marquardt(ba.FeasibilityResidual(m), "LDL", "Metis", "None", False, ite_max=12)
     ref = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, oracle.default_params(ite_max=12))
     _compare_trajectories(st, ref, f_tol=1e-8)
@@ -161,13 +200,14 @@ def _far_start(p):
     return x0
 
 
+@pytest.mark.parametrize("solver", SOLVERS)
 @pytest.mark.parametrize("linesearch", [False, True])
-def test_lm_rejected_steps_and_linesearch_match_oracle(ba, oracle, linesearch):
+def test_lm_rejected_steps_and_linesearch_match_oracle(ba, oracle, linesearch, solver):
     # the reject branch (lambda = max(lambda, 1/||delta||) * nu_m^(ntimes+1), src/lm.jl:306-325) and the
     # back-tracking branch (src/lm.jl:262-295, including its (dr - r)/dd update of the LDL path)
     p = ba.synth.make_problem((9, 300, 1500))
     x0 = _far_start(p)
-    m = _model(ba, p)
+    m = _model(ba, p, solver)
     kw = dict(nu_d=30.0, ite_max=1)  # two iterations: the wild start makes later ones chaotic
     st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", linesearch, x=x0, **kw)
     ref = oracle.lm_solve(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, x0,
@@ -181,10 +221,11 @@ def test_lm_rejected_steps_and_linesearch_match_oracle(ba, oracle, linesearch):
     _compare_trajectories(st, ref, f_tol=1e-4, loose=1e3)
 
 
-def test_lm_normalize_and_facto_variants_are_the_same_solve(ba):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_lm_normalize_and_facto_variants_are_the_same_solve(ba, solver):
     # every facto x perm x normalize combination of the reference solves the same system
     p = ba.synth.make_problem((9, 300, 1500))
-    m = _model(ba, p)
+    m = _model(ba, p, solver)
     a = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=5)
     b = ba.Levenberg_Marquardt(m, "QR", "Metis", "J", False, ite_max=5)
     assert a.objective == b.objective and a.iter == b.iter   # deterministic reductions: bit-identical reruns
@@ -311,7 +352,7 @@ def test_final_shape_on_one_gpu(ba, oracle):
 def test_two_level_preconditioner_changes_iterations_not_the_step(ba, oracle):
     # block-Jacobi + coarse level over camera clusters vs plain block-Jacobi: same solve, fewer PCG iterations
     p = ba.synth.make_problem("ladybug-49")
-    m = _model(ba, p)
+    m = _model(ba, p, "pcg")
     d_ref, dr2_ref = oracle.lm_step(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, 30.0)
     out = {}
     for n in (0, 2, 8):
@@ -322,13 +363,14 @@ def test_two_level_preconditioner_changes_iterations_not_the_step(ba, oracle):
     assert out[2] <= out[0] and out[8] <= out[0]
 
 
-def test_points_seen_by_more_than_32_cameras(ba, oracle):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_points_seen_by_more_than_32_cameras(ba, oracle, solver):
     # the point-major pass packs whole points into warps; a point with more than 32 observations takes the
     # multi-chunk path (one warp sweeps the point twice).  Parity of the step and of the trajectory there.
     p = ba.synth.make_problem((40, 200, 4000))
     deg = np.bincount(p.pnt_idx)[1:]
     assert (deg > 32).sum() >= 1 and deg.max() <= 40
-    m = _model(ba, p)
+    m = _model(ba, p, solver)
     d_ref, dr2_ref = oracle.lm_step(p.cam_idx, p.pnt_idx, p.pt2d, p.ncams, p.npnts, p.x0, 100.0)
     d, dr2, _, _, _ = ba.lm_step(m, p.x0, 100.0)
     assert _rel(d, d_ref) <= TOL and abs(dr2 - dr2_ref) <= TOL * dr2_ref
@@ -346,6 +388,7 @@ def test_deflated_pcg_gives_the_same_step_in_fewer_iterations(ba, monkeypatch):
     from conftest import assert_rel
     p = ba.synth.make_problem((160, 10000, 50000))       # 1440 camera rows: the multi-CTA vector kernels
     m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    m.set_solver("pcg")
     m.set_deflation(0)
     d_ref, dr_ref, _, _, it_ref = ba.lm_step(m, p.x0, 30.0, pcg_max_iter=2000)
     m.set_deflation(32)

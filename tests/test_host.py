@@ -109,10 +109,12 @@ int main(void) {
   printf("ba_lm_row %zu\n", sizeof(ba_lm_row));
   printf("ba_lm_stats %zu\n", sizeof(ba_lm_stats));
   P(ba_lm_params, restol); P(ba_lm_params, nu_d); P(ba_lm_params, lambda); P(ba_lm_params, ite_max);
-  P(ba_lm_params, linesearch); P(ba_lm_params, pcg_max_iter); P(ba_lm_params, pcg_tol);
-  P(ba_lm_row, iter); P(ba_lm_row, rho); P(ba_lm_row, accepted); P(ba_lm_row, ntimes);
+  P(ba_lm_params, linesearch); P(ba_lm_params, pcg_max_iter); P(ba_lm_params, pcg_tol); P(ba_lm_params, solver);
+  P(ba_lm_row, iter); P(ba_lm_row, rho); P(ba_lm_row, accepted); P(ba_lm_row, ntimes); P(ba_lm_row, solver);
+  P(ba_lm_row, converged); P(ba_lm_row, solve_rel);
   P(ba_lm_stats, status); P(ba_lm_stats, iter); P(ba_lm_stats, objective); P(ba_lm_stats, pcg_iters_total);
-  P(ba_lm_stats, t_backsub_ms);
+  P(ba_lm_stats, t_backsub_ms); P(ba_lm_stats, capped_solves); P(ba_lm_stats, worst_solve_rel);
+  P(ba_lm_stats, t_prepare_ms);
   return 0;
 }
 ''')
@@ -125,12 +127,17 @@ int main(void) {
     assert int(got["ba_lm_stats"]) == C.sizeof(L.LMStats)
     for cname, cls, names in (("ba_lm_params", L.LMParams, {"restol": "restol", "nu_d": "nu_d", "lambda": "lam",
                                                              "ite_max": "ite_max", "linesearch": "linesearch",
-                                                             "pcg_max_iter": "pcg_max_iter", "pcg_tol": "pcg_tol"}),
+                                                             "pcg_max_iter": "pcg_max_iter", "pcg_tol": "pcg_tol",
+                                                             "solver": "solver"}),
                               ("ba_lm_row", L.LMRow, {"iter": "iter", "rho": "rho", "accepted": "accepted",
-                                                       "ntimes": "ntimes"}),
+                                                       "ntimes": "ntimes", "solver": "solver", "converged": "converged",
+                                                       "solve_rel": "solve_rel"}),
                               ("ba_lm_stats", L.LMStats, {"status": "status", "iter": "iter", "objective": "objective",
                                                            "pcg_iters_total": "pcg_iters_total",
-                                                           "t_backsub_ms": "t_backsub_ms"})):
+                                                           "t_backsub_ms": "t_backsub_ms",
+                                                           "capped_solves": "capped_solves",
+                                                           "worst_solve_rel": "worst_solve_rel",
+                                                           "t_prepare_ms": "t_prepare_ms"})):
         for cf, pf in names.items():
             assert int(got["%s.%s" % (cname, cf)]) == getattr(cls, pf).offset, (cname, cf)
 
