@@ -110,6 +110,45 @@ def cpu_model() -> str:
     return "unknown"
 
 
+LM_REF_CONFIGS = ("ladybug-49", "trafalgar-257")   # configs of BASELINE.json on which both arms time full LM runs
+LM_REF_ITERS = 6
+
+
+def workload_config(args, p):
+    """The `config` object: identical in both arms."""
+    return {"workload": args.workload, "ncams": p.ncams, "npnts": p.npnts, "nobs": p.nobs}
+
+
+def reference_lm_legs(args, nt):
+    """LM iters/s of the CPU restatement (src/benchmark.jl:31: Levenberg_Marquardt(FeasibilityResidual(BA), :LDL,
+    :AMD, ...)): the oracle's src/lm.jl loop with the damped system eliminated in the order AMD gives it on a BA
+    Jacobian (points first, dense Cholesky of the camera system), all host threads.  Whole runs of LM_REF_ITERS
+    iterations on the small BASELINE.json configs; on the bench workload itself one iteration (evaluation + one
+    exact solve, LAPACK for the dense factor) as the bounded sample."""
+    import bundleadjustment.jl_b200.synth as synth
+    from oracle import oracle as O
+    out = {}
+    for name in LM_REF_CONFIGS:
+        q = synth.make_problem(name)
+        prm = O.default_params(ite_max=LM_REF_ITERS - 1, nthreads=nt)
+        t0 = time.perf_counter()
+        r = O.lm_solve(q.cam_idx, q.pnt_idx, q.pt2d, q.ncams, q.npnts, q.x0, prm, solver="schur")
+        dt = time.perf_counter() - t0
+        out[name] = {"value": r.iter / dt, "unit": "LM iters/s", "iters": r.iter, "objective": r.objective,
+                     "status": r.status, "seconds": dt}
+    if args.lm_iters > 0:
+        q = synth.make_problem(args.workload)
+        if q.ncams <= 2048:
+            t0 = time.perf_counter()
+            O.lm_step_schur(q.cam_idx, q.pnt_idx, q.pt2d, q.ncams, q.npnts, q.x0, 30.0, nthreads=nt, dense="scipy")
+            dt = time.perf_counter() - t0
+            out[args.workload] = {"value": 1.0 / dt, "unit": "LM iters/s", "iters": 1, "seconds": dt,
+                                  "sample": "one LM iteration: cons! + jac_coord! + J'r + one exact damped solve "
+                                            "(Schur-ordered, LAPACK dpotrf on the %d x %d camera system)"
+                                            % (9 * q.ncams, 9 * q.ncams)}
+    return out
+
+
 def run_reference(args):
     """CPU arm: the restatement of the reference (oracle/ba_oracle.c) on the host cores.  cons! uses all
     threads (Threads.@threads, src/BALNLPModels.jl:45); jac_coord! is capped at 3 like the reference
@@ -137,12 +176,14 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": args.workload, "ncams": p.ncams, "npnts": p.npnts, "nobs": p.nobs},
+           "config": workload_config(args, p),
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "port", "cpu_model": cpu_model(),
                             "sample": "full %s problem per step; cons! on %d threads, jac_coord! on %d "
                                       "(reference caps it at 3)" % (args.workload, nt, min(nt, 3))},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    if not args.no_lm_reference:
+        out["lm_configs"] = reference_lm_legs(args, nt)
     print(json.dumps(out), flush=True)
 
 
@@ -179,6 +220,8 @@ def main():
     ap.add_argument("--lm-iters", type=int, default=8, help="LM iterations timed in the lm leg (0 = skip)")
     ap.add_argument("--pcg-max-iter", type=int, default=None, help="cap PCG iterations per solve (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lm-reference", action="store_true", help="skip the LM legs on the small configs")
+    ap.add_argument("--solver", default="auto", choices=["auto", "pcg", "exact"], help="damped solve of the LM leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -299,36 +342,111 @@ def main():
     h2d, d2h = 8 * p.nvar, 208 * nl
     for ptr in (x_h, cx_h, vals_h):
         L.ba_free_pinned(ptr)
+    # the same call with ordinary (pageable) arrays -- what a plain `ccall` with Vector{Float64} passes.  The
+    # library pins caller buffers it sees repeatedly (cudaHostRegister, cached by address), so from the second
+    # call on the copies run at the pinned rate.
+    cx_p, vals_p = np.empty(2 * max(nl, 1)), np.empty(24 * max(nl, 1))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    t0 = time.perf_counter()
+    ba._lib.check(L.ba_residual_jac(h, vp(p.x0), vp(cx_p), vp(vals_p)), h)
+    first_pageable_s = time.perf_counter() - t0
+    ba._lib.check(L.ba_residual_jac(h, vp(p.x0), vp(cx_p), vp(vals_p)), h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ba._lib.check(L.ba_residual_jac(h, vp(p.x0), vp(cx_p), vp(vals_p)), h)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_pageable_s = float(t.item())
+    del cx_p, vals_p
 
     # ---- LM leg: full Levenberg-Marquardt iterations per second on the same problem ----------------------
-    lm = None
+    lm, lm_configs, parity = None, None, None
     if args.lm_iters > 0:
-        lm_warm = None
-        if world == 1:
-            # untimed warm-up (the contract's W): a 3-iteration solve of a small synthetic problem whose camera
-            # system is above the single-CTA threshold, so that every LM kernel is loaded before the timed call;
-            # nothing of the timed problem is precomputed -- its schedules (lm_prepare) are built inside the timing
-            pw = ba.synth.make_problem((160, 10000, 50000))
-            mw = ba.BALNLPModel(pw.cam_idx, pw.pnt_idx, pw.pt2d, pw.x0, pw.ncams, pw.npnts, pw.nobs, device=local)
-            try:
-                ba.Levenberg_Marquardt(mw, "LDL", "AMD", "None", False, ite_max=2, pcg_max_iter=args.pcg_max_iter)
-                lm_warm = "one 3-iteration solve of a (160, 10000, 50000) synthetic problem on its own handle"
-            finally:
-                mw.close()
         ba.init_comm(m)
+        # untimed warm-up (the contract's W), identical at every N: a 3-iteration solve of a small synthetic problem
+        # SHARDED like the timed one (own handle, own communicator), once per solver, so that every LM kernel, the
+        # NCCL channels and the peer-memory exchange are loaded before the timed call.  Nothing of the timed problem
+        # is precomputed: its schedules (lm_prepare) are built inside the timing.
+        pw = ba.synth.make_problem((160, 10000, 50000))
+        mw = ba.BALNLPModel(pw.cam_idx, pw.pnt_idx, pw.pt2d, pw.x0, pw.ncams, pw.npnts, pw.nobs, device=local,
+                            rank=rank, nranks=world)
+        ba._lib.check(L.ba_set_stream(mw.handle, C.c_void_p(stream.cuda_stream)), mw.handle)
+        ba.init_comm(mw)
+        steps_w = {}
+        try:
+            for sv in ("pcg", "exact"):
+                ba.Levenberg_Marquardt(mw, "LDL", "AMD", "None", False, ite_max=2, solver=sv,
+                                       pcg_max_iter=args.pcg_max_iter)
+                steps_w[sv] = ba.lm_step(mw, pw.x0, 30.0)[0]
+        finally:
+            mw.close()
+        lm_warm = ("3-iteration solves (PCG and exact) of a (160, 10000, 50000) synthetic problem, sharded over the "
+                   "same %d rank(s), on its own handle" % world)
+        if world > 1 and rank == 0:
+            # driver-visible multi-GPU parity: the sharded damped solve against the same solve on one GPU
+            m1 = ba.BALNLPModel(pw.cam_idx, pw.pnt_idx, pw.pt2d, pw.x0, pw.ncams, pw.npnts, pw.nobs, device=local)
+            parity = {"problem": "(160, 10000, 50000), lambda 30", "ranks": world}
+            try:
+                for sv in ("pcg", "exact"):
+                    m1.set_solver(sv)
+                    d1 = ba.lm_step(m1, pw.x0, 30.0)[0]
+                    parity[sv + "_rel_err_vs_1gpu"] = float(np.linalg.norm(steps_w[sv] - d1) / np.linalg.norm(d1))
+                parity["ok"] = bool(max(parity["pcg_rel_err_vs_1gpu"], parity["exact_rel_err_vs_1gpu"]) <= 1e-10)
+            finally:
+                m1.close()
         barrier()
         t0 = time.perf_counter()
         st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=args.lm_iters - 1,
-                                    pcg_max_iter=args.pcg_max_iter)
+                                    pcg_max_iter=args.pcg_max_iter, solver=args.solver)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         lm = {"metric": "LM iters/s", "value": st.iter / float(t.item()), "iters": st.iter,
-              "pcg_iters": st.pcg_iters, "objective0": st.rows[0]["f"] if st.rows else None,
+              "solver": st.rows[0]["solver"] if st.rows else None,
+              "pcg_iters": st.pcg_iters, "capped_solves": st.capped_solves, "worst_solve_rel": st.worst_solve_rel,
+              "objective0": st.rows[0]["f"] if st.rows else None,
               "objective": st.objective, "status": st.status, "timings_ms": st.timings_ms,
-              "e2e": "x0 host -> solution host through Levenberg_Marquardt()", "warmup": lm_warm}
+              "e2e": "x0 host -> solution host through Levenberg_Marquardt(), schedules (lm_prepare) included",
+              "warmup": lm_warm}
+        if st.chol_count:
+            fl = st.chol_n ** 3 / 3.0
+            lm["cholesky"] = {"n": st.chol_n, "count": st.chol_count, "ms_each": st.timings_ms["cholesky"] / st.chol_count,
+                              "TFLOPs": fl * st.chol_count / (st.timings_ms["cholesky"] * 1e-3) / 1e12,
+                              "schur_assembly_ms_each": st.timings_ms["schur_assembly"] / st.chol_count}
+        # a second, warm run on the same handle: the steady-state rate once the schedules exist
+        barrier()
+        t0 = time.perf_counter()
+        st2 = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=args.lm_iters - 1,
+                                     pcg_max_iter=args.pcg_max_iter, solver=args.solver)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lm["value_warm_handle"] = st2.iter / float(t.item())
+        lm["objective_rerun_equal"] = bool(st2.objective == st.objective)
+        if world == 1 and not args.no_lm_reference:
+            # the configs the reference arm times whole LM runs on (bench.py --impl reference, lm_configs)
+            lm_configs = {}
+            for name in LM_REF_CONFIGS:
+                q = ba.synth.make_problem(name)
+                mq = ba.BALNLPModel(q.cam_idx, q.pnt_idx, q.pt2d, q.x0, q.ncams, q.npnts, q.nobs, device=local)
+                try:
+                    t0 = time.perf_counter()
+                    sq = ba.Levenberg_Marquardt(mq, "LDL", "AMD", "None", False, ite_max=LM_REF_ITERS - 1)
+                    dtq = time.perf_counter() - t0
+                finally:
+                    mq.close()
+                lm_configs[name] = {"value": sq.iter / dtq, "unit": "LM iters/s", "iters": sq.iter,
+                                    "objective": sq.objective, "status": sq.status, "seconds": dtq,
+                                    "solver": sq.rows[0]["solver"] if sq.rows else None}
+            lm_configs[args.workload] = {"value": lm["value"], "unit": "LM iters/s", "iters": lm["iters"]}
 
     if rank == 0:
         clocks = sampler.summary()  # sampled every 100 ms from warm-up to the end of the last leg
@@ -345,14 +463,16 @@ def main():
             "metric": METRIC, "value": p.nobs / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "ncams": p.ncams, "npnts": p.npnts, "nobs": p.nobs,
-                       "sharding": "observations, contiguous point ranges, %d rank(s)" % world,
+            "config": workload_config(args, p),
+            "layout": {"sharding": "observations, contiguous point ranges, %d rank(s)" % world,
                        "l2": "per-step footprint %.0f MB, outputs rotate over %d buffers (> L2)" % (
                            step_bytes / 1e6, ring)},
-            "e2e": {"value": p.nobs / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "pcie_GB/s": (h2d + d2h) / e2e_s / 1e9,
+            "e2e": {"value": p.nobs / e2e_pageable_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "pcie_GB/s": (h2d + d2h) / e2e_pageable_s / 1e9,
                     "note": "bound by the device-to-host copy of vals (192 B/obs) over PCIe, not by the kernel",
-                    "api": "ba_residual_jac (host pointers, pinned), per rank"},
+                    "api": "ba_residual_jac with ordinary (pageable) host arrays, per rank -- what a ccall passes; the "
+                           "library pins buffers it sees repeatedly",
+                    "value_pinned_buffers": p.nobs / e2e_s / 1e6, "first_call_s": first_pageable_s},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "ba::k_eval<true,true>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, world),
@@ -368,6 +488,10 @@ def main():
         }
         if lm:
             out["lm"] = lm
+        if lm_configs:
+            out["lm_configs"] = lm_configs
+        if parity:
+            out["parity_multi_gpu"] = parity
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(p, args.workload)
         print(json.dumps(out), flush=True)

@@ -43,7 +43,8 @@ class LMStats(C.Structure):
                 ("dual_feas", C.c_double), ("lambda_final", C.c_double), ("elapsed_s", C.c_double),
                 ("pcg_iters_total", C.c_int64), ("t_eval_ms", C.c_double), ("t_assemble_ms", C.c_double),
                 ("t_pcg_ms", C.c_double), ("t_backsub_ms", C.c_double), ("capped_solves", C.c_int64),
-                ("worst_solve_rel", C.c_double), ("t_prepare_ms", C.c_double)]
+                ("worst_solve_rel", C.c_double), ("t_prepare_ms", C.c_double), ("t_schur_ms", C.c_double),
+                ("t_chol_ms", C.c_double), ("chol_n", C.c_int64), ("chol_count", C.c_int64)]
 
 
 ITER_CB = C.CFUNCTYPE(None, C.POINTER(LMRow), C.c_void_p)
@@ -53,12 +54,14 @@ _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int32, C.c_double
 SYMBOLS = {
     "ba_create": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, C.c_int, C.POINTER(_vp)]),
     "ba_create_sharded": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "ba_create_multi": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, C.POINTER(_vp)]),
     "ba_destroy": (C.c_int, [_vp]),
     "ba_shard_range": (C.c_int, [_vp] + [C.POINTER(_i64)] * 4),
     "ba_partition_observations": (C.c_int, [_i64, _vp, C.c_int, _vp]),
     "ba_last_error": (C.c_char_p, [_vp]),
     "ba_version": (C.c_char_p, []),
     "ba_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "ba_measure_fp64_mma_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "ba_set_stream": (C.c_int, [_vp, _vp]),
     "ba_alloc_pinned": (C.c_int, [C.c_uint64, C.POINTER(_vp)]),
     "ba_free_pinned": (C.c_int, [_vp]),

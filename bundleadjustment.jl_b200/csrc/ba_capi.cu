@@ -24,6 +24,13 @@ int fail(ba_handle* h, int code, const char* msg) {
 int stage_x(ba_handle* h, const double* x) {
   int rc = dev_alloc(h, &h->d_x, (size_t)h->nvar());
   if (rc) return rc;
+  if (h->nranks > 1) {
+    // observation-sharded: the per-observation kernels of this rank touch its own points and the cameras only
+    const size_t p0 = 3 * (size_t)h->pnt0, np = 3 * (size_t)h->npnts_l(), c0 = 3 * (size_t)h->npnts;
+    if (np) BA_CUDA(cudaMemcpyAsync(h->d_x + p0, x + p0, sizeof(double) * np, cudaMemcpyHostToDevice, h->stream));
+    BA_CUDA(cudaMemcpyAsync(h->d_x + c0, x + c0, sizeof(double) * 9 * (size_t)h->ncams, cudaMemcpyHostToDevice, h->stream));
+    return BA_OK;
+  }
   BA_CUDA(cudaMemcpyAsync(h->d_x, x, sizeof(double) * (size_t)h->nvar(), cudaMemcpyHostToDevice, h->stream));
   return BA_OK;
 }
@@ -34,6 +41,9 @@ int refresh_cams(ba_handle* h, const double* x_dev) {
   return BA_OK;
 }
 
+}  // namespace
+
+namespace ba {
 int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, const int64_t* pnt,
                 const double* pt2d, int device, int rank, int nranks, ba_handle** out) {
   if (!out) return BA_ERR_ARG;
@@ -94,10 +104,10 @@ int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, 
   BA_CUDA(cudaStreamSynchronize(h->stream));
   return BA_OK;
 }
-
-}  // namespace
+}  // namespace ba
 
 namespace {
+using ba::create_impl;
 // FP64 FMA throughput probe: 8 independent chains per thread, operands from kernel arguments so that
 // nothing folds at compile time
 __global__ void __launch_bounds__(256) k_fp64_fma(double* out, int iters, double a, double b) {
@@ -113,9 +123,57 @@ __global__ void __launch_bounds__(256) k_fp64_fma(double* out, int iters, double
   for (int j = 0; j < 8; ++j) s += x[j];
   out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
 }
+// FP64 tensor-core probe: 8 independent m8n8k4 accumulators per warp, operands in registers
+__global__ void __launch_bounds__(256) k_fp64_mma(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c[j][0] = c[j][1] = (double)(threadIdx.x + j) * 1e-3;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(c[j][0]), "+d"(c[j][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
 }  // namespace
 
 extern "C" {
+
+int ba_measure_fp64_mma_peak(int device, double* tflops) {
+  if (!tflops) return BA_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return BA_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BA_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 4, iters = 1 << 14;
+  double* out = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(reinterpret_cast<void**>(&out), sizeof(double) * 256 * (size_t)blocks) != cudaSuccess) return BA_ERR_CUDA;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 0.f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, 0);
+    k_fp64_mma<<<blocks, 256>>>(out, iters, 1e-3, 1e-3);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+  }
+  const cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (err != cudaSuccess || !(best > 0.f)) return BA_ERR_CUDA;
+  // 8 MMAs of 8 x 8 x 4 (512 flops) per warp and iteration
+  *tflops = 512.0 * 8.0 * iters * 8.0 * blocks / (best * 1e-3) / 1e12;
+  return BA_OK;
+}
 
 int ba_measure_fp64_peak(int device, double* tflops) {
   if (!tflops) return BA_ERR_ARG;
@@ -178,6 +236,11 @@ int ba_create_sharded(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t*
 
 int ba_destroy(ba_handle* h) {
   if (!h) return BA_OK;
+  if (h->group) {
+    ba::group_release(h);
+    delete h;
+    return BA_OK;
+  }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   ba::lm_release(h);
@@ -203,6 +266,7 @@ int ba_shard_range(const ba_handle* h, int64_t* obs0, int64_t* obs1, int64_t* pn
 
 int ba_set_stream(ba_handle* h, void* s) {
   if (!h) return BA_ERR_ARG;
+  if (h->group) return fail(h, BA_ERR_ARG, "not available on a multi-GPU handle (ba_create_multi)");
   BA_CUDA(cudaSetDevice(h->device));
   if (h->stream) BA_CUDA(cudaStreamSynchronize(h->stream));
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -223,6 +287,7 @@ int ba_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? BA_OK : BA
 
 int ba_sync(ba_handle* h) {
   if (!h) return BA_ERR_ARG;
+  if (h->group) return ba::group_apply(h, [](ba_handle* s) { return ba_sync(s); });
   BA_CUDA(cudaSetDevice(h->device));
   BA_CUDA(cudaStreamSynchronize(h->stream));
   return BA_OK;
@@ -230,6 +295,7 @@ int ba_sync(ba_handle* h) {
 
 int ba_set_coarse_clusters(ba_handle* h, int n) {
   if (!h || n < 0) return BA_ERR_ARG;
+  if (h->group) return ba::group_apply(h, [n](ba_handle* s) { return ba_set_coarse_clusters(s, n); });
   if (n != h->coarse_clusters) {
     BA_CUDA(cudaSetDevice(h->device));
     if (h->stream) BA_CUDA(cudaStreamSynchronize(h->stream));
@@ -241,6 +307,7 @@ int ba_set_coarse_clusters(ba_handle* h, int n) {
 
 int ba_set_deflation(ba_handle* h, int k) {
   if (!h || k < 0 || k > 32) return BA_ERR_ARG;
+  if (h->group) return ba::group_apply(h, [k](ba_handle* s) { return ba_set_deflation(s, k); });
   if (k != h->deflate) {
     BA_CUDA(cudaSetDevice(h->device));
     if (h->stream) BA_CUDA(cudaStreamSynchronize(h->stream));
@@ -252,6 +319,10 @@ int ba_set_deflation(ba_handle* h, int k) {
 
 int ba_set_solver(ba_handle* h, int solver) {
   if (!h || solver < BA_SOLVER_AUTO || solver > BA_SOLVER_EXACT) return fail(h, BA_ERR_ARG, "unknown solver");
+  if (h->group) {
+    h->solver = solver;
+    return ba::group_apply(h, [solver](ba_handle* s) { return ba_set_solver(s, solver); });
+  }
   if (solver != h->solver) {
     BA_CUDA(cudaSetDevice(h->device));
     if (h->stream) BA_CUDA(cudaStreamSynchronize(h->stream));
@@ -263,6 +334,7 @@ int ba_set_solver(ba_handle* h, int solver) {
 
 int ba_last_solve_info(const ba_handle* h, int32_t* solver, int32_t* converged, double* rel, int32_t* iters) {
   if (!h) return BA_ERR_ARG;
+  h = ba::group_first(h);
   if (solver) *solver = h->lm.last_solver;
   if (converged) *converged = h->lm.last_converged;
   if (rel) *rel = h->lm.last_rel;
@@ -272,6 +344,7 @@ int ba_last_solve_info(const ba_handle* h, int32_t* solver, int32_t* converged, 
 
 int ba_set_profiling(ba_handle* h, int on) {
   if (!h) return BA_ERR_ARG;
+  if (h->group) return fail(h, BA_ERR_ARG, "not available on a multi-GPU handle (ba_create_multi)");
   h->profile = on != 0;
   return BA_OK;
 }
@@ -291,6 +364,7 @@ int ba_last_eval_ms(ba_handle* h, float* ms) {
 // ---- device-pointer variants ------------------------------------------------------------------
 int ba_residual_dev(ba_handle* h, const double* x, double* cx) {
   if (!h || !x || !cx) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return fail(h, BA_ERR_ARG, "device-pointer calls are per GPU: not available on a multi-GPU handle");
   BA_CUDA(cudaSetDevice(h->device));
   int rc = refresh_cams(h, x);
   if (rc) return rc;
@@ -301,6 +375,7 @@ int ba_residual_dev(ba_handle* h, const double* x, double* cx) {
 
 int ba_jac_coord_dev(ba_handle* h, const double* x, double* vals) {
   if (!h || !x || !vals) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return fail(h, BA_ERR_ARG, "device-pointer calls are per GPU: not available on a multi-GPU handle");
   BA_CUDA(cudaSetDevice(h->device));
   int rc = refresh_cams(h, x);
   if (rc) return rc;
@@ -311,6 +386,7 @@ int ba_jac_coord_dev(ba_handle* h, const double* x, double* vals) {
 
 int ba_residual_jac_dev(ba_handle* h, const double* x, double* cx, double* vals) {
   if (!h || !x || !cx || !vals) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return fail(h, BA_ERR_ARG, "device-pointer calls are per GPU: not available on a multi-GPU handle");
   BA_CUDA(cudaSetDevice(h->device));
   int rc = refresh_cams(h, x);
   if (rc) return rc;
@@ -321,6 +397,7 @@ int ba_residual_jac_dev(ba_handle* h, const double* x, double* cx, double* vals)
 
 int ba_jac_structure_dev(ba_handle* h, int64_t* rows, int64_t* cols) {
   if (!h || !rows || !cols) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return fail(h, BA_ERR_ARG, "device-pointer calls are per GPU: not available on a multi-GPU handle");
   BA_CUDA(cudaSetDevice(h->device));
   ba::launch_jac_structure(h, rows, cols, h->stream);
   BA_CUDA(cudaGetLastError());
@@ -329,6 +406,7 @@ int ba_jac_structure_dev(ba_handle* h, int64_t* rows, int64_t* cols) {
 
 int ba_jprod_dev(ba_handle* h, const double* x, const double* v, double* Jv) {
   if (!h || !x || !v || !Jv) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return fail(h, BA_ERR_ARG, "device-pointer calls are per GPU: not available on a multi-GPU handle");
   BA_CUDA(cudaSetDevice(h->device));
   int rc = refresh_cams(h, x);
   if (rc) return rc;
@@ -339,6 +417,7 @@ int ba_jprod_dev(ba_handle* h, const double* x, const double* v, double* Jv) {
 
 int ba_jtprod_dev(ba_handle* h, const double* x, const double* v, double* Jtv) {
   if (!h || !x || !v || !Jtv) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return fail(h, BA_ERR_ARG, "device-pointer calls are per GPU: not available on a multi-GPU handle");
   BA_CUDA(cudaSetDevice(h->device));
   int rc = refresh_cams(h, x);
   if (rc) return rc;
@@ -354,53 +433,50 @@ int ba_jtprod_dev(ba_handle* h, const double* x, const double* v, double* Jtv) {
 // ---- host-pointer calls (the ones Julia's ccall binds) ----------------------------------------
 int ba_residual(ba_handle* h, const double* x, double* cx) {
   if (!h || !x || !cx) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return ba::group_residual(h, x, cx, nullptr);
   BA_CUDA(cudaSetDevice(h->device));
   int rc;
   if ((rc = stage_x(h, x))) return rc;
   if ((rc = dev_alloc(h, &h->d_cx, 2 * (size_t)h->nobs_l()))) return rc;
   if ((rc = ba_residual_dev(h, h->d_x, h->d_cx))) return rc;
-  BA_CUDA(cudaMemcpyAsync(cx, h->d_cx, sizeof(double) * 2 * (size_t)h->nobs_l(), cudaMemcpyDeviceToHost, h->stream));
-  BA_CUDA(cudaStreamSynchronize(h->stream));
-  return BA_OK;
+  return ba::copy_to_host(h, cx, h->d_cx, sizeof(double) * 2 * (size_t)h->nobs_l());
 }
 
 int ba_jac_coord(ba_handle* h, const double* x, double* vals) {
   if (!h || !x || !vals) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return ba::group_residual(h, x, nullptr, vals);
   BA_CUDA(cudaSetDevice(h->device));
   int rc;
   if ((rc = stage_x(h, x))) return rc;
   if ((rc = dev_alloc(h, &h->d_vals, 24 * (size_t)h->nobs_l()))) return rc;
   if ((rc = ba_jac_coord_dev(h, h->d_x, h->d_vals))) return rc;
-  BA_CUDA(cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * 24 * (size_t)h->nobs_l(), cudaMemcpyDeviceToHost, h->stream));
-  BA_CUDA(cudaStreamSynchronize(h->stream));
-  return BA_OK;
+  return ba::copy_to_host(h, vals, h->d_vals, sizeof(double) * 24 * (size_t)h->nobs_l());
 }
 
 int ba_residual_jac(ba_handle* h, const double* x, double* cx, double* vals) {
   if (!h || !x || !cx || !vals) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return ba::group_residual(h, x, cx, vals);
   BA_CUDA(cudaSetDevice(h->device));
   int rc;
   if ((rc = stage_x(h, x))) return rc;
   if ((rc = dev_alloc(h, &h->d_cx, 2 * (size_t)h->nobs_l()))) return rc;
   if ((rc = dev_alloc(h, &h->d_vals, 24 * (size_t)h->nobs_l()))) return rc;
   if ((rc = ba_residual_jac_dev(h, h->d_x, h->d_cx, h->d_vals))) return rc;
-  BA_CUDA(cudaMemcpyAsync(cx, h->d_cx, sizeof(double) * 2 * (size_t)h->nobs_l(), cudaMemcpyDeviceToHost, h->stream));
-  BA_CUDA(cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * 24 * (size_t)h->nobs_l(), cudaMemcpyDeviceToHost, h->stream));
-  BA_CUDA(cudaStreamSynchronize(h->stream));
-  return BA_OK;
+  if ((rc = ba::copy_to_host(h, cx, h->d_cx, sizeof(double) * 2 * (size_t)h->nobs_l()))) return rc;
+  return ba::copy_to_host(h, vals, h->d_vals, sizeof(double) * 24 * (size_t)h->nobs_l());
 }
 
 int ba_jac_structure(ba_handle* h, int64_t* rows, int64_t* cols) {
   if (!h || !rows || !cols) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return ba::group_jac_structure(h, rows, cols);
   BA_CUDA(cudaSetDevice(h->device));
   int rc;
   const size_t n = 24 * (size_t)h->nobs_l();
   if ((rc = dev_alloc(h, &h->d_rows, n))) return rc;
   if ((rc = dev_alloc(h, &h->d_cols, n))) return rc;
   if ((rc = ba_jac_structure_dev(h, h->d_rows, h->d_cols))) return rc;
-  BA_CUDA(cudaMemcpyAsync(rows, h->d_rows, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, h->stream));
-  BA_CUDA(cudaMemcpyAsync(cols, h->d_cols, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, h->stream));
-  BA_CUDA(cudaStreamSynchronize(h->stream));
+  if ((rc = ba::copy_to_host(h, rows, h->d_rows, sizeof(int64_t) * n))) return rc;
+  if ((rc = ba::copy_to_host(h, cols, h->d_cols, sizeof(int64_t) * n))) return rc;
   // the structure is needed once per solve (src/lm.jl:53): do not keep 2 x 192 B/obs resident
   cudaFree(h->d_rows); cudaFree(h->d_cols);
   h->d_rows = h->d_cols = nullptr;
@@ -409,6 +485,7 @@ int ba_jac_structure(ba_handle* h, int64_t* rows, int64_t* cols) {
 
 int ba_jprod(ba_handle* h, const double* x, const double* v, double* Jv) {
   if (!h || !x || !v || !Jv) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return ba::group_jprod(h, x, v, Jv);
   BA_CUDA(cudaSetDevice(h->device));
   int rc;
   if ((rc = stage_x(h, x))) return rc;
@@ -423,6 +500,7 @@ int ba_jprod(ba_handle* h, const double* x, const double* v, double* Jv) {
 
 int ba_jtprod(ba_handle* h, const double* x, const double* v, double* Jtv) {
   if (!h || !x || !v || !Jtv) return fail(h, BA_ERR_ARG, "null argument");
+  if (h->group) return ba::group_jtprod(h, x, v, Jtv);
   BA_CUDA(cudaSetDevice(h->device));
   int rc;
   if ((rc = stage_x(h, x))) return rc;

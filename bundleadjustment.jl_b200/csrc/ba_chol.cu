@@ -25,11 +25,12 @@ namespace ba {
 namespace {
 
 constexpr int CT = CHOL_TILE;     // 128
+constexpr int TM = 64;            // rows of a CTA tile of the two products (columns: CT)
 constexpr int KC = 16;            // k per pipeline stage
 constexpr int LDSM = KC + 4;      // padded row stride (doubles): fragment loads are bank-conflict free
 constexpr int STAGES = 3;
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM = STAGES * 2 * CT * LDSM * (int)sizeof(double);  // 122880 B
+constexpr int GEMM_SMEM = STAGES * (TM + CT) * LDSM * (int)sizeof(double);  // 92160 B: two CTAs per SM
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -46,25 +47,32 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// acc = A (128 x 128, rows lda apart) * B' (B: 128 x 128, rows ldb apart); accumulator fragment layout of
-// m8n8k4: warp (wm, wn) of 2 x 4 owns rows wm*64.., columns wn*32..; tile (mi, ni): lane holds row 8 mi + lane/4,
-// columns 8 ni + 2 (lane%4) + {0, 1}.
+// acc = A (64 x 128, rows lda apart) * B' (B: 128 x 128, rows ldb apart); accumulator fragment layout of
+// m8n8k4: warp (wm, wn) of 2 x 4 owns rows wm*32.., columns wn*32..; tile (mi, ni): lane holds row 8 mi + lane/4,
+// columns 8 ni + 2 (lane%4) + {0, 1}.  Two such CTAs share an SM (8 + 8 warps): while one waits (prologue loads,
+// epilogue, the fixed issue distance of dependent DMMAs) the other keeps the FP64 tensor pipe busy, and the
+// half-height tiles halve the tail of the last wave.
 __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t lda, const double* __restrict__ B,
-                                         int64_t ldb, double (&acc)[8][4][2], double* sm) {
+                                         int64_t ldb, double (&acc)[4][4][2], double* sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int mi = 0; mi < 8; ++mi)
+  for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
   auto load_stage = [&](int stage, int kc) {
-    double* As = sm + stage * (2 * CT * LDSM);
-    double* Bs = As + CT * LDSM;
+    double* As = sm + stage * ((TM + CT) * LDSM);
+    double* Bs = As + TM * LDSM;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = tid + i * GEMM_THREADS;  // 1024 16-byte pieces per operand
+    for (int i = 0; i < 2; ++i) {
+      const int c = tid + i * GEMM_THREADS;  // 512 16-byte pieces of A
       const int row = c >> 3, part = c & 7;
       cp_async16(As + row * LDSM + part * 2, A + (int64_t)row * lda + kc * KC + part * 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + i * GEMM_THREADS;  // 1024 pieces of B
+      const int row = c >> 3, part = c & 7;
       cp_async16(Bs + row * LDSM + part * 2, B + (int64_t)row * ldb + kc * KC + part * 2);
     }
   };
@@ -79,17 +87,17 @@ __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t l
     __syncthreads();  // stage kc has landed for everybody; everybody is done with stage kc - 1
     if (kc + STAGES - 1 < NK) load_stage((kc + STAGES - 1) % STAGES, kc + STAGES - 1);
     cp_async_commit();
-    const double* As = sm + (kc % STAGES) * (2 * CT * LDSM) + (wm * 64 + g) * LDSM + t;
-    const double* Bs = sm + (kc % STAGES) * (2 * CT * LDSM) + CT * LDSM + (wn * 32 + g) * LDSM + t;
+    const double* As = sm + (kc % STAGES) * ((TM + CT) * LDSM) + (wm * 32 + g) * LDSM + t;
+    const double* Bs = sm + (kc % STAGES) * ((TM + CT) * LDSM) + TM * LDSM + (wn * 32 + g) * LDSM + t;
 #pragma unroll
     for (int ks = 0; ks < KC / 4; ++ks) {
-      double a[8], b[4];
+      double a[4], b[4];
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi) a[mi] = As[mi * 8 * LDSM + ks * 4];
+      for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * LDSM + ks * 4];
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * LDSM + ks * 4];
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi)
+      for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
@@ -98,21 +106,21 @@ __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t l
   __syncthreads();
 }
 
-// trailing update: tile (i, j) = (j0 + blockIdx.y + blockIdx.x, j0 + blockIdx.y), i < nb: A_ij -= P_i P_j'
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// trailing update, half tiles: blockIdx.x = 2 (i - j) + half, blockIdx.y = j - j0; A_ij[half] -= P_i[half] P_j'
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb) {
   extern __shared__ __align__(16) double sm[];
-  const int j = j0 + blockIdx.y, i = j + blockIdx.x;
+  const int j = j0 + blockIdx.y, i = j + (blockIdx.x >> 1), half = blockIdx.x & 1;
   if (i >= nb) return;
-  const double* Pi = A + (int64_t)i * CT * ld + (int64_t)k * CT;
+  const double* Pi = A + ((int64_t)i * CT + half * TM) * ld + (int64_t)k * CT;
   const double* Pj = A + (int64_t)j * CT * ld + (int64_t)k * CT;
-  double acc[8][4][2];
+  double acc[4][4][2];
   tile_abt(Pi, ld, Pj, ld, acc, sm);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
-  double* C = A + ((int64_t)i * CT + wm * 64 + g) * ld + (int64_t)j * CT + wn * 32 + 2 * t;
+  double* C = A + ((int64_t)i * CT + half * TM + wm * 32 + g) * ld + (int64_t)j * CT + wn * 32 + 2 * t;
 #pragma unroll
-  for (int mi = 0; mi < 8; ++mi)
+  for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) {
       double2* p = reinterpret_cast<double2*>(C + (int64_t)mi * 8 * ld + ni * 8);
@@ -123,36 +131,83 @@ k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb) {
     }
 }
 
-// panel solve: P_i <- P_i Linv_kk' for the row tiles i = k + 1 + blockIdx.x
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// panel solve: P_i[half] <- P_i[half] Linv_kk' for the row tiles i = k + 1 + blockIdx.x / 2
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_chol_trsm(double* __restrict__ A, int64_t ld, int k, const double* __restrict__ Dinv) {
   extern __shared__ __align__(16) double sm[];
-  const int i = k + 1 + blockIdx.x;
-  double* Pi = A + (int64_t)i * CT * ld + (int64_t)k * CT;
-  double acc[8][4][2];
-  tile_abt(Pi, ld, Dinv + (int64_t)k * CT * CT, CT, acc, sm);  // (every read of P_i is complete on return)
+  const int i = k + 1 + (blockIdx.x >> 1), half = blockIdx.x & 1;
+  double* Pi = A + ((int64_t)i * CT + half * TM) * ld + (int64_t)k * CT;
+  double acc[4][4][2];
+  tile_abt(Pi, ld, Dinv + (int64_t)k * CT * CT, CT, acc, sm);  // (every read of these rows is complete on return)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
-  double* C = Pi + (int64_t)(wm * 64 + g) * ld + wn * 32 + 2 * t;
+  double* C = Pi + (int64_t)(wm * 32 + g) * ld + wn * 32 + 2 * t;
 #pragma unroll
-  for (int mi = 0; mi < 8; ++mi)
+  for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni)
       *reinterpret_cast<double2*>(C + (int64_t)mi * 8 * ld + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
 }
 
 // ---- diagonal block -------------------------------------------------------------------------------------
+// One CTA factorises the 128 x 128 diagonal block in shared memory and inverts the factor.  It sits on the critical
+// path of every panel step, so it is organised for latency (ncu: the first version spent 45 % of its time in the
+// one-warp 16 x 16 steps and 30 % in the scalar loops of the inversion):
+//   * 16-column sub-panels; the 16 x 16 diagonal block is factorised by ONE warp in registers (rows in lanes,
+//     columns by shuffles, rsqrt instead of sqrt + division on the dependent chain);
+//   * the rows below are solved against it by forward substitution, one thread per row (independent rows);
+//   * the trailing update uses 4 x 4 register patches;
+//   * after the loop the eight 16 x 16 diagonal factors are inverted by eight warps AT ONCE, and the inverse of the
+//     whole factor is assembled by recursive doubling ([L11 0; L21 L22]^-1 = [X11 0; -X22 L21 X11, X22]: three
+//     levels of two small products, again in 4 x 4 register patches).
 constexpr int PO_THREADS = 512;
 constexpr int PO_LD = CT + 1;  // padded row stride in shared memory
 constexpr int PO_SB = 16;      // sub-panel width
-constexpr int PO_SMEM = (CT * PO_LD + CT) * (int)sizeof(double);
+constexpr int PO_SMEM = (CT * PO_LD + CT + 64 * 65) * (int)sizeof(double);
+
+// c (m x m, row stride ldc) = sign * a (m x m, lda) * b (m x m, ldb), all in shared memory; the CTA's threads
+// enumerate (pair, 4 x 4 patch) items: item -> pair pi = item / ((m/4)^2); the three operands of a pair sit at
+// a0 + pi * astep etc.
+__device__ __forceinline__ void po_gemm(int m, int npair, const double* a0, int lda, int astep, const double* b0, int ldb,
+                                        int bstep, double* c0, int ldc, int cstep, double sign) {
+  const int pm = m >> 2, per = pm * pm;
+  for (int item = threadIdx.x; item < npair * per; item += PO_THREADS) {
+    const int pi = item / per, rem = item - pi * per, pr = rem / pm, pc = rem - pr * pm;
+    const double* a = a0 + pi * astep + 4 * pr * lda;
+    const double* b = b0 + pi * bstep + 4 * pc;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < m; ++q) {
+      double va[4], vb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        va[i] = a[i * lda + q];
+        vb[i] = b[q * ldb + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += va[i] * vb[j];
+    }
+    double* c = c0 + pi * cstep + 4 * pr * ldc + 4 * pc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[i * ldc + j] = sign * acc[i][j];
+  }
+}
 
 // A_kk (lower) <- L_kk, Dinv[k] <- L_kk^-1.  info: first non-positive pivot (1-based global index), else untouched.
 __global__ void __launch_bounds__(PO_THREADS, 1)
 k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Dinv, int* __restrict__ info) {
   extern __shared__ __align__(16) double smp[];
-  double* a = smp;                  // 128 x 129
-  double* col = smp + CT * PO_LD;   // 128 scratch
+  double* a = smp;                       // 128 x 129: the block, then its inverse
+  double* rinv = smp + CT * PO_LD;       // 128: reciprocals of the diagonal of L
+  double* tmp = rinv + CT;               // 64 x 65 scratch of the doubling levels
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* Akk = A + (int64_t)k * CT * ld + (int64_t)k * CT;
   for (int e = tid; e < CT * CT; e += PO_THREADS) {
@@ -161,54 +216,84 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
   }
   __syncthreads();
   for (int j0 = 0; j0 < CT; j0 += PO_SB) {
-    // (a) 16 x 16 diagonal sub-block, one warp, lane = row
+    // (a) 16 x 16 diagonal sub-block: Cholesky by warp 0, row r in lane r (lanes 16..31 mirror)
     if (warp == 0) {
-      const int r = j0 + (lane & 15);
+      const int r = lane & 15;
+      double row[PO_SB];
+#pragma unroll
+      for (int c = 0; c < PO_SB; ++c) row[c] = a[(j0 + r) * PO_LD + j0 + c];  // zeros above the diagonal
+#pragma unroll
       for (int j = 0; j < PO_SB; ++j) {
-        const double djj = a[(j0 + j) * PO_LD + j0 + j];
+        const double djj = __shfl_sync(0xffffffffu, row[j], j);
         if (!(djj > 0.0) && lane == 0) atomicCAS(info, 0, k * CT + j0 + j + 1);
-        const double d = sqrt(djj);
-        __syncwarp();
-        if (lane < 16) {
-          if (lane == j) a[r * PO_LD + j0 + j] = d;
-          else if (lane > j) a[r * PO_LD + j0 + j] /= d;
+        // no division on this dependent chain: l_jj = d_jj * rsqrt(d_jj), l_rj = a_rj * rsqrt(d_jj)
+        const double rs = rsqrt(djj);
+        const double l = row[j] * rs;  // (rows above j hold zeros in this column)
+        row[j] = l;
+        if (lane == j) rinv[j0 + j] = rs;
+#pragma unroll
+        for (int c = j + 1; c < PO_SB; ++c) {
+          const double lc = __shfl_sync(0xffffffffu, l, c);
+          if (c <= r) row[c] -= l * lc;
         }
-        __syncwarp();
-        if (lane < 16 && lane > j) {
-          const double lrj = a[r * PO_LD + j0 + j];
-          for (int c = j + 1; c <= lane; ++c) a[r * PO_LD + j0 + c] -= lrj * a[(j0 + c) * PO_LD + j0 + j];
-        }
-        __syncwarp();
+      }
+      if (lane < PO_SB) {
+#pragma unroll
+        for (int c = 0; c < PO_SB; ++c)
+          if (c <= r) a[(j0 + r) * PO_LD + j0 + c] = row[c];
       }
     }
     __syncthreads();
-    // (b) rows below: forward substitution against the 16 x 16 factor, one thread per row
+    // (b) rows below: x L16' = row by forward substitution, one thread per row
     const int nbelow = CT - j0 - PO_SB;
     if (tid < nbelow) {
-      double* row = a + (j0 + PO_SB + tid) * PO_LD + j0;
+      double* rowp = a + (j0 + PO_SB + tid) * PO_LD + j0;
       double x[PO_SB];
 #pragma unroll
       for (int j = 0; j < PO_SB; ++j) {
-        double s = row[j];
+        double sacc = rowp[j];
 #pragma unroll
-        for (int q = 0; q < j; ++q) s -= x[q] * a[(j0 + j) * PO_LD + j0 + q];
-        x[j] = s / a[(j0 + j) * PO_LD + j0 + j];
+        for (int q = 0; q < j; ++q) sacc -= x[q] * a[(j0 + j) * PO_LD + j0 + q];
+        x[j] = sacc * rinv[j0 + j];
       }
 #pragma unroll
-      for (int j = 0; j < PO_SB; ++j) row[j] = x[j];
+      for (int j = 0; j < PO_SB; ++j) rowp[j] = x[j];
     }
     __syncthreads();
-    // (c) trailing update of the lower triangle: a[r][c] -= sum_q a[r][j0+q] a[c][j0+q]
-    const int base = j0 + PO_SB;
-    for (int e = tid; e < nbelow * nbelow; e += PO_THREADS) {
-      const int rr = e / nbelow, cc = e - rr * nbelow;
-      if (cc > rr) continue;
-      const double* pr = a + (base + rr) * PO_LD + j0;
-      const double* pc = a + (base + cc) * PO_LD + j0;
-      double s = 0.0;
+    // (c) trailing update of the lower triangle in 4 x 4 patches: a[r][c] -= sum_q a[r][j0+q] a[c][j0+q]
+    const int np = nbelow >> 2, tp = np * (np + 1) / 2;
+    if (tid < tp) {
+      int pr = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+      while (pr * (pr + 1) / 2 > tid) --pr;
+      while ((pr + 1) * (pr + 2) / 2 <= tid) ++pr;
+      const int pc = tid - pr * (pr + 1) / 2;
+      const int base = j0 + PO_SB;
+      const double* ar = a + (base + 4 * pr) * PO_LD + j0;
+      const double* ac = a + (base + 4 * pc) * PO_LD + j0;
+      double acc[4][4];
 #pragma unroll
-      for (int q = 0; q < PO_SB; ++q) s += pr[q] * pc[q];
-      a[(base + rr) * PO_LD + base + cc] -= s;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 4
+      for (int q = 0; q < PO_SB; ++q) {
+        double vr[4], vc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vr[i] = ar[i * PO_LD + q];
+          vc[i] = ac[i * PO_LD + q];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += vr[i] * vc[j];
+      }
+      double* out = a + (base + 4 * pr) * PO_LD + base + 4 * pc;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (pc < pr || j <= i) out[i * PO_LD + j] -= acc[i][j];
     }
     __syncthreads();
   }
@@ -216,24 +301,41 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
     const int r = e >> 7, c = e & 127;
     if (c <= r) Akk[(int64_t)r * ld + c] = a[r * PO_LD + c];
   }
-  __syncthreads();
-  // in-place inverse of the lower-triangular factor, last column first:
-  //   x_jj = 1 / l_jj;  x[j+1:, j] = -x_jj * Xinv[j+1:, j+1:] l[j+1:, j]
-  for (int j = CT - 1; j >= 0; --j) {
-    const double xjj = 1.0 / a[j * PO_LD + j];
-    if (tid > j && tid < CT) col[tid] = a[tid * PO_LD + j];
-    __syncthreads();
-    // row i in (j, 128): sum_{q = j+1..i} X[i][q] col[q]; 4 threads per row
-    {
-      const int i = j + 1 + (tid >> 2), part = tid & 3;
-      double s = 0.0;
-      if (i < CT)
-        for (int q = j + 1 + part; q <= i; q += 4) s += a[i * PO_LD + q] * col[q];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (i < CT && part == 0) a[i * PO_LD + j] = -xjj * s;
+  __syncthreads();  // the factor has been read out before its storage is reused
+  // inverse of the factor, in place.  Diagonal 16 x 16 blocks: warp w < 8 inverts block w; lane c solves L x = e_c
+  // (column c of X); L[i][q] arrives from lane i's registers.
+  if (warp < CT / PO_SB) {
+    const int b0 = warp * PO_SB, r = lane & 15;
+    double row[PO_SB], x[PO_SB];
+#pragma unroll
+    for (int c = 0; c < PO_SB; ++c) row[c] = a[(b0 + r) * PO_LD + b0 + c];
+    const double ri_own = rinv[b0 + r];
+#pragma unroll
+    for (int i = 0; i < PO_SB; ++i) {
+      double sacc = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < i; ++q) {
+        const double liq = __shfl_sync(0xffffffffu, row[q], i);
+        sacc -= liq * x[q];  // x[q] == 0 for q < r
+      }
+      const double ri = __shfl_sync(0xffffffffu, ri_own, i);
+      x[i] = (i >= r) ? sacc * ri : 0.0;
     }
-    if (tid == 0) a[j * PO_LD + j] = xjj;
+    __syncwarp();  // every lane has read its row of L before the block is overwritten
+    if (lane < PO_SB) {
+#pragma unroll
+      for (int i = 0; i < PO_SB; ++i) a[(b0 + i) * PO_LD + b0 + r] = x[i];  // X[i][c = r] (zeros above the diagonal)
+    }
+  }
+  __syncthreads();
+  // X21 = -X22 (L21 X11) for block sizes 16, 32, 64
+  for (int m = PO_SB; m < CT; m <<= 1) {
+    const int npair = CT / (2 * m), step = 2 * m * PO_LD + 2 * m;
+    // T = L21 X11
+    po_gemm(m, npair, a + m * PO_LD, PO_LD, step, a, PO_LD, step, tmp, m + 1, m * (m + 1), 1.0);
+    __syncthreads();
+    // X21 = -X22 T
+    po_gemm(m, npair, a + m * PO_LD + m, PO_LD, step, tmp, m + 1, m * (m + 1), a + m * PO_LD, PO_LD, step, -1.0);
     __syncthreads();
   }
   double* D = Dinv + (int64_t)k * CT * CT;
@@ -244,73 +346,102 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
 }
 
 // ---- substitution sweeps ----------------------------------------------------------------------------------
-constexpr int SV_THREADS = 256;
+// 2 cn/128 dependent steps, each a tiny kernel: organised for latency (every global load of a step is issued up
+// front -- the tile loads do not depend on the small solve with the diagonal block), launched as one CUDA graph.
+constexpr int SV_THREADS = 512;
 
 // step k of L y = b: every CTA forms y_k = Linv_kk w_k; CTA 0 stores it, CTA c > 0 updates row tile i = k + c:
-// w_i -= L_ik y_k
+// w_i -= L_ik y_k.  Warp w owns rows 8 w .. 8 w + 7; a lane holds columns 2 lane, 2 lane + 1, 64 + 2 lane, 65 + 2 lane.
 __global__ void __launch_bounds__(SV_THREADS)
 k_chol_fwd(const double* __restrict__ L, int64_t ld, const double* __restrict__ Dinv, double* __restrict__ w,
            double* __restrict__ y, int k) {
-  __shared__ double wk[CT], yk[CT];
+  __shared__ double yk[CT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < CT) wk[tid] = w[(int64_t)k * CT + tid];
-  __syncthreads();
-  const double* D = Dinv + (int64_t)k * CT * CT;
-  for (int r = warp; r < CT; r += SV_THREADS / 32) {  // warp per row, lanes across the row
-    double s = 0.0;
+  const int i = k + blockIdx.x;
+  const double* D = Dinv + (int64_t)k * CT * CT + (int64_t)(warp * 8) * CT + 2 * lane;
+  const double* T = L + ((int64_t)i * CT + warp * 8) * ld + (int64_t)k * CT + 2 * lane;
+  double2 d0[8], d1[8], t0[8], t1[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) s += D[r * CT + lane + 32 * u] * wk[lane + 32 * u];
+  for (int r = 0; r < 8; ++r) {
+    d0[r] = *reinterpret_cast<const double2*>(D + r * CT);
+    d1[r] = *reinterpret_cast<const double2*>(D + r * CT + 64);
+  }
+  if (blockIdx.x > 0) {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) yk[r] = s;
+    for (int r = 0; r < 8; ++r) {
+      t0[r] = *reinterpret_cast<const double2*>(T + (int64_t)r * ld);
+      t1[r] = *reinterpret_cast<const double2*>(T + (int64_t)r * ld + 64);
+    }
+  }
+  const double2 w0 = *reinterpret_cast<const double2*>(w + (int64_t)k * CT + 2 * lane);
+  const double2 w1 = *reinterpret_cast<const double2*>(w + (int64_t)k * CT + 64 + 2 * lane);
+  double s[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) s[r] = (d0[r].x * w0.x + d0[r].y * w0.y) + (d1[r].x * w1.x + d1[r].y * w1.y);
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) yk[warp * 8 + r] = s[r];
   }
   __syncthreads();
   if (blockIdx.x == 0) {
     if (tid < CT) y[(int64_t)k * CT + tid] = yk[tid];
     return;
   }
-  const int i = k + blockIdx.x;
-  const double* T = L + (int64_t)i * CT * ld + (int64_t)k * CT;
-  for (int r = warp; r < CT; r += SV_THREADS / 32) {
-    double s = 0.0;
+  const double y00 = yk[2 * lane], y01 = yk[2 * lane + 1], y10 = yk[64 + 2 * lane], y11 = yk[65 + 2 * lane];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) s += T[(int64_t)r * ld + lane + 32 * u] * yk[lane + 32 * u];
+  for (int r = 0; r < 8; ++r) s[r] = (t0[r].x * y00 + t0[r].y * y01) + (t1[r].x * y10 + t1[r].y * y11);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) w[(int64_t)i * CT + r] -= s;
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  if (lane == 0) {
+    double* wi = w + (int64_t)i * CT + warp * 8;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) wi[r] -= s[r];
   }
 }
 
 // step i of L' x = y (i descending): every CTA forms x_i = Linv_ii' y_i; CTA i stores it, CTA kk < i updates
-// y_kk -= L_{i,kk}' x_i
+// y_kk -= L_{i,kk}' x_i.  Thread (c, part): column c, rows 32 part .. 32 part + 31 (coalesced across c).
 __global__ void __launch_bounds__(SV_THREADS)
 k_chol_bwd(const double* __restrict__ L, int64_t ld, const double* __restrict__ Dinv, double* __restrict__ y,
            double* __restrict__ x, int i) {
-  __shared__ double yi[CT], xi[CT], half[CT];
+  __shared__ double yi[CT], xi[CT], part[3][CT];
   const int tid = threadIdx.x;
+  const int c = tid & (CT - 1), h = tid >> 7;  // column, quarter of the rows
+  const int kk = blockIdx.x;
+  const double* D = Dinv + (int64_t)i * CT * CT + (int64_t)(h * 32) * CT + c;
+  const double* T = L + ((int64_t)i * CT + h * 32) * ld + (int64_t)kk * CT + c;
+  double dv[32], tv[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) dv[r] = D[r * CT];
+  if (kk != i) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) tv[r] = T[(int64_t)r * ld];
+  }
   if (tid < CT) yi[tid] = y[(int64_t)i * CT + tid];
   __syncthreads();
-  const double* D = Dinv + (int64_t)i * CT * CT;
-  const int c = tid & (CT - 1), h = tid >> 7;  // column, half of the rows
-  {
-    double s = 0.0;
-    for (int r = h * 64; r < h * 64 + 64; ++r) s += D[r * CT + c] * yi[r];
-    if (h == 1) half[c] = s;
-    __syncthreads();
-    if (h == 0) xi[c] = s + half[c];
-    __syncthreads();
-  }
-  const int kk = blockIdx.x;
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) s += dv[r] * yi[h * 32 + r];
+  if (h > 0) part[h - 1][c] = s;
+  __syncthreads();
+  if (h == 0) xi[c] = ((s + part[0][c]) + part[1][c]) + part[2][c];
+  __syncthreads();
   if (kk == i) {
     if (tid < CT) x[(int64_t)i * CT + tid] = xi[tid];
     return;
   }
-  const double* T = L + (int64_t)i * CT * ld + (int64_t)kk * CT;
-  double s = 0.0;
-  for (int r = h * 64; r < h * 64 + 64; ++r) s += T[(int64_t)r * ld + c] * xi[r];
-  if (h == 1) half[c] = s;
+  s = 0.0;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) s += tv[r] * xi[h * 32 + r];
+  if (h > 0) part[h - 1][c] = s;
   __syncthreads();
-  if (h == 0) y[(int64_t)kk * CT + c] -= s + half[c];
+  if (h == 0) y[(int64_t)kk * CT + c] -= ((s + part[0][c]) + part[1][c]) + part[2][c];
 }
 
 }  // namespace
@@ -323,6 +454,7 @@ int chol_plan_init(ba_handle* h, chol_plan& P, int64_t cn) {
   BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_Dinv), sizeof(double) * (size_t)(nb * CT * CT)));
   BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_y), sizeof(double) * (size_t)cn));
   BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_w), sizeof(double) * (size_t)cn));
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_x), sizeof(double) * (size_t)cn));
   BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_info), sizeof(int)));
   BA_CUDA(cudaStreamCreateWithFlags(&P.side, cudaStreamNonBlocking));
   BA_CUDA(cudaEventCreateWithFlags(&P.ev_col, cudaEventDisableTiming));
@@ -341,6 +473,7 @@ void chol_plan_release(chol_plan& P) {
   cudaFree(P.d_Dinv32);
   cudaFree(P.d_y);
   cudaFree(P.d_w);
+  cudaFree(P.d_x);
   cudaFree(P.d_info);
   if (P.solve_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(P.solve_graph));
   if (P.side) cudaStreamDestroy(P.side);
@@ -356,24 +489,24 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
   static const bool no_lookahead = getenv("BAGPU_CHOL_NO_LOOKAHEAD") != nullptr;
   BA_CUDA(cudaMemsetAsync(P.d_info, 0, sizeof(int), s));
   k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, 0, P.d_Dinv, P.d_info);
-  if (nb > 1) k_chol_trsm<<<nb - 1, GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, 0, P.d_Dinv);
+  if (nb > 1) k_chol_trsm<<<2 * (nb - 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, 0, P.d_Dinv);
   for (int k = 0; k + 1 < nb; ++k) {
     // panel k is final in A[k+1:, k].  Column k+1 of the trailing matrix first ...
-    k_chol_syrk<<<dim3(nb - k - 1, 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 1, nb);
+    k_chol_syrk<<<dim3(2 * (nb - k - 1), 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 1, nb);
     const bool rest = k + 2 < nb;
     if (rest && !no_lookahead) {
       // ... then panel k+1 (potrf + trsm) on the side stream, under the rest of the update
       BA_CUDA(cudaEventRecord(P.ev_col, s));
       BA_CUDA(cudaStreamWaitEvent(P.side, P.ev_col, 0));
       k_chol_potrf<<<1, PO_THREADS, PO_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv, P.d_info);
-      k_chol_trsm<<<nb - k - 2, GEMM_THREADS, GEMM_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv);
+      k_chol_trsm<<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv);
       BA_CUDA(cudaEventRecord(P.ev_panel, P.side));
-      k_chol_syrk<<<dim3(nb - k - 2, nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb);
+      k_chol_syrk<<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb);
       BA_CUDA(cudaStreamWaitEvent(s, P.ev_panel, 0));
     } else {
-      if (rest) k_chol_syrk<<<dim3(nb - k - 2, nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb);
+      if (rest) k_chol_syrk<<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb);
       k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, k + 1, P.d_Dinv, P.d_info);
-      if (rest) k_chol_trsm<<<nb - k - 2, GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k + 1, P.d_Dinv);
+      if (rest) k_chol_trsm<<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k + 1, P.d_Dinv);
     }
   }
   BA_CUDA(cudaGetLastError());
@@ -391,9 +524,34 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
 int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, double* x, cudaStream_t s) {
   const int64_t cn = P.cn;
   const int nb = (int)(cn / CT);
+  static const bool no_graph = getenv("BAGPU_NO_GRAPH") != nullptr || getenv("BAGPU_DEBUG_SYNC") != nullptr;
+  // the sweeps always run from P.d_w into P.d_x: fixed pointers, so the 2 nb launches are captured once per
+  // (matrix, plan) and replayed as one graph launch
   BA_CUDA(cudaMemcpyAsync(P.d_w, b, sizeof(double) * (size_t)cn, cudaMemcpyDeviceToDevice, s));
-  for (int k = 0; k < nb; ++k) k_chol_fwd<<<nb - k, SV_THREADS, 0, s>>>(L, cn, P.d_Dinv, P.d_w, P.d_y, k);
-  for (int i = nb - 1; i >= 0; --i) k_chol_bwd<<<i + 1, SV_THREADS, 0, s>>>(L, cn, P.d_Dinv, P.d_y, x, i);
+  auto sweeps = [&]() {
+    for (int k = 0; k < nb; ++k) k_chol_fwd<<<nb - k, SV_THREADS, 0, s>>>(L, cn, P.d_Dinv, P.d_w, P.d_y, k);
+    for (int i = nb - 1; i >= 0; --i) k_chol_bwd<<<i + 1, SV_THREADS, 0, s>>>(L, cn, P.d_Dinv, P.d_y, P.d_x, i);
+  };
+  if (!no_graph && !P.graph_off && (!P.solve_graph || P.solve_graph_A != L)) {
+    if (P.solve_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(P.solve_graph));
+    P.solve_graph = nullptr;
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();  // e.g. the legacy default stream: plain launches from now on
+      P.graph_off = true;
+    } else {
+      sweeps();
+      BA_CUDA(cudaStreamEndCapture(s, &g));
+      cudaGraphExec_t ge = nullptr;
+      BA_CUDA(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      P.solve_graph = ge;
+      P.solve_graph_A = L;
+    }
+  }
+  if (P.solve_graph && !no_graph) BA_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(P.solve_graph), s));
+  else sweeps();
+  BA_CUDA(cudaMemcpyAsync(x, P.d_x, sizeof(double) * (size_t)cn, cudaMemcpyDeviceToDevice, s));
   BA_CUDA(cudaGetLastError());
   return BA_OK;
 }

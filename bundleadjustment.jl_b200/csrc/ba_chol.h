@@ -22,11 +22,13 @@ struct chol_plan {
   float* d_Dinv32 = nullptr; // the same in FP32 (mixed-precision factor)
   double* d_y = nullptr;     // cn: forward-substitution result
   double* d_w = nullptr;     // cn: right-hand side being consumed
+  double* d_x = nullptr;     // cn: solution of the sweeps
   int* d_info = nullptr;     // 0 ok, j + 1 = first non-positive pivot
   cudaStream_t side = nullptr;   // panel stream (look-ahead)
   cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_join = nullptr;
   void* solve_graph = nullptr;   // cudaGraphExec_t of the 2 cn/128 substitution steps
   const void* solve_graph_A = nullptr;
+  bool graph_off = false;        // capture not possible on the caller's stream
   bool attrs_set = false;
 };
 

@@ -85,12 +85,56 @@ int allreduce_sum_i64(ba_handle* h, long long* buf, size_t n) {
   return BA_OK;
 }
 
+// own mailbox block: [flags | pad | mail[2][9 ncams]]
+int p2p_alloc_block(ba_handle* h) {
+  ba_p2p_state& P = h->p2p;
+  if (h->nranks > 16) {
+    h->err = "peer-memory exchange supports at most 16 ranks";
+    return BA_ERR_ARG;
+  }
+  BA_CUDA(cudaSetDevice(h->device));
+  if (!P.block) {
+    const size_t bytes = P.mail_off + 2 * 9 * (size_t)h->ncams * sizeof(double);
+    BA_CUDA(cudaMalloc(&P.block, bytes));
+    BA_CUDA(cudaMemset(P.block, 0, bytes));
+  }
+  return BA_OK;
+}
+
+// blocks[r] = device pointer to rank r's block, usable from this rank's device (IPC-mapped, or a raw peer
+// pointer inside one process)
+int p2p_attach(ba_handle* h, void* const* blocks) {
+  ba_p2p_state& P = h->p2p;
+  BA_CUDA(cudaSetDevice(h->device));
+  P.nranks = h->nranks;
+  P.rank = h->rank;
+  std::vector<double*> mail((size_t)h->nranks);
+  std::vector<unsigned long long*> flags((size_t)h->nranks);
+  for (int r = 0; r < h->nranks; ++r) {
+    P.peer_block[r] = blocks[r];
+    flags[(size_t)r] = reinterpret_cast<unsigned long long*>(P.peer_block[r]);
+    mail[(size_t)r] = reinterpret_cast<double*>(static_cast<char*>(P.peer_block[r]) + P.mail_off);
+  }
+  if (!P.d_mail) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_mail), sizeof(double*) * 16));
+  if (!P.d_flags) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_flags), sizeof(unsigned long long*) * 16));
+  if (!P.d_seq) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_seq), sizeof(unsigned long long)));
+  BA_CUDA(cudaMemcpy(P.d_mail, mail.data(), sizeof(double*) * (size_t)h->nranks, cudaMemcpyHostToDevice));
+  BA_CUDA(cudaMemcpy(P.d_flags, flags.data(), sizeof(unsigned long long*) * (size_t)h->nranks, cudaMemcpyHostToDevice));
+  BA_CUDA(cudaMemset(P.d_seq, 0, sizeof(unsigned long long)));
+  static const bool off = getenv("BAGPU_NO_P2P") != nullptr;
+  P.ready = !off;
+  // a captured PCG graph holds the NCCL variant: drop it
+  if (h->lm.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(h->lm.pcg_graph));
+  h->lm.pcg_graph = nullptr;
+  return BA_OK;
+}
+
 void comm_release(ba_handle* h) {
   if (h->comm && api().ok) api().destroy(h->comm);
   h->comm = nullptr;
   ba_p2p_state& P = h->p2p;
   for (int r = 0; r < P.nranks; ++r)
-    if (P.peer_block[r] && P.peer_block[r] != P.block) cudaIpcCloseMemHandle(P.peer_block[r]);
+    if (P.ipc && P.peer_block[r] && P.peer_block[r] != P.block) cudaIpcCloseMemHandle(P.peer_block[r]);
   cudaFree(P.d_mail);
   cudaFree(P.d_flags);
   cudaFree(P.d_seq);
@@ -145,17 +189,9 @@ int ba_comm_init(ba_handle* h, const uint8_t id128[128]) {
 int ba_comm_ipc_export(ba_handle* h, uint8_t handle64[64]) {
   if (!h || !handle64) return BA_ERR_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  if (h->nranks > 16) {
-    h->err = "peer-memory exchange supports at most 16 ranks";
-    return BA_ERR_ARG;
-  }
-  BA_CUDA(cudaSetDevice(h->device));
+  int rc = ba::p2p_alloc_block(h);
+  if (rc) return rc;
   ba_p2p_state& P = h->p2p;
-  if (!P.block) {
-    const size_t bytes = P.mail_off + 2 * 9 * (size_t)h->ncams * sizeof(double);
-    BA_CUDA(cudaMalloc(&P.block, bytes));
-    BA_CUDA(cudaMemset(P.block, 0, bytes));
-  }
   cudaIpcMemHandle_t mh;
   BA_CUDA(cudaIpcGetMemHandle(&mh, P.block));
   memcpy(handle64, &mh, 64);
@@ -170,33 +206,18 @@ int ba_comm_ipc_import(ba_handle* h, const uint8_t* handles) {
     return BA_ERR_ARG;
   }
   BA_CUDA(cudaSetDevice(h->device));
-  P.nranks = h->nranks;
-  P.rank = h->rank;
-  std::vector<double*> mail((size_t)h->nranks);
-  std::vector<unsigned long long*> flags((size_t)h->nranks);
+  std::vector<void*> blocks((size_t)h->nranks, nullptr);
   for (int r = 0; r < h->nranks; ++r) {
     if (r == h->rank) {
-      P.peer_block[r] = P.block;
+      blocks[(size_t)r] = P.block;
     } else {
       cudaIpcMemHandle_t mh;
       memcpy(&mh, handles + 64 * (size_t)r, 64);
-      BA_CUDA(cudaIpcOpenMemHandle(&P.peer_block[r], mh, cudaIpcMemLazyEnablePeerAccess));
+      BA_CUDA(cudaIpcOpenMemHandle(&blocks[(size_t)r], mh, cudaIpcMemLazyEnablePeerAccess));
     }
-    flags[(size_t)r] = reinterpret_cast<unsigned long long*>(P.peer_block[r]);
-    mail[(size_t)r] = reinterpret_cast<double*>(static_cast<char*>(P.peer_block[r]) + P.mail_off);
   }
-  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_mail), sizeof(double*) * 16));
-  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_flags), sizeof(unsigned long long*) * 16));
-  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_seq), sizeof(unsigned long long)));
-  BA_CUDA(cudaMemcpy(P.d_mail, mail.data(), sizeof(double*) * (size_t)h->nranks, cudaMemcpyHostToDevice));
-  BA_CUDA(cudaMemcpy(P.d_flags, flags.data(), sizeof(unsigned long long*) * (size_t)h->nranks, cudaMemcpyHostToDevice));
-  BA_CUDA(cudaMemset(P.d_seq, 0, sizeof(unsigned long long)));
-  static const bool off = getenv("BAGPU_NO_P2P") != nullptr;
-  P.ready = !off;
-  // a captured PCG graph holds the NCCL variant: drop it
-  if (h->lm.pcg_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(h->lm.pcg_graph));
-  h->lm.pcg_graph = nullptr;
-  return BA_OK;
+  P.ipc = true;
+  return ba::p2p_attach(h, blocks.data());
 }
 
 // Back to NCCL for the per-iteration exchange (all ranks must agree: call it on every rank or on none).

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -9,6 +10,7 @@
 #include "ba_chol.h"
 
 struct ncclComm;
+struct ba_group;  // ba_group.cu: the per-device sub-handles of a multi-GPU handle
 
 #define BA_CUDA(call)                                                                          \
   do {                                                                                         \
@@ -90,6 +92,8 @@ struct ba_lm_state {
   double* d_ex = nullptr;     // 2 vectors of cn: scaled right-hand side / residual, scaled solution
   ba::chol_plan chol;
   bool attrs_set = false;     // cudaFuncSetAttribute is per device: done once per handle
+  double t_schur_ms = 0.0, t_chol_ms = 0.0;  // accumulated phase times of the exact factor (CUDA events)
+  int64_t chol_count = 0;
   // outcome of the last damped solve (ba_last_solve_info)
   int last_solver = 0, last_converged = 0, last_iters = 0;
   double last_rel = 0.0;
@@ -113,6 +117,7 @@ struct ba_lm_state {
 // NVLink/NVSwitch): every rank owns one exported block [flags (16 x u64) | pad | mail[2][9 ncams]].
 struct ba_p2p_state {
   bool ready = false;
+  bool ipc = false;                      // peer blocks were opened with CUDA IPC (else: raw in-process peer pointers)
   int nranks = 0, rank = 0;
   void* block = nullptr;                 // own allocation (cudaMalloc, exported)
   void* peer_block[16] = {nullptr};      // opened peer blocks (own entry = block)
@@ -151,6 +156,7 @@ struct ba_handle {
   ba_lm_state lm;
   ncclComm* comm = nullptr;
   ba_p2p_state p2p;
+  ba_group* group = nullptr;  // non-null: this handle only fans out to one sub-handle per GPU (ba_create_multi)
   mutable std::string err;
   int64_t nvar() const { return 9 * ncams + 3 * npnts; }
   int64_t nobs_l() const { return obs1 - obs0; }
@@ -173,6 +179,22 @@ int lm_prepare(ba_handle* h);
 // hold the records of x): Jtv_cams = sum_k B_k' v_k, 9 per camera
 int lm_jtprod_cams(ba_handle* h, const double* x, const double* v, double* Jtv_cams);
 void lm_release(ba_handle* h);
+// ---- ba_group.cu / ba_capi.cu -----------------------------------------------------------------
+int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, const int64_t* pnt, const double* pt2d,
+                int device, int rank, int nranks, ba_handle** out);
+void group_release(ba_handle* h);
+int group_residual(ba_handle* h, const double* x, double* cx, double* vals);
+int group_jac_structure(ba_handle* h, int64_t* rows, int64_t* cols);
+int group_jprod(ba_handle* h, const double* x, const double* v, double* Jv);
+int group_jtprod(ba_handle* h, const double* x, const double* v, double* Jtv);
+int group_lm_step(ba_handle* h, const double* x, double lambda, double pcg_tol, int32_t pcg_max_iter, double* delta,
+                  double* dr2, double* obj, double* jtr, int32_t* pcg_iters);
+int group_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* p, ba_lm_stats* st, ba_iter_cb cb, void* user);
+int group_apply(ba_handle* h, const std::function<int(ba_handle*)>& f);  // setters: the same call on every sub-handle
+const ba_handle* group_first(const ba_handle* h);
+// ---- ba_hostio.cu ---------------------------------------------------------------------------
+// dst (host, pageable or page-locked) <- src (device); ordered after the handle's stream; returns when complete
+int copy_to_host(ba_handle* h, void* dst, const void* src, size_t bytes);
 // ---- ba_comm.cu -----------------------------------------------------------------------------
 int allreduce_sum(ba_handle* h, double* buf, size_t n);
 int allreduce_sum_i64(ba_handle* h, long long* buf, size_t n);

@@ -387,6 +387,8 @@ struct Solver {
   int exact_factor(double lambda) {
     int rc;
     const int64_t cn = S.cn;
+    const bool tr = trace_on();
+    cudaEventRecord(S.ev[5], s);
     k_exact_diag<<<nblk(n9, 256), 256, 0, s>>>(n9, lambda, S.d_Ug, S.d_cd);
     k_exact_y<<<nblk(nl, PT_THREADS), PT_THREADS, 0, s>>>(h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_Vinv, S.d_cd,
                                                           S.d_Yh);
@@ -399,10 +401,27 @@ struct Solver {
     if ((rc = allreduce_sum_i64(h, reinterpret_cast<long long*>(S.d_S), (size_t)(cn * cn)))) return rc;
     k_exact_finish<<<dim3(nblk(cn, 256), (unsigned)cn), 256, 0, s>>>(n9, cn, S.d_H, S.d_Cr, S.d_cd, S.d_S);
     if ((rc = check())) return rc;
+    cudaEventRecord(S.ev[6], s);
     int info = 0;
-    rc = chol_factor(h, S.chol, S.d_S, s, &info);  // synchronises (pivot check)
-    if (rc) return rc;
-    if ((rc = read_scalars())) return rc;
+    if ((rc = chol_factor(h, S.chol, S.d_S, s, nullptr))) return rc;
+    cudaEventRecord(S.ev[7], s);
+    BA_CUDA(cudaMemcpyAsync(&info, S.chol.d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if ((rc = read_scalars())) return rc;  // synchronises: pivot check + S_ERR
+    if (info != 0) {
+      h->err = "Cholesky of the reduced camera system: non-positive pivot";
+      return BA_ERR_NUMERIC;
+    }
+    float ta = 0, tc = 0;
+    cudaEventElapsedTime(&ta, S.ev[5], S.ev[6]);
+    cudaEventElapsedTime(&tc, S.ev[6], S.ev[7]);
+    S.t_schur_ms += ta;
+    S.t_chol_ms += tc;
+    S.chol_count += 1;
+    if (tr) {
+      const double fl = (double)cn * cn * cn / 3.0;
+      fprintf(stderr, "[bagpu] exact factor: assembly of S (%lld x %lld) %.2f ms, Cholesky %.2f ms (%.1f TFLOP/s)\n",
+              (long long)cn, (long long)cn, ta, tc, fl / (tc * 1e-3) / 1e12);
+    }
     if (S.h_scal[S_ERR] != 0.0) {
       h->err = "Schur diagonal block not positive definite";
       return BA_ERR_NUMERIC;
@@ -842,6 +861,7 @@ int ba_lm_step(ba_handle* h, const double* x, double lambda, double pcg_tol, int
     if (h) h->err = "null argument";
     return BA_ERR_ARG;
   }
+  if (h->group) return ba::group_lm_step(h, x, lambda, pcg_tol, pcg_max_iter, delta, dr2, obj, jtr, pcg_iters);
   int rc = ba::lm_prepare(h);
   if (rc) return rc;
   BA_CUDA(cudaSetDevice(h->device));
@@ -886,6 +906,7 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
     if (h) h->err = "null argument";
     return BA_ERR_ARG;
   }
+  if (h->group) return ba::group_lm_solve(h, x_inout, prm_in, st, cb, user);
   ba_lm_params prm;
   if (prm_in) prm = *prm_in; else ba_lm_default_params(&prm);
   static const bool trace = getenv("BAGPU_TRACE") != nullptr;  // per-iteration phase times on stderr
@@ -902,6 +923,8 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
     fprintf(stderr, "[bagpu] lm_prepare %.1f ms\n", std::chrono::duration<double>(wall0 - wall_prep).count() * 1e3);
   const double t_prepare = was_ready ? 0.0 : std::chrono::duration<double>(wall0 - wall_prep).count() * 1e3;
   double t_eval = 0, t_asm = 0, t_pcg = 0, t_back = 0, worst_rel = 0;
+  S.t_schur_ms = S.t_chol_ms = 0.0;
+  S.chol_count = 0;
   int64_t pcg_total = 0, capped = 0;
   auto rec = [&](int i) { cudaEventRecord(S.ev[i], h->stream); };
   auto lap = [&](int a, int b) {
@@ -1056,6 +1079,8 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
     st->pcg_iters_total = pcg_total;
     st->t_eval_ms = t_eval; st->t_assemble_ms = t_asm; st->t_pcg_ms = t_pcg; st->t_backsub_ms = t_back;
     st->capped_solves = capped; st->worst_solve_rel = worst_rel; st->t_prepare_ms = t_prepare;
+    st->t_schur_ms = S.t_schur_ms; st->t_chol_ms = S.t_chol_ms;
+    st->chol_n = S.exact ? S.cn : 0; st->chol_count = S.chol_count;
   }
   return BA_OK;
 }

@@ -39,6 +39,8 @@ class GenericExecutionStats:
     timings_ms: dict = field(default_factory=dict)
     capped_solves: int = 0          # damped solves that stopped at pcg_max_iter (their steps are inexact)
     worst_solve_rel: float = 0.0    # largest relative residual a damped solve stopped at
+    chol_n: int = 0                 # exact solver: order of the dense factorisations (0: PCG) and how many ran
+    chol_count: int = 0
 
 
 def default_params(**kw) -> _lib.LMParams:
@@ -103,7 +105,9 @@ def Levenberg_Marquardt(model, facto="LDL", perm="AMD", normalize="None", linese
         elapsed_time=elapsed, dual_feas=st.dual_feas, rows=rows, pcg_iters=int(st.pcg_iters_total),
         lambda_final=st.lambda_final,
         timings_ms=dict(eval=st.t_eval_ms, assemble=st.t_assemble_ms, pcg=st.t_pcg_ms, backsub=st.t_backsub_ms,
-                        device_total=st.elapsed_s * 1e3, prepare=st.t_prepare_ms),
+                        device_total=st.elapsed_s * 1e3, prepare=st.t_prepare_ms, schur_assembly=st.t_schur_ms,
+                        cholesky=st.t_chol_ms),
+        chol_n=int(st.chol_n), chol_count=int(st.chol_count),
         capped_solves=int(st.capped_solves), worst_solve_rel=st.worst_solve_rel)
 
 

@@ -74,11 +74,13 @@ class BALNLPModel:
 
     Build it from arrays (``cams_indices``/``pnts_indices`` 1-based, ``pt2d`` interleaved, ``x0``) --
     what ``readfile`` returns (src/ReadFiles.jl:9-53) -- or from a BAL file with ``from_file``.
-    ``rank``/``nranks`` select the observation shard of a one-process-per-GPU run.
+    ``rank``/``nranks`` select the observation shard of a one-process-per-GPU run; ``ngpus`` (an int, or "all")
+    puts several GPUs behind this one model in this one process (ba_create_multi): every method then behaves as
+    on one GPU, with full-length arrays.
     """
 
     def __init__(self, cams_indices, pnts_indices, pt2d, x0, ncams, npnts, nobs=None, *, name="BAL",
-                 device=0, rank=0, nranks=1):
+                 device=0, rank=0, nranks=1, ngpus=None):
         self.cams_indices = np.ascontiguousarray(cams_indices, dtype=np.int64)
         self.pnts_indices = np.ascontiguousarray(pnts_indices, dtype=np.int64)
         self.nobs = int(len(self.cams_indices) if nobs is None else nobs)
@@ -93,7 +95,15 @@ class BALNLPModel:
         self.device, self.rank, self.nranks = int(device), int(rank), int(nranks)
         L = _lib.lib()
         h = C.c_void_p()
-        if nranks == 1:
+        self.ngpus = None
+        if ngpus is not None:
+            if nranks != 1:
+                raise ValueError("ngpus (one process, several GPUs) and rank/nranks (one process per GPU) exclude each other")
+            n = 0 if ngpus == "all" else int(ngpus)
+            rc = L.ba_create_multi(self.ncams, self.npnts, self.nobs, _ptr(self.cams_indices),
+                                   _ptr(self.pnts_indices), _ptr(self.pt2d), n, None, C.byref(h))
+            self.ngpus = ngpus
+        elif nranks == 1:
             rc = L.ba_create(self.ncams, self.npnts, self.nobs, _ptr(self.cams_indices), _ptr(self.pnts_indices),
                              _ptr(self.pt2d), self.device, C.byref(h))
         else:

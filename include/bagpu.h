@@ -61,6 +61,15 @@ BA_API int ba_create(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* 
 BA_API int ba_create_sharded(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam_idx_1based,
                       const int64_t* pnt_idx_1based, const double* pt2d, int device, int rank,
                       int nranks, ba_handle** out);
+/* Several GPUs behind ONE handle in ONE process -- the mode a single-process caller (the reference's Julia session,
+ * src/main.jl:27-30) uses: `ngpus` devices (devices[0..ngpus), or 0..ngpus-1 when devices is NULL; ngpus <= 0 = all
+ * visible devices).  The library shards the observations over the devices exactly like ba_create_sharded, runs one
+ * host thread per device, sets up NCCL and the peer-memory exchange itself, and presents FULL-LENGTH arrays to the
+ * caller: every host-pointer entry point (ba_residual ... ba_jtprod, ba_lm_step, ba_lm_solve) behaves as on a
+ * single-GPU handle.  Device-pointer variants, ba_set_stream and ba_set_profiling are per GPU and return BA_ERR_ARG. */
+BA_API int ba_create_multi(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam_idx_1based,
+                           const int64_t* pnt_idx_1based, const double* pt2d, int ngpus, const int* devices,
+                           ba_handle** out);
 BA_API int ba_destroy(ba_handle* h);
 BA_API int ba_shard_range(const ba_handle* h, int64_t* obs0, int64_t* obs1, int64_t* pnt0, int64_t* pnt1);
 /* Host-side partition used by ba_create_sharded (no GPU needed): cuts[r]..cuts[r+1] is rank r's
@@ -71,6 +80,9 @@ BA_API const char* ba_version(void);
 /* FP64 FMA throughput of `device` in TFLOP/s, measured with a register-resident FMA kernel (the secondary ceiling
  * of this path next to HBM bandwidth; not part of the reference's surface). */
 BA_API int ba_measure_fp64_peak(int device, double* tflops);
+/* The same for the FP64 tensor-core path (mma.sync.m8n8k4.f64, DMMA): the ceiling of the dense Cholesky of
+ * BA_SOLVER_EXACT. */
+BA_API int ba_measure_fp64_mma_peak(int device, double* tflops);
 /* Run this handle's work on an existing stream (cudaStream_t passed as void*), e.g. the
  * caller's current stream so that its own CUDA events bracket the kernels. */
 BA_API int ba_set_stream(ba_handle* h, void* cuda_stream);
@@ -160,6 +172,10 @@ typedef struct ba_lm_stats {
   int64_t capped_solves;   /* damped solves that hit pcg_max_iter before pcg_tol (their steps are inexact) */
   double worst_solve_rel;  /* largest solve_rel over the iterations */
   double t_prepare_ms;     /* one-off schedule construction + allocations (first LM call on a handle) */
+  /* BA_SOLVER_EXACT only (both are part of t_assemble_ms): explicit assembly of the reduced camera system, and
+   * its dense Cholesky factorisations (chol_n^3 / 3 flops each, chol_count of them) */
+  double t_schur_ms, t_chol_ms;
+  int64_t chol_n, chol_count;
 } ba_lm_stats;
 
 typedef void (*ba_iter_cb)(const ba_lm_row* row, void* user);

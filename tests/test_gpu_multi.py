@@ -140,3 +140,50 @@ def test_two_gpu_deflated_pcg_matches_one_gpu(ba):
     assert got["acc"] == [r["accepted"] for r in st.rows]
     assert np.allclose(got["f"], [r["f"] for r in st.rows], rtol=1e-8, atol=0)
     assert abs(got["objective"] - st.objective) <= 1e-8 * st.objective
+
+
+@pytest.mark.parametrize("solver", ["pcg", "exact"])
+def test_single_process_multi_gpu_handle_matches_one_gpu(ba, oracle, solver):
+    """ba_create_multi: several GPUs behind one handle in one process (the mode the reference's single Julia
+    process can reach).  Every host-pointer entry point must return the full-length arrays of the one-GPU handle."""
+    import torch
+    from conftest import TOL, parity_report, rel_errors
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs two CUDA devices")
+    ng = min(ng, 4)
+    p = ba.synth.make_problem((160, 10000, 50000))   # camera system above the single-CTA threshold
+    m1 = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    mg = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs, ngpus=ng)
+    assert mg.nobs_local == p.nobs and mg.obs_range == (0, p.nobs)
+    for m in (m1, mg):
+        m.set_solver(solver)
+    cx1, v1 = m1.cons_jac_coord_(p.x0)
+    cxg, vg = mg.cons_jac_coord_(p.x0)
+    assert np.array_equal(cx1, cxg) and np.array_equal(v1, vg)          # same kernels on the same observations
+    assert np.array_equal(m1.cons(p.x0), mg.cons(p.x0))
+    r1, c1 = m1.jac_structure()
+    rg, cg = mg.jac_structure()
+    assert np.array_equal(r1, rg) and np.array_equal(c1, cg)
+    rng = np.random.default_rng(2)
+    v, w = rng.normal(size=p.nvar), rng.normal(size=2 * p.nobs)
+    assert np.array_equal(m1.jprod_(p.x0, v), mg.jprod_(p.x0, v))
+    e = rel_errors(mg.jtprod_(p.x0, w), m1.jtprod_(p.x0, w))
+    assert e[0] <= 1e-13
+    d1, dr1, o1, j1, _ = ba.lm_step(m1, p.x0, 30.0, want_jtr=True)
+    dg, drg, og, jg, _ = ba.lm_step(mg, p.x0, 30.0, want_jtr=True)
+    es, ej = rel_errors(dg, d1), rel_errors(jg, j1)
+    assert es[0] <= TOL and ej[0] <= 1e-13 and abs(drg - dr1) <= 1e-11 * dr1 and abs(og - o1) <= 1e-13 * o1
+    s1 = ba.Levenberg_Marquardt(m1, "LDL", "AMD", "None", False, ite_max=5, solver=solver)
+    sg = ba.Levenberg_Marquardt(ba.FeasibilityResidual(mg), "LDL", "AMD", "None", False, ite_max=5, solver=solver)
+    assert sg.status == s1.status and sg.iter == s1.iter
+    assert [r["accepted"] for r in sg.rows] == [r["accepted"] for r in s1.rows]
+    worst = max(abs(a["f"] - b["f"]) / b["f"] for a, b in zip(sg.rows, s1.rows))
+    parity_report("single_process_multi_gpu", ngpus=ng, solver=solver, step=es[0], jtr=ej[0], trajectory_f=worst,
+                  objective=abs(sg.objective - s1.objective) / s1.objective)
+    assert worst <= 1e-9 and abs(sg.objective - s1.objective) <= 1e-9 * s1.objective
+    assert rel_errors(sg.solution, s1.solution)[0] <= 1e-8
+    with pytest.raises(ba.BAError):
+        ba._lib.check(ba._lib.lib().ba_set_profiling(mg.handle, 1), mg.handle)   # per-GPU call: refused on a group
+    mg.close()
+    m1.close()

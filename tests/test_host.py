@@ -114,7 +114,7 @@ int main(void) {
   P(ba_lm_row, converged); P(ba_lm_row, solve_rel);
   P(ba_lm_stats, status); P(ba_lm_stats, iter); P(ba_lm_stats, objective); P(ba_lm_stats, pcg_iters_total);
   P(ba_lm_stats, t_backsub_ms); P(ba_lm_stats, capped_solves); P(ba_lm_stats, worst_solve_rel);
-  P(ba_lm_stats, t_prepare_ms);
+  P(ba_lm_stats, t_prepare_ms); P(ba_lm_stats, t_chol_ms); P(ba_lm_stats, chol_count);
   return 0;
 }
 ''')
@@ -137,7 +137,8 @@ int main(void) {
                                                            "t_backsub_ms": "t_backsub_ms",
                                                            "capped_solves": "capped_solves",
                                                            "worst_solve_rel": "worst_solve_rel",
-                                                           "t_prepare_ms": "t_prepare_ms"})):
+                                                           "t_prepare_ms": "t_prepare_ms", "t_chol_ms": "t_chol_ms",
+                                                           "chol_count": "chol_count"})):
         for cf, pf in names.items():
             assert int(got["%s.%s" % (cname, cf)]) == getattr(cls, pf).offset, (cname, cf)
 
@@ -211,3 +212,36 @@ def test_select_orthonormal_drops_dependent_columns(ba):
     assert np.all(Cm[3] == 0.0)                 # the ghost column takes no part
     Q = Y @ Cm
     assert np.allclose(Q.T @ Q, np.eye(kept.value), atol=1e-10)
+
+
+def test_julia_glue_structs_list_the_header_fields_in_order():
+    """julia/lm_gpu.jl cannot be executed here (no Julia): at least its isbits mirrors of ba_lm_params / ba_lm_row /
+    ba_lm_stats must name the fields of include/bagpu.h in the same order with matching widths, and every symbol the
+    glue ccalls must be declared in the header."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "bagpu.h")).read()
+    jl = open(os.path.join(ROOT, "bundleadjustment.jl_b200", "julia", "lm_gpu.jl")).read()
+    jl2 = open(os.path.join(ROOT, "bundleadjustment.jl_b200", "julia", "BALNLPModels.jl")).read()
+
+    def c_fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            ty, names = decl.split(None, 1)
+            for n in names.split(","):
+                out.append((n.strip(), {"double": "Float64", "int64_t": "Int64", "int32_t": "Int32"}[ty]))
+        return out
+
+    def jl_fields(name):
+        body = re.search(r"struct %s\n(.*?)\nend" % name, jl, re.S).group(1)
+        return [(m.group(1), m.group(2)) for m in re.finditer(r"(\w+)::(\w+)", body)]
+
+    for cname, jname in (("ba_lm_params", "BALMParams"), ("ba_lm_stats", "BALMStats"), ("ba_lm_row", "BALMRow")):
+        assert c_fields(cname) == jl_fields(jname), cname
+    declared = set(re.findall(r"BA_API\s+[\w\s\*]+?\b(ba_\w+)\s*\(", hdr))
+    used = set(re.findall(r"ccall\(\(:(ba_\w+), libbagpu\)", jl + jl2))
+    assert used and used <= declared, used - declared
