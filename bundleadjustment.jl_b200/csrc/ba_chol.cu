@@ -170,11 +170,13 @@ constexpr int PO_SMEM = (CT * PO_LD + CT + 64 * 65) * (int)sizeof(double);
 // a0 + pi * astep etc.
 __device__ __forceinline__ void po_gemm(int m, int npair, const double* a0, int lda, int astep, const double* b0, int ldb,
                                         int bstep, double* c0, int ldc, int cstep, double sign) {
+  // item -> (pair, R, C); the thread owns rows R + i m/4 and columns C + j m/4 (i, j < 4): consecutive lanes have
+  // consecutive C, so the loads of b and the stores of c are conflict-free and the loads of a are broadcasts
   const int pm = m >> 2, per = pm * pm;
   for (int item = threadIdx.x; item < npair * per; item += PO_THREADS) {
-    const int pi = item / per, rem = item - pi * per, pr = rem / pm, pc = rem - pr * pm;
-    const double* a = a0 + pi * astep + 4 * pr * lda;
-    const double* b = b0 + pi * bstep + 4 * pc;
+    const int pi = item / per, rem = item - pi * per, R = rem / pm, C = rem - R * pm;
+    const double* a = a0 + pi * astep + R * lda;
+    const double* b = b0 + pi * bstep + C;
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -185,26 +187,35 @@ __device__ __forceinline__ void po_gemm(int m, int npair, const double* a0, int 
       double va[4], vb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        va[i] = a[i * lda + q];
-        vb[i] = b[q * ldb + i];
+        va[i] = a[i * pm * lda + q];
+        vb[i] = b[q * ldb + i * pm];
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] += va[i] * vb[j];
     }
-    double* c = c0 + pi * cstep + 4 * pr * ldc + 4 * pc;
+    double* c = c0 + pi * cstep + R * ldc + C;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) c[i * ldc + j] = sign * acc[i][j];
+      for (int j = 0; j < 4; ++j) c[i * pm * ldc + j * pm] = sign * acc[i][j];
   }
 }
 
 // A_kk (lower) <- L_kk, Dinv[k] <- L_kk^-1.  info: first non-positive pivot (1-based global index), else untouched.
 __global__ void __launch_bounds__(PO_THREADS, 1)
-k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Dinv, int* __restrict__ info) {
+k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Dinv, int* __restrict__ info,
+             long long* __restrict__ prof) {
   extern __shared__ __align__(16) double smp[];
+  long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = 0;  // phase cycle counts (BAGPU_POTRF_PROF; thread 0 only)
+#define PO_LAP(slot)                          \
+  if (prof && threadIdx.x == 0) {             \
+    const long long now_ = clock64();         \
+    tk[slot] += now_ - tl;                    \
+    tl = now_;                                \
+  }
+  if (prof && threadIdx.x == 0) tl = clock64();
   double* a = smp;                       // 128 x 129: the block, then its inverse
   double* rinv = smp + CT * PO_LD;       // 128: reciprocals of the diagonal of L
   double* tmp = rinv + CT;               // 64 x 65 scratch of the doubling levels
@@ -215,35 +226,39 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
     a[r * PO_LD + c] = (c <= r) ? Akk[(int64_t)r * ld + c] : 0.0;
   }
   __syncthreads();
+  PO_LAP(0)
   for (int j0 = 0; j0 < CT; j0 += PO_SB) {
-    // (a) 16 x 16 diagonal sub-block: Cholesky by warp 0, row r in lane r (lanes 16..31 mirror)
+    // (a) 16 x 16 diagonal sub-block: Cholesky by 16 lanes of warp 0; lane r keeps row r in registers, a column
+    // travels through shared memory (one store, one warp barrier, broadcast loads); no division on the chain:
+    // l_jj = d_jj * rsqrt(d_jj), l_rj = a_rj * rsqrt(d_jj), every lane forms rsqrt(d_jj) itself
     if (warp == 0) {
       const int r = lane & 15;
+      double* blk = a + j0 * PO_LD + j0;
       double row[PO_SB];
 #pragma unroll
-      for (int c = 0; c < PO_SB; ++c) row[c] = a[(j0 + r) * PO_LD + j0 + c];  // zeros above the diagonal
+      for (int c = 0; c < PO_SB; ++c) row[c] = blk[r * PO_LD + c];  // zeros above the diagonal
 #pragma unroll
       for (int j = 0; j < PO_SB; ++j) {
-        const double djj = __shfl_sync(0xffffffffu, row[j], j);
+        if (lane == j) blk[j * PO_LD + j] = row[j];  // the updated pivot
+        __syncwarp();
+        const double djj = blk[j * PO_LD + j];
         if (!(djj > 0.0) && lane == 0) atomicCAS(info, 0, k * CT + j0 + j + 1);
-        // no division on this dependent chain: l_jj = d_jj * rsqrt(d_jj), l_rj = a_rj * rsqrt(d_jj)
         const double rs = rsqrt(djj);
         const double l = row[j] * rs;  // (rows above j hold zeros in this column)
         row[j] = l;
+        __syncwarp();                  // everybody has read the pivot before it is overwritten by l_jj
+        if (lane < PO_SB) blk[r * PO_LD + j] = l;
         if (lane == j) rinv[j0 + j] = rs;
+        __syncwarp();
 #pragma unroll
         for (int c = j + 1; c < PO_SB; ++c) {
-          const double lc = __shfl_sync(0xffffffffu, l, c);
+          const double lc = blk[c * PO_LD + j];
           if (c <= r) row[c] -= l * lc;
         }
       }
-      if (lane < PO_SB) {
-#pragma unroll
-        for (int c = 0; c < PO_SB; ++c)
-          if (c <= r) a[(j0 + r) * PO_LD + j0 + c] = row[c];
-      }
     }
     __syncthreads();
+    PO_LAP(1)
     // (b) rows below: x L16' = row by forward substitution, one thread per row
     const int nbelow = CT - j0 - PO_SB;
     if (tid < nbelow) {
@@ -260,16 +275,16 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
       for (int j = 0; j < PO_SB; ++j) rowp[j] = x[j];
     }
     __syncthreads();
-    // (c) trailing update of the lower triangle in 4 x 4 patches: a[r][c] -= sum_q a[r][j0+q] a[c][j0+q]
-    const int np = nbelow >> 2, tp = np * (np + 1) / 2;
-    if (tid < tp) {
-      int pr = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
-      while (pr * (pr + 1) / 2 > tid) --pr;
-      while ((pr + 1) * (pr + 2) / 2 <= tid) ++pr;
-      const int pc = tid - pr * (pr + 1) / 2;
+    PO_LAP(2)
+    // (c) trailing update of the lower triangle: a[r][c] -= sum_q a[r][j0+q] a[c][j0+q].  A thread owns rows
+    // R + i np and columns C + j np (np = nbelow / 4): consecutive lanes have consecutive C (conflict-free loads of
+    // the column operand, broadcast loads of the row operand); entries above the diagonal are computed and dropped.
+    const int np = nbelow >> 2;
+    for (int item = tid; item < np * np; item += PO_THREADS) {
+      const int R = item / np, C = item - R * np;
       const int base = j0 + PO_SB;
-      const double* ar = a + (base + 4 * pr) * PO_LD + j0;
-      const double* ac = a + (base + 4 * pc) * PO_LD + j0;
+      const double* ar = a + (base + R) * PO_LD + j0;
+      const double* ac = a + (base + C) * PO_LD + j0;
       double acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -280,54 +295,53 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
         double vr[4], vc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          vr[i] = ar[i * PO_LD + q];
-          vc[i] = ac[i * PO_LD + q];
+          vr[i] = ar[i * np * PO_LD + q];
+          vc[i] = ac[i * np * PO_LD + q];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] += vr[i] * vc[j];
       }
-      double* out = a + (base + 4 * pr) * PO_LD + base + 4 * pc;
+      double* out = a + (base + R) * PO_LD + base + C;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (pc < pr || j <= i) out[i * PO_LD + j] -= acc[i][j];
+          if (C + j * np <= R + i * np) out[i * np * PO_LD + j * np] -= acc[i][j];
     }
     __syncthreads();
+    PO_LAP(3)
   }
   for (int e = tid; e < CT * CT; e += PO_THREADS) {
     const int r = e >> 7, c = e & 127;
     if (c <= r) Akk[(int64_t)r * ld + c] = a[r * PO_LD + c];
   }
   __syncthreads();  // the factor has been read out before its storage is reused
-  // inverse of the factor, in place.  Diagonal 16 x 16 blocks: warp w < 8 inverts block w; lane c solves L x = e_c
-  // (column c of X); L[i][q] arrives from lane i's registers.
-  if (warp < CT / PO_SB) {
-    const int b0 = warp * PO_SB, r = lane & 15;
-    double row[PO_SB], x[PO_SB];
+  PO_LAP(4)
+  // inverse of the factor, in place.  Diagonal 16 x 16 blocks first: thread (block b, column c) solves L_bb x = e_c
+  // by forward substitution, L read from shared memory (the 16 threads of a block read the same word: broadcast)
+  {
+    const int b0 = (tid >> 4) * PO_SB, c = tid & 15;
+    double x[PO_SB];
+    if (tid < CT) {
+      const double* blk = a + b0 * PO_LD + b0;
 #pragma unroll
-    for (int c = 0; c < PO_SB; ++c) row[c] = a[(b0 + r) * PO_LD + b0 + c];
-    const double ri_own = rinv[b0 + r];
+      for (int i = 0; i < PO_SB; ++i) {
+        double sacc = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-    for (int i = 0; i < PO_SB; ++i) {
-      double sacc = (i == r) ? 1.0 : 0.0;
-#pragma unroll
-      for (int q = 0; q < i; ++q) {
-        const double liq = __shfl_sync(0xffffffffu, row[q], i);
-        sacc -= liq * x[q];  // x[q] == 0 for q < r
+        for (int q = 0; q < i; ++q) sacc -= blk[i * PO_LD + q] * x[q];  // x[q] == 0 for q < c
+        x[i] = (i >= c) ? sacc * rinv[b0 + i] : 0.0;
       }
-      const double ri = __shfl_sync(0xffffffffu, ri_own, i);
-      x[i] = (i >= r) ? sacc * ri : 0.0;
     }
-    __syncwarp();  // every lane has read its row of L before the block is overwritten
-    if (lane < PO_SB) {
+    __syncthreads();  // every thread has read L before the blocks are overwritten
+    if (tid < CT) {
 #pragma unroll
-      for (int i = 0; i < PO_SB; ++i) a[(b0 + i) * PO_LD + b0 + r] = x[i];  // X[i][c = r] (zeros above the diagonal)
+      for (int i = 0; i < PO_SB; ++i) a[(b0 + i) * PO_LD + b0 + c] = x[i];  // X[i][c] (zeros above the diagonal)
     }
   }
   __syncthreads();
+  PO_LAP(5)
   // X21 = -X22 (L21 X11) for block sizes 16, 32, 64
   for (int m = PO_SB; m < CT; m <<= 1) {
     const int npair = CT / (2 * m), step = 2 * m * PO_LD + 2 * m;
@@ -338,11 +352,16 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
     po_gemm(m, npair, a + m * PO_LD + m, PO_LD, step, tmp, m + 1, m * (m + 1), a + m * PO_LD, PO_LD, step, -1.0);
     __syncthreads();
   }
+  PO_LAP(6)
   double* D = Dinv + (int64_t)k * CT * CT;
   for (int e = tid; e < CT * CT; e += PO_THREADS) {
     const int r = e >> 7, c = e & 127;
     D[e] = (c <= r) ? a[r * PO_LD + c] : 0.0;
   }
+  PO_LAP(7)
+  if (prof && threadIdx.x == 0)
+    for (int i = 0; i < 8; ++i) prof[i] = tk[i];
+#undef PO_LAP
 }
 
 // ---- substitution sweeps ----------------------------------------------------------------------------------
@@ -475,6 +494,7 @@ void chol_plan_release(chol_plan& P) {
   cudaFree(P.d_w);
   cudaFree(P.d_x);
   cudaFree(P.d_info);
+  cudaFree(P.d_prof);
   if (P.solve_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(P.solve_graph));
   if (P.side) cudaStreamDestroy(P.side);
   if (P.ev_col) cudaEventDestroy(P.ev_col);
@@ -488,7 +508,13 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
   const int nb = (int)(cn / CT);
   static const bool no_lookahead = getenv("BAGPU_CHOL_NO_LOOKAHEAD") != nullptr;
   BA_CUDA(cudaMemsetAsync(P.d_info, 0, sizeof(int), s));
-  k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, 0, P.d_Dinv, P.d_info);
+  static const bool want_prof = getenv("BAGPU_POTRF_PROF") != nullptr;
+  long long* prof = nullptr;
+  if (want_prof) {  // development aid: phase cycle counts of the first diagonal block
+    if (!P.d_prof) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_prof), 8 * sizeof(long long)));
+    prof = P.d_prof;
+  }
+  k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, 0, P.d_Dinv, P.d_info, prof);
   if (nb > 1) k_chol_trsm<<<2 * (nb - 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, 0, P.d_Dinv);
   for (int k = 0; k + 1 < nb; ++k) {
     // panel k is final in A[k+1:, k].  Column k+1 of the trailing matrix first ...
@@ -498,18 +524,25 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
       // ... then panel k+1 (potrf + trsm) on the side stream, under the rest of the update
       BA_CUDA(cudaEventRecord(P.ev_col, s));
       BA_CUDA(cudaStreamWaitEvent(P.side, P.ev_col, 0));
-      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv, P.d_info);
+      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv, P.d_info, nullptr);
       k_chol_trsm<<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv);
       BA_CUDA(cudaEventRecord(P.ev_panel, P.side));
       k_chol_syrk<<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb);
       BA_CUDA(cudaStreamWaitEvent(s, P.ev_panel, 0));
     } else {
       if (rest) k_chol_syrk<<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb);
-      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, k + 1, P.d_Dinv, P.d_info);
+      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, k + 1, P.d_Dinv, P.d_info, nullptr);
       if (rest) k_chol_trsm<<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k + 1, P.d_Dinv);
     }
   }
   BA_CUDA(cudaGetLastError());
+  if (prof) {
+    long long hp[8];
+    BA_CUDA(cudaMemcpyAsync(hp, prof, sizeof hp, cudaMemcpyDeviceToHost, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+    fprintf(stderr, "[bagpu] potrf cycles: load %lld | (a) %lld (b) %lld (c) %lld | store L %lld | inv16 %lld | doubling %lld "
+            "| store Linv %lld\n", hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7]);
+  }
   if (info_host) {
     BA_CUDA(cudaMemcpyAsync(info_host, P.d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
     BA_CUDA(cudaStreamSynchronize(s));

@@ -24,6 +24,7 @@ struct chol_plan {
   double* d_w = nullptr;     // cn: right-hand side being consumed
   double* d_x = nullptr;     // cn: solution of the sweeps
   int* d_info = nullptr;     // 0 ok, j + 1 = first non-positive pivot
+  long long* d_prof = nullptr;  // BAGPU_POTRF_PROF: phase cycle counts of the first diagonal block
   cudaStream_t side = nullptr;   // panel stream (look-ahead)
   cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_join = nullptr;
   void* solve_graph = nullptr;   // cudaGraphExec_t of the 2 cn/128 substitution steps
