@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q, small_max):
+def _worker(rank, world, port, q, small_max, solver):
     sys.path.insert(0, ROOT)
     if small_max is not None:
         os.environ["BAGPU_VEC_SMALL_MAX"] = small_max  # read once by libbagpu: selects the PCG vector path
@@ -23,6 +23,7 @@ def _worker(rank, world, port, q, small_max):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     p = ba.synth.make_problem((12, 400, 2000))
     m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs, device=rank, rank=rank, nranks=world)
+    m.set_solver(solver)
     ba.init_comm(m)
     d, dr2, obj, _, it = ba.lm_step(m, p.x0, 100.0)
     st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False)
@@ -38,8 +39,10 @@ def _worker(rank, world, port, q, small_max):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("small_max", [None, "0"])  # fused single-CTA vector kernel / multi-CTA kernels
-def test_two_gpu_lm_matches_one_gpu(ba, small_max):
+# PCG with the fused single-CTA vector kernel / with the multi-CTA kernels; the exact solve (sharded assembly of the
+# reduced camera system, integer allreduce, replicated factorisation)
+@pytest.mark.parametrize("solver,small_max", [("pcg", None), ("pcg", "0"), ("exact", None)])
+def test_two_gpu_lm_matches_one_gpu(ba, small_max, solver):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two CUDA devices")
@@ -47,7 +50,8 @@ def test_two_gpu_lm_matches_one_gpu(ba, small_max):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port + (7 if small_max else 0), q, small_max)) for r in range(2)]
+    port += (7 if small_max else 0) + (3 if solver == "exact" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, small_max, solver)) for r in range(2)]
     for pr in procs:
         pr.start()
     got = q.get(timeout=600)
@@ -56,6 +60,7 @@ def test_two_gpu_lm_matches_one_gpu(ba, small_max):
         assert pr.exitcode == 0
     p = ba.synth.make_problem((12, 400, 2000))
     m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    m.set_solver(solver)
     d, dr2, obj, _, it = ba.lm_step(m, p.x0, 100.0)
     st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False)
     rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
@@ -93,6 +98,7 @@ def _worker_deflated(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     p = ba.synth.make_problem(BIG)
     m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs, device=rank, rank=rank, nranks=world)
+    m.set_solver("pcg")
     m.set_deflation(32)
     ba.init_comm(m)
     seq, st = _deflated_sequence(ba, m, p)
@@ -123,6 +129,7 @@ def test_two_gpu_deflated_pcg_matches_one_gpu(ba):
         assert pr.exitcode == 0
     p = ba.synth.make_problem(BIG)
     m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    m.set_solver("pcg")
     m.set_deflation(32)
     seq, st = _deflated_sequence(ba, m, p)
     m.set_deflation(0)
