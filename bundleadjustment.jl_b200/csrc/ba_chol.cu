@@ -16,6 +16,7 @@
 // the next panel's column is launched first, then the next potrf + trsm run on a side stream under the rest
 // of the trailing update.
 // Roofline: n^3/3 flops against the FP64 peak (ba_measure_fp64_peak; DMMA and DFMA peaks coincide on B200).
+#include <unistd.h>
 #include <algorithm>
 #include <cstdlib>
 #include "ba_internal.h"
@@ -47,6 +48,26 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double2 ld_volatile_d2(const double2* p) {
+  double2 v;
+  asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// bounded wait for a flag written by another rank (~2 s): false on time-out
+__device__ __forceinline__ bool wait_epoch(const unsigned long long* f, unsigned long long epoch) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys_u64(f) < epoch)
+    if (clock64() - t0 > 4000000000ll) return false;
+  return true;
+}
 // acc = A (64 x 128, rows lda apart) * B' (B: 128 x 128, rows ldb apart); accumulator fragment layout of
 // m8n8k4: warp (wm, wn) of 2 x 4 owns rows wm*32.., columns wn*32..; tile (mi, ni): lane holds row 8 mi + lane/4,
 // columns 8 ni + 2 (lane%4) + {0, 1}.  Two such CTAs share an SM (8 + 8 warps): while one waits (prologue loads,
@@ -106,12 +127,28 @@ __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t l
   __syncthreads();
 }
 
-// trailing update, half tiles: blockIdx.x = 2 (i - j) + half, blockIdx.y = j - j0; A_ij[half] -= P_i[half] P_j'
+// trailing update, half tiles: A_ij[half] -= P_i[half] P_j', j = j0 + blockIdx.y.
+//   single GPU : i = j + blockIdx.x / 2
+//   DIST       : i = i0 + R (blockIdx.x / 2), the rank's own tile rows from i0 on; the CTA first waits until every
+//                rank's tiles of panel k have landed in this rank's copy of the matrix (flags over NVLink)
+template <bool DIST>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb) {
+k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, chol_peers P, int* __restrict__ info) {
   extern __shared__ __align__(16) double sm[];
-  const int j = j0 + blockIdx.y, i = j + (blockIdx.x >> 1), half = blockIdx.x & 1;
-  if (i >= nb) return;
+  const int j = j0 + blockIdx.y, half = blockIdx.x & 1;
+  const int i = DIST ? i0 + P.R * (int)(blockIdx.x >> 1) : j + (int)(blockIdx.x >> 1);
+  if (i >= nb || i < j) return;
+  if (DIST) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < P.R && !wait_epoch(P.ctl[P.q] + CHOL_NBMAX + 16 * k + threadIdx.x, P.epoch)) ok = 0;
+    __syncthreads();
+    if (!ok) {
+      if (threadIdx.x == 0) atomicCAS(info, 0, -2);
+      return;
+    }
+  }
   const double* Pi = A + ((int64_t)i * CT + half * TM) * ld + (int64_t)k * CT;
   const double* Pj = A + (int64_t)j * CT * ld + (int64_t)k * CT;
   double acc[4][4][2];
@@ -131,22 +168,93 @@ k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb) {
     }
 }
 
-// panel solve: P_i[half] <- P_i[half] Linv_kk' for the row tiles i = k + 1 + blockIdx.x / 2
+// panel solve: P_i[half] <- P_i[half] Linv_kk'.
+//   single GPU : row tiles i = k + 1 + blockIdx.x / 2
+//   DIST       : the rank's own row tiles i = i0 + R (blockIdx.x / 2); the result is stored into EVERY rank's copy of
+//                the matrix (peer-memory stores over NVLink fused into the epilogue: the all-gather of the panel),
+//                and the CTA that finishes last tells every rank that this rank's part of panel k is complete
+template <bool DIST>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-k_chol_trsm(double* __restrict__ A, int64_t ld, int k, const double* __restrict__ Dinv) {
+k_chol_trsm(double* __restrict__ A, int64_t ld, int k, const double* __restrict__ Dinv, int i0, chol_peers P,
+            int* __restrict__ cnt) {
   extern __shared__ __align__(16) double sm[];
-  const int i = k + 1 + (blockIdx.x >> 1), half = blockIdx.x & 1;
-  double* Pi = A + ((int64_t)i * CT + half * TM) * ld + (int64_t)k * CT;
+  const int half = blockIdx.x & 1;
+  const int i = DIST ? i0 + P.R * (int)(blockIdx.x >> 1) : k + 1 + (int)(blockIdx.x >> 1);
+  const int64_t off = ((int64_t)i * CT + half * TM) * ld + (int64_t)k * CT;
   double acc[4][4][2];
-  tile_abt(Pi, ld, Dinv + (int64_t)k * CT * CT, CT, acc, sm);  // (every read of these rows is complete on return)
+  tile_abt(A + off, ld, Dinv + (int64_t)k * CT * CT, CT, acc, sm);  // (every read of these rows is complete on return)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
-  double* C = Pi + (int64_t)(wm * 32 + g) * ld + wn * 32 + 2 * t;
+  const int64_t o2 = off + (int64_t)(wm * 32 + g) * ld + wn * 32 + 2 * t;
+  if (!DIST) {
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni)
-      *reinterpret_cast<double2*>(C + (int64_t)mi * 8 * ld + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+      for (int ni = 0; ni < 4; ++ni)
+        *reinterpret_cast<double2*>(A + o2 + (int64_t)mi * 8 * ld + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+    return;
+  }
+  for (int r = 0; r < P.R; ++r) {
+    double* C = P.S[r] + o2;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+        *reinterpret_cast<double2*>(C + (int64_t)mi * 8 * ld + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int last;
+  if (threadIdx.x == 0) last = (atomicAdd(cnt, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < P.R) st_release_sys_u64(P.ctl[threadIdx.x] + CHOL_NBMAX + 16 * k + P.q, P.epoch);
+    if (threadIdx.x == 0) *cnt = 0;  // ready for the next panel (kernel boundaries order this)
+  }
+}
+
+// a rank without tile rows below k still reports "done with panel k" (it has fetched the diagonal block)
+__global__ void k_chol_signal(int k, chol_peers P) {
+  if ((int)threadIdx.x < P.R) st_release_sys_u64(P.ctl[threadIdx.x] + CHOL_NBMAX + 16 * k + P.q, P.epoch);
+}
+
+// end of a distributed factorisation: every rank has reported every panel, i.e. all peer stores into this rank's
+// matrix have landed and nobody reads this rank's diagonal blocks any more (the matrix may be reused)
+__global__ void __launch_bounds__(256)
+k_chol_wait_all(int nb, chol_peers P, int* __restrict__ info) {
+  for (int e = threadIdx.x; e < nb * P.R; e += 256) {
+    const int k = e / P.R, r = e - k * P.R;
+    if (!wait_epoch(P.ctl[P.q] + CHOL_NBMAX + 16 * k + r, P.epoch)) atomicCAS(info, 0, -2);
+  }
+}
+
+// non-owners pull L_kk and Linv_kk from the owner of tile row k once its flag says they are complete
+__global__ void __launch_bounds__(256)
+k_chol_fetch_diag(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Dinv, chol_peers P, int owner,
+                  int* __restrict__ info) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = wait_epoch(P.ctl[P.q] + k, P.epoch) ? 1 : 0;
+  __syncthreads();
+  if (!ok) {
+    if (threadIdx.x == 0) atomicCAS(info, 0, -2);
+    return;
+  }
+  const int64_t base = (int64_t)k * CT * ld + (int64_t)k * CT;
+  const double* sL = P.S[owner] + base;
+  const double* sD = P.D[owner] + (int64_t)k * CT * CT;
+  double* dD = Dinv + (int64_t)k * CT * CT;
+  const int n2 = CT * CT / 2;  // double2 items per block
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < 2 * n2; e += gridDim.x * 256) {
+    if (e < n2) {
+      const int r = e >> 6, c2 = e & 63;
+      *reinterpret_cast<double2*>(A + base + (int64_t)r * ld + 2 * c2) =
+          ld_volatile_d2(reinterpret_cast<const double2*>(sL + (int64_t)r * ld + 2 * c2));
+    } else {
+      const int f = e - n2;
+      *reinterpret_cast<double2*>(dD + 2 * f) = ld_volatile_d2(reinterpret_cast<const double2*>(sD + 2 * f));
+    }
+  }
 }
 
 // ---- diagonal block -------------------------------------------------------------------------------------
@@ -206,7 +314,7 @@ __device__ __forceinline__ void po_gemm(int m, int npair, const double* a0, int 
 // A_kk (lower) <- L_kk, Dinv[k] <- L_kk^-1.  info: first non-positive pivot (1-based global index), else untouched.
 __global__ void __launch_bounds__(PO_THREADS, 1)
 k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Dinv, int* __restrict__ info,
-             long long* __restrict__ prof) {
+             long long* __restrict__ prof, chol_peers P) {
   extern __shared__ __align__(16) double smp[];
   long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = 0;  // phase cycle counts (BAGPU_POTRF_PROF; thread 0 only)
 #define PO_LAP(slot)                          \
@@ -362,6 +470,11 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
   if (prof && threadIdx.x == 0)
     for (int i = 0; i < 8; ++i) prof[i] = tk[i];
 #undef PO_LAP
+  if (P.R > 1) {  // distributed: L_kk and Linv_kk are complete in this rank's memory -- every rank may fetch them
+    __threadfence_system();
+    __syncthreads();
+    if (tid < P.R) st_release_sys_u64(P.ctl[tid] + k, P.epoch);
+  }
 }
 
 // ---- substitution sweeps ----------------------------------------------------------------------------------
@@ -475,13 +588,19 @@ int chol_plan_init(ba_handle* h, chol_plan& P, int64_t cn) {
   BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_w), sizeof(double) * (size_t)cn));
   BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_x), sizeof(double) * (size_t)cn));
   BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_info), sizeof(int)));
-  BA_CUDA(cudaStreamCreateWithFlags(&P.side, cudaStreamNonBlocking));
+  {  // the panel stream must get SMs while the trailing update fills the machine: highest priority
+    int lo = 0, hi = 0;
+    BA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    BA_CUDA(cudaStreamCreateWithPriority(&P.side, cudaStreamNonBlocking, hi));
+  }
   BA_CUDA(cudaEventCreateWithFlags(&P.ev_col, cudaEventDisableTiming));
   BA_CUDA(cudaEventCreateWithFlags(&P.ev_panel, cudaEventDisableTiming));
   BA_CUDA(cudaEventCreateWithFlags(&P.ev_join, cudaEventDisableTiming));
   // per device (a process may hold handles on several devices): set once per plan
-  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  BA_CUDA(cudaFuncSetAttribute(k_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_trsm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_trsm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   BA_CUDA(cudaFuncSetAttribute(k_chol_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM));
   P.attrs_set = true;
   return BA_OK;
@@ -495,6 +614,12 @@ void chol_plan_release(chol_plan& P) {
   cudaFree(P.d_x);
   cudaFree(P.d_info);
   cudaFree(P.d_prof);
+  cudaFree(P.d_ctl);
+  cudaFree(P.d_cnt);
+  for (int r = 0; r < CHOL_RMAX; ++r)
+    if (P.peer_ipc[r])
+      for (int j = 0; j < 3; ++j)
+        if (P.peer_open[3 * r + j]) cudaIpcCloseMemHandle(P.peer_open[3 * r + j]);
   if (P.solve_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(P.solve_graph));
   if (P.side) cudaStreamDestroy(P.side);
   if (P.ev_col) cudaEventDestroy(P.ev_col);
@@ -507,6 +632,8 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
   const int64_t cn = P.cn, ld = cn;
   const int nb = (int)(cn / CT);
   static const bool no_lookahead = getenv("BAGPU_CHOL_NO_LOOKAHEAD") != nullptr;
+  chol_peers solo = {};
+  solo.R = 1;
   BA_CUDA(cudaMemsetAsync(P.d_info, 0, sizeof(int), s));
   static const bool want_prof = getenv("BAGPU_POTRF_PROF") != nullptr;
   long long* prof = nullptr;
@@ -514,25 +641,25 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
     if (!P.d_prof) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_prof), 8 * sizeof(long long)));
     prof = P.d_prof;
   }
-  k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, 0, P.d_Dinv, P.d_info, prof);
-  if (nb > 1) k_chol_trsm<<<2 * (nb - 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, 0, P.d_Dinv);
+  k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, 0, P.d_Dinv, P.d_info, prof, solo);
+  if (nb > 1) k_chol_trsm<false><<<2 * (nb - 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, 0, P.d_Dinv, 0, solo, nullptr);
   for (int k = 0; k + 1 < nb; ++k) {
     // panel k is final in A[k+1:, k].  Column k+1 of the trailing matrix first ...
-    k_chol_syrk<<<dim3(2 * (nb - k - 1), 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 1, nb);
+    k_chol_syrk<false><<<dim3(2 * (nb - k - 1), 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 1, nb, 0, solo, nullptr);
     const bool rest = k + 2 < nb;
     if (rest && !no_lookahead) {
       // ... then panel k+1 (potrf + trsm) on the side stream, under the rest of the update
       BA_CUDA(cudaEventRecord(P.ev_col, s));
       BA_CUDA(cudaStreamWaitEvent(P.side, P.ev_col, 0));
-      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv, P.d_info, nullptr);
-      k_chol_trsm<<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv);
+      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv, P.d_info, nullptr, solo);
+      k_chol_trsm<false><<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv, 0, solo, nullptr);
       BA_CUDA(cudaEventRecord(P.ev_panel, P.side));
-      k_chol_syrk<<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb);
+      k_chol_syrk<false><<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb, 0, solo, nullptr);
       BA_CUDA(cudaStreamWaitEvent(s, P.ev_panel, 0));
     } else {
-      if (rest) k_chol_syrk<<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb);
-      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, k + 1, P.d_Dinv, P.d_info, nullptr);
-      if (rest) k_chol_trsm<<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k + 1, P.d_Dinv);
+      if (rest) k_chol_syrk<false><<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb, 0, solo, nullptr);
+      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, k + 1, P.d_Dinv, P.d_info, nullptr, solo);
+      if (rest) k_chol_trsm<false><<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k + 1, P.d_Dinv, 0, solo, nullptr);
     }
   }
   BA_CUDA(cudaGetLastError());
@@ -551,6 +678,125 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
       return BA_ERR_NUMERIC;
     }
   }
+  return BA_OK;
+}
+
+// ---- distributed factorisation ------------------------------------------------------------------------------
+namespace {
+struct peer_record {  // what the ranks exchange (NCCL all-gather of the raw bytes)
+  long long pid;
+  int device, ok;
+  void *S, *D, *ctl;
+  cudaIpcMemHandle_t hS, hD, hC;
+};
+}  // namespace
+
+int chol_dist_setup(ba_handle* h, chol_plan& P, double* A) {
+  P.dist_ready = false;
+  static const bool off = getenv("BAGPU_CHOL_REPLICATED") != nullptr || getenv("BAGPU_NO_P2P") != nullptr;
+  const int R = h->nranks;
+  if (R < 2 || R > CHOL_RMAX || !h->comm || P.cn / CT > CHOL_NBMAX) return BA_OK;
+  BA_CUDA(cudaSetDevice(h->device));
+  const size_t ctl_n = (size_t)CHOL_NBMAX * (1 + 16);
+  if (!P.d_ctl) {
+    BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_ctl), ctl_n * sizeof(unsigned long long)));
+    BA_CUDA(cudaMemset(P.d_ctl, 0, ctl_n * sizeof(unsigned long long)));
+    BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_cnt), sizeof(int)));
+    BA_CUDA(cudaMemset(P.d_cnt, 0, sizeof(int)));
+  }
+  peer_record mine = {};
+  mine.pid = (long long)getpid();
+  mine.device = h->device;
+  mine.S = A; mine.D = P.d_Dinv; mine.ctl = P.d_ctl;
+  mine.ok = off ? 0 : 1;
+  if (mine.ok && (cudaIpcGetMemHandle(&mine.hS, A) != cudaSuccess || cudaIpcGetMemHandle(&mine.hD, P.d_Dinv) != cudaSuccess ||
+                  cudaIpcGetMemHandle(&mine.hC, P.d_ctl) != cudaSuccess)) {
+    cudaGetLastError();
+    mine.ok = 0;
+  }
+  std::vector<peer_record> all((size_t)R);
+  int rc = allgather_host(h, &mine, all.data(), sizeof(peer_record));
+  if (rc) return rc;
+  int ok = 1;
+  for (const peer_record& p : all) ok &= p.ok;
+  chol_peers V = {};
+  V.R = R; V.q = h->rank; V.epoch = 0;
+  if (ok) {
+    for (int r = 0; r < R && ok; ++r) {
+      const peer_record& p = all[(size_t)r];
+      if (r == h->rank) {
+        V.S[r] = A; V.D[r] = P.d_Dinv; V.ctl[r] = P.d_ctl;
+      } else if (p.pid == mine.pid) {  // same process (ba_create_multi): raw pointers + peer access
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, h->device, p.device) != cudaSuccess || !can) { ok = 0; break; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(p.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; break; }
+        cudaGetLastError();
+        V.S[r] = static_cast<double*>(p.S); V.D[r] = static_cast<double*>(p.D);
+        V.ctl[r] = static_cast<unsigned long long*>(p.ctl);
+      } else {
+        void *a = nullptr, *b = nullptr, *c = nullptr;
+        if (cudaIpcOpenMemHandle(&a, p.hS, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&b, p.hD, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&c, p.hC, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = 0;
+          break;
+        }
+        P.peer_ipc[r] = true;
+        P.peer_open[3 * r] = a; P.peer_open[3 * r + 1] = b; P.peer_open[3 * r + 2] = c;
+        V.S[r] = static_cast<double*>(a); V.D[r] = static_cast<double*>(b);
+        V.ctl[r] = static_cast<unsigned long long*>(c);
+      }
+    }
+  }
+  // every rank must take the same path: agree on the outcome
+  int mine_ok = ok;
+  std::vector<int> oks((size_t)R);
+  if ((rc = allgather_host(h, &mine_ok, oks.data(), sizeof(int)))) return rc;
+  for (int v : oks) ok &= v;
+  if (!ok) return BA_OK;  // replicated factorisation
+  P.peers = V;
+  P.dist_ready = true;
+  return BA_OK;
+}
+
+int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) {
+  const int64_t cn = P.cn, ld = cn;
+  const int nb = (int)(cn / CT);
+  chol_peers& V = P.peers;
+  const int R = V.R, q = V.q;
+  V.epoch += 1;  // the same count on every rank: all of them factorise the same sequence of matrices
+  auto first_own = [&](int from) { return from + (((q - from) % R) + R) % R; };          // first own tile row >= from
+  auto count_own = [&](int from) { const int i0 = first_own(from); return i0 < nb ? (nb - 1 - i0) / R + 1 : 0; };
+  BA_CUDA(cudaMemsetAsync(P.d_info, 0, sizeof(int), s));
+  // diagonal block k and the panel below it, on stream st
+  auto panel = [&](int k, cudaStream_t st) {
+    if (k % R == q) k_chol_potrf<<<1, PO_THREADS, PO_SMEM, st>>>(A, ld, k, P.d_Dinv, P.d_info, nullptr, V);
+    else k_chol_fetch_diag<<<16, 256, 0, st>>>(A, ld, k, P.d_Dinv, V, k % R, P.d_info);
+    const int n = count_own(k + 1);
+    if (n > 0) k_chol_trsm<true><<<2 * n, GEMM_THREADS, GEMM_SMEM, st>>>(A, ld, k, P.d_Dinv, first_own(k + 1), V, P.d_cnt);
+    else k_chol_signal<<<1, 32, 0, st>>>(k, V);
+  };
+  panel(0, s);
+  for (int k = 0; k + 1 < nb; ++k) {
+    // own tiles of column k + 1 first (they gate the next panel), then the next panel on the side stream under
+    // the rest of this rank's trailing update
+    const int nc = count_own(k + 1);
+    if (nc > 0)
+      k_chol_syrk<true><<<dim3(2 * nc, 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 1, nb, first_own(k + 1), V, P.d_info);
+    BA_CUDA(cudaEventRecord(P.ev_col, s));
+    BA_CUDA(cudaStreamWaitEvent(P.side, P.ev_col, 0));
+    panel(k + 1, P.side);
+    BA_CUDA(cudaEventRecord(P.ev_panel, P.side));
+    const int nr = count_own(k + 2);
+    if (nr > 0 && k + 2 < nb)
+      k_chol_syrk<true><<<dim3(2 * nr, nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb, first_own(k + 2), V,
+                                                                                P.d_info);
+    BA_CUDA(cudaStreamWaitEvent(s, P.ev_panel, 0));
+  }
+  k_chol_wait_all<<<1, 256, 0, s>>>(nb, V, P.d_info);
+  BA_CUDA(cudaGetLastError());
   return BA_OK;
 }
 

@@ -15,6 +15,21 @@ constexpr int CHOL_TILE = 128;  // block size of the factorisation; matrices are
 
 inline int64_t chol_padded(int64_t n) { return (n + CHOL_TILE - 1) / CHOL_TILE * CHOL_TILE; }
 
+constexpr int CHOL_NBMAX = 160;   // tile rows at most (cn <= 20480)
+constexpr int CHOL_RMAX = 16;     // ranks at most in the distributed factorisation
+
+// Peer view of the distributed factorisation: every rank's copy of the matrix, of the diagonal-block inverses and
+// of the control block (flags), addressable from this rank's device (CUDA IPC mappings or raw in-process pointers).
+// Control block of a rank (unsigned long long): [k] = epoch once Linv_kk / L_kk of step k may be fetched from the
+// owner of tile row k; [CHOL_NBMAX + 16 k + r] = epoch once rank r's tiles of panel k have landed in this rank's matrix.
+struct chol_peers {
+  double* S[CHOL_RMAX];
+  double* D[CHOL_RMAX];
+  unsigned long long* ctl[CHOL_RMAX];
+  int R, q;
+  unsigned long long epoch;
+};
+
 // Workspace of one factorisation: the matrix itself is owned by the caller.
 struct chol_plan {
   int64_t cn = 0;            // padded order (multiple of CHOL_TILE)
@@ -31,6 +46,13 @@ struct chol_plan {
   const void* solve_graph_A = nullptr;
   bool graph_off = false;        // capture not possible on the caller's stream
   bool attrs_set = false;
+  // distributed factorisation over the ranks of a sharded handle (tile row i belongs to rank i mod R)
+  bool dist_ready = false;
+  chol_peers peers = {};
+  unsigned long long* d_ctl = nullptr;  // own control block
+  int* d_cnt = nullptr;                 // CTAs of the current panel solve that have finished (last one signals)
+  bool peer_ipc[CHOL_RMAX] = {};
+  void* peer_open[3 * CHOL_RMAX] = {};  // IPC mappings to close
 };
 
 int chol_plan_init(ba_handle* h, chol_plan& P, int64_t cn);
@@ -38,6 +60,14 @@ void chol_plan_release(chol_plan& P);
 // A (cn x cn, row-major, leading dimension cn, lower triangle) <- L with A = L L'.  Returns BA_OK and leaves
 // *info_host = 0, or the 1-based index of the first non-positive pivot (BA_ERR_NUMERIC).
 int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info_host);
+// Collective over the ranks of a sharded handle (needs its NCCL communicator): exchange the addresses of A, the
+// diagonal-block inverses and the control blocks (CUDA IPC between processes, raw pointers + peer access inside one
+// process).  Leaves P.dist_ready false (replicated factorisation) when peer access is not available on every rank.
+int chol_dist_setup(ba_handle* h, chol_plan& P, double* A);
+// Right-looking factorisation distributed over the ranks: each rank updates its own tile rows; panels travel by
+// peer-memory stores fused into the panel-solve kernel, diagonal blocks are pulled from their owner; flags over
+// NVLink order the steps.  On return every rank holds the complete factor (the sweeps run replicated).
+int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s);
 // x <- (L L')^-1 b for one right-hand side (b and x: cn doubles on the device, may alias).
 int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, double* x, cudaStream_t s);
 

@@ -21,6 +21,7 @@ typedef int (*fn_get_uid)(nccl_uid*);
 typedef int (*fn_comm_init_rank)(ncclComm**, int, nccl_uid, int);
 typedef int (*fn_comm_destroy)(ncclComm*);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int /*dtype*/, int /*op*/, ncclComm*, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int /*dtype*/, ncclComm*, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
 constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
 
@@ -30,6 +31,7 @@ struct nccl_api {
   fn_comm_init_rank init_rank = nullptr;
   fn_comm_destroy destroy = nullptr;
   fn_allreduce allreduce = nullptr;
+  fn_allgather allgather = nullptr;
   fn_errstr errstr = nullptr;
   bool ok = false;
 };
@@ -47,6 +49,7 @@ nccl_api& api() {
   a.init_rank = (fn_comm_init_rank)dlsym(a.so, "ncclCommInitRank");
   a.destroy = (fn_comm_destroy)dlsym(a.so, "ncclCommDestroy");
   a.allreduce = (fn_allreduce)dlsym(a.so, "ncclAllReduce");
+  a.allgather = (fn_allgather)dlsym(a.so, "ncclAllGather");
   a.errstr = (fn_errstr)dlsym(a.so, "ncclGetErrorString");
   a.ok = a.get_uid && a.init_rank && a.destroy && a.allreduce;
   return a;
@@ -82,6 +85,31 @@ int allreduce_sum_i64(ba_handle* h, long long* buf, size_t n) {
     h->err = std::string("ncclAllReduce: ") + (api().errstr ? api().errstr(rc) : "error");
     return BA_ERR_COMM;
   }
+  return BA_OK;
+}
+
+// host-side all-gather of `bytes` per rank (small control records: IPC handles, pointers); synchronises the stream
+int allgather_host(ba_handle* h, const void* send, void* recv, size_t bytes) {
+  if (h->nranks == 1) {
+    memcpy(recv, send, bytes);
+    return BA_OK;
+  }
+  if (!h->comm || !api().allgather) {
+    h->err = "sharded handle used before ba_comm_init";
+    return BA_ERR_COMM;
+  }
+  char* d = nullptr;
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), bytes * (size_t)(h->nranks + 1)));
+  BA_CUDA(cudaMemcpyAsync(d, send, bytes, cudaMemcpyHostToDevice, h->stream));
+  const int rc = api().allgather(d, d + bytes, bytes, 0 /* ncclInt8 */, h->comm, h->stream);
+  if (rc != 0) {
+    cudaFree(d);
+    h->err = std::string("ncclAllGather: ") + (api().errstr ? api().errstr(rc) : "error");
+    return BA_ERR_COMM;
+  }
+  BA_CUDA(cudaMemcpyAsync(recv, d + bytes, bytes * (size_t)h->nranks, cudaMemcpyDeviceToHost, h->stream));
+  BA_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(d);
   return BA_OK;
 }
 

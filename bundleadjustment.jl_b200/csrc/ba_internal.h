@@ -198,5 +198,6 @@ int copy_to_host(ba_handle* h, void* dst, const void* src, size_t bytes);
 // ---- ba_comm.cu -----------------------------------------------------------------------------
 int allreduce_sum(ba_handle* h, double* buf, size_t n);
 int allreduce_sum_i64(ba_handle* h, long long* buf, size_t n);
+int allgather_host(ba_handle* h, const void* send, void* recv, size_t bytes);
 void comm_release(ba_handle* h);
 }  // namespace ba

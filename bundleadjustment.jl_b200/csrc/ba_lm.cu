@@ -31,6 +31,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include "ba_internal.h"
 #include "ba_math.cuh"
 #include "ba_ritz.h"
@@ -123,13 +124,40 @@ int lm_prepare(ba_handle* h) {
     S.ntasks = (int64_t)tstart.size();
     tstart.push_back((int32_t)nl);
   }
-  // ---- camera-major order (stable counting sort) and tasks
+  // ---- camera-major order (stable counting sort) and tasks.  The sort runs on a few host threads: thread t
+  // counts the cameras of its contiguous chunk of observations, the (camera, chunk) counts are turned into start
+  // positions, and every thread scatters its own chunk -- stable, hence deterministic.
   std::vector<int32_t> cam_start((size_t)ncams + 1, 0), cperm((size_t)nl), tb, te, tc, cam_t0((size_t)ncams + 1, 0);
-  for (int64_t k = 0; k < nl; ++k) cam_start[(size_t)h->h_cam[(size_t)k] + 1]++;
-  for (int64_t c = 0; c < ncams; ++c) cam_start[(size_t)c + 1] += cam_start[(size_t)c];
   {
-    std::vector<int32_t> fill(cam_start.begin(), cam_start.end() - 1);
-    for (int64_t k = 0; k < nl; ++k) cperm[(size_t)fill[(size_t)h->h_cam[(size_t)k]]++] = (int32_t)k;
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), 8, nl / 200000 + 1}));
+    std::vector<std::vector<int32_t>> cnt((size_t)nt, std::vector<int32_t>((size_t)ncams, 0));
+    auto chunk = [&](int t) { return std::pair<int64_t, int64_t>(nl * t / nt, nl * (t + 1) / nt); };
+    auto par = [&](const std::function<void(int)>& f) {
+      std::vector<std::thread> th;
+      for (int t = 1; t < nt; ++t) th.emplace_back(f, t);
+      f(0);
+      for (auto& x : th) x.join();
+    };
+    par([&](int t) {
+      const auto r = chunk(t);
+      int32_t* c = cnt[(size_t)t].data();
+      for (int64_t k = r.first; k < r.second; ++k) c[h->h_cam[(size_t)k]]++;
+    });
+    int32_t run = 0;
+    for (int64_t c = 0; c < ncams; ++c) {
+      cam_start[(size_t)c] = run;
+      for (int t = 0; t < nt; ++t) {
+        const int32_t n = cnt[(size_t)t][(size_t)c];
+        cnt[(size_t)t][(size_t)c] = run;  // becomes the write cursor of (chunk t, camera c)
+        run += n;
+      }
+    }
+    cam_start[(size_t)ncams] = run;
+    par([&](int t) {
+      const auto r = chunk(t);
+      int32_t* cur = cnt[(size_t)t].data();
+      for (int64_t k = r.first; k < r.second; ++k) cperm[(size_t)cur[h->h_cam[(size_t)k]]++] = (int32_t)k;
+    });
   }
   int tsz = 32;  // observations per camera task: enough tasks to fill 148 SMs, at most 256 per warp
   while (tsz < 256 && nl / tsz > 148 * 64) tsz *= 2;
@@ -235,6 +263,8 @@ int lm_prepare(ba_handle* h) {
     ALLOC(S.d_cd, 9 * ncams);
     ALLOC(S.d_ex, 2 * S.cn);
     if ((rc = chol_plan_init(h, S.chol, S.cn))) return rc;
+    // sharded: distribute the factorisation over the ranks (collective; falls back to the replicated one)
+    if (h->nranks > 1 && (rc = chol_dist_setup(h, S.chol, S.d_S))) return rc;
   }
 #undef ALLOC
   // opt-in shared-memory sizes are per device: set them for this handle's device
@@ -250,9 +280,7 @@ int lm_prepare(ba_handle* h) {
   BA_CUDA(up(S.d_tstart, tstart.data(), tstart.size() * 4));
   BA_CUDA(up(S.d_pstart, pstart.data(), pstart.size() * 4));
   BA_CUDA(up(S.d_cperm, cperm.data(), cperm.size() * 4));
-  std::vector<int32_t> pntc((size_t)nl);
-  for (int64_t i = 0; i < nl; ++i) pntc[(size_t)i] = h->h_pnt[(size_t)cperm[(size_t)i]];
-  BA_CUDA(up(S.d_pntc, pntc.data(), pntc.size() * 4));
+  if (nl) k_gather_i32<<<nblk(nl, 256), 256, 0, h->stream>>>(nl, S.d_cperm, h->d_pnt, S.d_pntc);  // point id at each camera-major position
   BA_CUDA(up(S.d_ctask_beg, tb.data(), tb.size() * 4));
   BA_CUDA(up(S.d_ctask_end, te.data(), te.size() * 4));
   BA_CUDA(up(S.d_cam_t0, cam_t0.data(), cam_t0.size() * 4));
@@ -403,10 +431,14 @@ struct Solver {
     if ((rc = check())) return rc;
     cudaEventRecord(S.ev[6], s);
     int info = 0;
-    if ((rc = chol_factor(h, S.chol, S.d_S, s, nullptr))) return rc;
+    if ((rc = S.chol.dist_ready ? chol_factor_dist(h, S.chol, S.d_S, s) : chol_factor(h, S.chol, S.d_S, s, nullptr))) return rc;
     cudaEventRecord(S.ev[7], s);
     BA_CUDA(cudaMemcpyAsync(&info, S.chol.d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
     if ((rc = read_scalars())) return rc;  // synchronises: pivot check + S_ERR
+    if (info == -2) {
+      h->err = "distributed Cholesky: a peer's flag never arrived (a rank is missing or stalled)";
+      return BA_ERR_COMM;
+    }
     if (info != 0) {
       h->err = "Cholesky of the reduced camera system: non-positive pivot";
       return BA_ERR_NUMERIC;
@@ -419,8 +451,9 @@ struct Solver {
     S.chol_count += 1;
     if (tr) {
       const double fl = (double)cn * cn * cn / 3.0;
-      fprintf(stderr, "[bagpu] exact factor: assembly of S (%lld x %lld) %.2f ms, Cholesky %.2f ms (%.1f TFLOP/s)\n",
-              (long long)cn, (long long)cn, ta, tc, fl / (tc * 1e-3) / 1e12);
+      fprintf(stderr, "[bagpu] exact factor: assembly of S (%lld x %lld) %.2f ms, Cholesky %.2f ms (%.1f TFLOP/s%s)\n",
+              (long long)cn, (long long)cn, ta, tc, fl / (tc * 1e-3) / 1e12,
+              S.chol.dist_ready ? ", distributed over the ranks" : "");
     }
     if (S.h_scal[S_ERR] != 0.0) {
       h->err = "Schur diagonal block not positive definite";

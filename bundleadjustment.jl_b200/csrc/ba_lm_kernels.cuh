@@ -1678,6 +1678,13 @@ k_exact_resid(int64_t n9, int64_t cn, const double* __restrict__ b, const double
   }
 }
 
+// out[i] = src[idx[i]]
+__global__ void __launch_bounds__(256)
+k_gather_i32(int64_t n, const int32_t* __restrict__ idx, const int32_t* __restrict__ src, int32_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x;
+  if (i < n) out[i] = __ldg(src + __ldg(idx + i));
+}
+
 __global__ void k_seq_inc(unsigned long long* seqp) { *seqp += 1; }
 
 __global__ void k_copy_cam_delta(int64_t n9, const double* __restrict__ xc, double* __restrict__ delta_c) {
