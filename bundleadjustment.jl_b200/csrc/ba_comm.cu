@@ -211,7 +211,9 @@ int ba_comm_init(ba_handle* h, const uint8_t id128[128]) {
       if (n && !wrc) wrc = ba::allreduce_sum(h, warm, n);
   BA_CUDA(cudaStreamSynchronize(h->stream));
   cudaFree(warm);
-  return wrc;
+  if (wrc) return wrc;
+  // the exact solve's workspace and the peer mappings of its distributed factorisation belong to the communicator
+  return ba::lm_exact_workspace(h);
 }
 
 int ba_comm_ipc_export(ba_handle* h, uint8_t handle64[64]) {

@@ -86,7 +86,8 @@ struct ba_lm_state {
   // ---- exact solve: explicit reduced camera system + dense Cholesky (ba_chol.cu) ---------------------
   bool exact = false;         // decided in lm_prepare from ba_handle::solver and the problem size
   int64_t cn = 0;             // 9 ncams padded to a multiple of 128
-  double* d_S = nullptr;      // cn x cn row-major: fixed-point sums, then the scaled matrix, then its factor L
+  double* d_S = nullptr;      // cn x cn row-major: the scaled matrix, then its factor L
+  long long* d_Sq = nullptr;  // packed lower-triangular tiles: fixed-point sums of the off-diagonal blocks
   double* d_Yh = nullptr;     // 27 per local observation: D_c^-1 (B'A) L_p
   double* d_cd = nullptr;     // 9 ncams: sqrt(diag(U + lambda I)), the Jacobi scaling
   double* d_ex = nullptr;     // 2 vectors of cn: scaled right-hand side / residual, scaled solution
@@ -175,6 +176,7 @@ void launch_jtprod(const ba_handle* h, const double* x, const double* camtab, co
                    bool with_cameras, cudaStream_t s);
 // ---- ba_lm.cu -------------------------------------------------------------------------------
 int lm_prepare(ba_handle* h);
+int lm_exact_workspace(ba_handle* h);  // dense matrix + (distributed) factorisation workspace of the exact solve
 // camera part of J(x)'v by the ordered camera-major pass (needs point-major observations; h->d_camtab must
 // hold the records of x): Jtv_cams = sum_k B_k' v_k, 9 per camera
 int lm_jtprod_cams(ba_handle* h, const double* x, const double* v, double* Jtv_cams);

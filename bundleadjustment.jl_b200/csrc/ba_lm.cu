@@ -78,6 +78,40 @@ constexpr int DEFL_NR = 4;      // vectors per pass of the multi-vector Schur pr
 
 }  // namespace
 
+// Decide whether the damped solve of this handle is the exact one and, if so, allocate the dense matrix and the
+// factorisation workspace; on a sharded handle with a communicator also exchange the peer addresses of the
+// distributed factorisation (collective over the ranks).  Called from lm_prepare, and ahead of time from
+// ba_comm_init / ba_create_multi so that this one-off setup (CUDA IPC mappings of every peer's matrix) is part of
+// creating the communicator rather than of the first Levenberg_Marquardt call.
+int lm_exact_workspace(ba_handle* h) {
+  ba_lm_state& S = h->lm;
+  const int64_t ncams = h->ncams;
+  if (S.d_S) return BA_OK;
+  BA_CUDA(cudaSetDevice(h->device));
+  // auto = up to EXACT_AUTO_CAMS cameras (the factorisation is n^3/3 flops)
+  S.exact = h->sorted && ncams > 0 &&
+            (h->solver == BA_SOLVER_EXACT || (h->solver == BA_SOLVER_AUTO && ncams <= exact_auto_cams()));
+  S.cn = chol_padded(9 * ncams);
+  if (S.exact && (double)S.cn * (double)S.cn * 8.0 > exact_max_bytes()) {
+    if (h->solver == BA_SOLVER_EXACT) {
+      h->err = "BA_SOLVER_EXACT: the dense reduced camera system does not fit (raise BAGPU_EXACT_MAX_GB or use PCG)";
+      return BA_ERR_ARG;
+    }
+    S.exact = false;
+  }
+  if (!S.exact) return BA_OK;
+  int rc;
+  if ((rc = dmalloc(h, &S.d_S, (size_t)(S.cn * S.cn)))) return rc;
+  {
+    const int64_t nbt = S.cn / CHOL_TILE;
+    if ((rc = dmalloc(h, &S.d_Sq, (size_t)(nbt * (nbt + 1) / 2 * CHOL_TILE * CHOL_TILE)))) return rc;
+  }
+  if ((rc = chol_plan_init(h, S.chol, S.cn))) return rc;
+  // sharded: distribute the factorisation over the ranks (falls back to the replicated one without peer access)
+  if (h->nranks > 1 && h->comm && (rc = chol_dist_setup(h, S.chol, S.d_S))) return rc;
+  return BA_OK;
+}
+
 int lm_prepare(ba_handle* h) {
   ba_lm_state& S = h->lm;
   if (S.ready) return BA_OK;
@@ -243,28 +277,11 @@ int lm_prepare(ba_handle* h) {
   S.npart = 4 * (int64_t)std::max<int64_t>(nblk(std::max(nl, npl), PT_THREADS), 1024);
   ALLOC(S.d_part, S.npart + 16);  // + scratch for the four step norms
   ALLOC(S.d_scal, S_COUNT);
-  // exact solve: auto = up to EXACT_AUTO_CAMS cameras (the factorisation is n^3/3 flops on a replicated matrix)
-  S.exact = h->solver == BA_SOLVER_EXACT || (h->solver == BA_SOLVER_AUTO && ncams <= exact_auto_cams());
-  S.cn = chol_padded(9 * ncams);
-  if (S.exact && ncams > 0) {
-    if ((double)S.cn * (double)S.cn * 8.0 > exact_max_bytes()) {
-      if (h->solver == BA_SOLVER_EXACT) {
-        h->err = "BA_SOLVER_EXACT: the dense reduced camera system does not fit (raise BAGPU_EXACT_MAX_GB or use PCG)";
-        return BA_ERR_ARG;
-      }
-      S.exact = false;
-    }
-  } else {
-    S.exact = false;
-  }
+  if ((rc = lm_exact_workspace(h))) return rc;
   if (S.exact) {
-    ALLOC(S.d_S, S.cn * S.cn);
     ALLOC(S.d_Yh, 27 * nl);
     ALLOC(S.d_cd, 9 * ncams);
     ALLOC(S.d_ex, 2 * S.cn);
-    if ((rc = chol_plan_init(h, S.chol, S.cn))) return rc;
-    // sharded: distribute the factorisation over the ranks (collective; falls back to the replicated one)
-    if (h->nranks > 1 && (rc = chol_dist_setup(h, S.chol, S.d_S))) return rc;
   }
 #undef ALLOC
   // opt-in shared-memory sizes are per device: set them for this handle's device
@@ -321,7 +338,7 @@ void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,
                   S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
-                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_Z, S.d_Zcand, S.d_harv, S.d_hcoef, S.d_zpart, S.d_dsmall, S.d_w4, S.d_q4, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal, S.d_S, S.d_Yh, S.d_cd, S.d_ex};
+                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_Z, S.d_Zcand, S.d_harv, S.d_hcoef, S.d_zpart, S.d_dsmall, S.d_w4, S.d_q4, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal, S.d_S, S.d_Sq, S.d_Yh, S.d_cd, S.d_ex};
   for (void* p : ptrs) cudaFree(p);
   chol_plan_release(S.chol);
   if (S.h_scal) cudaFreeHost(S.h_scal);
@@ -420,14 +437,15 @@ struct Solver {
     k_exact_diag<<<nblk(n9, 256), 256, 0, s>>>(n9, lambda, S.d_Ug, S.d_cd);
     k_exact_y<<<nblk(nl, PT_THREADS), PT_THREADS, 0, s>>>(h->d_cam, h->d_pnt, h->pnt0, nl, S.d_Jp, S.d_Vinv, S.d_cd,
                                                           S.d_Yh);
-    BA_CUDA(cudaMemsetAsync(S.d_S, 0, sizeof(double) * (size_t)(cn * cn), s));
+    const int64_t nbt = cn / CHOL_TILE, packed = nbt * (nbt + 1) / 2 * CHOL_TILE * CHOL_TILE;
+    BA_CUDA(cudaMemsetAsync(S.d_Sq, 0, sizeof(long long) * (size_t)packed, s));
     if ((rc = check())) return rc;
     if (nl > 0)
       k_exact_assemble<<<(unsigned)std::min<int64_t>(nblk(nl, 8), 148 * 16), 256, 0, s>>>(
-          S.d_pstart, h->d_pnt, h->pnt0, h->d_cam, nl, S.d_Yh, reinterpret_cast<unsigned long long*>(S.d_S), cn);
+          S.d_pstart, h->d_pnt, h->pnt0, h->d_cam, nl, S.d_Yh, reinterpret_cast<unsigned long long*>(S.d_Sq));
     if ((rc = check())) return rc;
-    if ((rc = allreduce_sum_i64(h, reinterpret_cast<long long*>(S.d_S), (size_t)(cn * cn)))) return rc;
-    k_exact_finish<<<dim3(nblk(cn, 256), (unsigned)cn), 256, 0, s>>>(n9, cn, S.d_H, S.d_Cr, S.d_cd, S.d_S);
+    if ((rc = allreduce_sum_i64(h, S.d_Sq, (size_t)packed))) return rc;
+    k_exact_finish<<<dim3(nblk(cn, 256), (unsigned)cn), 256, 0, s>>>(n9, cn, S.d_H, S.d_Cr, S.d_cd, S.d_Sq, S.d_S);
     if ((rc = check())) return rc;
     cudaEventRecord(S.ev[6], s);
     int info = 0;

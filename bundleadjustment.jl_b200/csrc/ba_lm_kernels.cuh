@@ -1525,6 +1525,13 @@ k_defl_gram(int64_t n9, int N, const double* __restrict__ Y, double* __restrict_
 // ---------------------------------------------------------------------------------------------
 constexpr double EX_SCALE = 2305843009213693952.0;  // 2^61
 
+// The fixed-point sums live in a PACKED lower-triangular layout of 128 x 128 tiles (tile (ti, tj), tj <= ti, at
+// (ti (ti + 1) / 2 + tj) * 128 * 128, row-major inside): half the bytes to clear and to sum over the ranks.
+__device__ __forceinline__ int64_t ex_packed(int64_t r, int64_t c) {
+  const int64_t ti = r >> 7, tj = c >> 7;
+  return ((ti * (ti + 1) / 2 + tj) << 14) + ((r & 127) << 7) + (c & 127);
+}
+
 // cd[i] = sqrt(U_ii + lambda) for the n9 camera unknowns
 __global__ void __launch_bounds__(256)
 k_exact_diag(int64_t n9, double lambda, const double* __restrict__ Ug, double* __restrict__ cd) {
@@ -1574,7 +1581,7 @@ k_exact_y(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_i
 __global__ void __launch_bounds__(256)
 k_exact_assemble(const int32_t* __restrict__ pstart, const int32_t* __restrict__ pnt_idx, int64_t pnt0,
                  const int32_t* __restrict__ cam_idx, int64_t nl, const double* __restrict__ Yh,
-                 unsigned long long* __restrict__ Sq, int64_t ld) {
+                 unsigned long long* __restrict__ Sq) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = blockIdx.x * (int64_t)8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
   const int la = lane < 27 ? lane : 0;
@@ -1606,17 +1613,17 @@ k_exact_assemble(const int32_t* __restrict__ pstart, const int32_t* __restrict__
         }
         if (live) {
           const long long q = __double2ll_rn(v * EX_SCALE);
-          atomicAdd(Sq + ((int64_t)cr * 9 + i) * ld + (int64_t)cc * 9 + j, (unsigned long long)q);
+          atomicAdd(Sq + ex_packed((int64_t)cr * 9 + i, (int64_t)cc * 9 + j), (unsigned long long)q);
         }
       }
     }
   }
 }
 
-// fixed point -> double over the lower triangle, diagonal blocks added, identity on the padding; in place
+// packed fixed point -> row-major double over the lower triangle, diagonal blocks added, identity on the padding
 __global__ void __launch_bounds__(256)
 k_exact_finish(int64_t n9, int64_t cn, const double* __restrict__ H, const double* __restrict__ Cr,
-               const double* __restrict__ cd, double* S) {
+               const double* __restrict__ cd, const long long* __restrict__ Sq, double* __restrict__ S) {
   const int64_t r = blockIdx.y;
   const int64_t c = blockIdx.x * (int64_t)256 + threadIdx.x;
   if (c > r || c >= cn) return;
@@ -1625,8 +1632,7 @@ k_exact_finish(int64_t n9, int64_t cn, const double* __restrict__ H, const doubl
     *sp = (r == c) ? 1.0 : 0.0;
     return;
   }
-  const long long q = *reinterpret_cast<const long long*>(sp);
-  double v = -((double)q / EX_SCALE);
+  double v = -((double)Sq[ex_packed(r, c)] / EX_SCALE);
   const int64_t br = r / 9, bc = c / 9;
   if (br == bc) {
     const int i = (int)(r - 9 * br), j = (int)(c - 9 * bc);  // j <= i
