@@ -12,6 +12,10 @@
 // strided across the lanes of a warp, so each warp transposes its 32x24 tile through a padded
 // shared-memory buffer and writes 6144 contiguous bytes with 16-byte stores.  The same buffer first
 // stages the warp's 32 camera records, fetched cooperatively as whole 128-byte lines.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <cuda.h>  // CUtensorMap and the encoder's signature only: the entry point is resolved at run time
 #include "ba_internal.h"
 #include "ba_math.cuh"
 
@@ -52,14 +56,20 @@ __device__ __forceinline__ void load_cam(const double* __restrict__ camtab, int 
   }
 }
 
-template <bool WCX, bool WVALS>
+// TMA variant of the Jacobian store (TMA = true): the 32 x 24 values of a full warp are exactly 6144 contiguous
+// bytes of `vals`.  Seen as a 2-D tensor of 128-byte rows (16 doubles), they are a 48-row box; every lane drops
+// its 12 16-byte pieces into the warp's shared-memory tile at the positions the hardware 128-byte swizzle expects
+// (piece c of row R at R * 128 + ((c ^ (R & 7)) << 4): at most 2-way bank conflicts instead of the 4-way ones of a
+// dense tile), and ONE bulk tensor store per warp (cp.async.bulk.tensor, UTMASTG in SASS) moves the tile: no
+// transposed shared-memory reads and no per-lane global stores.  The last, partial warp keeps the generic path.
+template <bool WCX, bool WVALS, bool TMA>
 __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MINBLOCKS)
 k_eval(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
        const double2* __restrict__ pt2d, const double* __restrict__ xpts,
        const double* camtab, double* __restrict__ cx, double* __restrict__ vals,
-       int64_t nobs) {
-  constexpr int WROW = WVALS ? 32 * STAGE_ROW : 32 * CAM_ROW2;  // double2 per warp
-  __shared__ double2 stage[(EVAL_THREADS / 32) * WROW];
+       int64_t nobs, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int WROW = TMA ? 384 : (WVALS ? 32 * STAGE_ROW : 32 * CAM_ROW2);  // double2 per warp (TMA: 6144 B)
+  __shared__ __align__(1024) double2 stage[(EVAL_THREADS / 32) * WROW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t wbase = (blockIdx.x * (int64_t)(EVAL_THREADS / 32) + warp) * 32;
   if (wbase >= nobs) return;
@@ -90,33 +100,138 @@ k_eval(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
   if (WCX && valid) __stcs(reinterpret_cast<double2*>(cx) + k, make_double2(o.F[0], o.F[1]));
   if (WVALS) {
     __syncwarp();  // every lane has its camera record in registers: the buffer can be reused
-    // Transpose through shared memory with dense 192-byte rows and an XOR swizzle of the 16-byte column
-    // index by ((row >> 1) & 3): the per-lane row writes (row stride 12 words) and the transposed reads
-    // (32 consecutive words per instruction) are both bank-conflict free, because the swizzle only permutes
-    // words inside aligned groups of four.
-    double2* row = st + lane * STAGE_ROW;
-    const int sw = EVAL_SWIZZLE ? (lane >> 1) & 3 : 0;
     // reference order: row 1 = [A(3) B(9)], row 2 likewise; per-entry NaN -> 0
-    row[0 ^ sw] = make_double2(nan0(o.A[0]), nan0(o.A[1]));
-    row[1 ^ sw] = make_double2(nan0(o.A[2]), nan0(o.B[0]));
-    row[2 ^ sw] = make_double2(nan0(o.B[1]), nan0(o.B[2]));
-    row[3 ^ sw] = make_double2(nan0(o.B[3]), nan0(o.B[4]));
-    row[4 ^ sw] = make_double2(nan0(o.B[5]), nan0(o.B[6]));
-    row[5 ^ sw] = make_double2(nan0(o.B[7]), nan0(o.B[8]));
-    row[6 ^ sw] = make_double2(nan0(o.A[3]), nan0(o.A[4]));
-    row[7 ^ sw] = make_double2(nan0(o.A[5]), nan0(o.B[9]));
-    row[8 ^ sw] = make_double2(nan0(o.B[10]), nan0(o.B[11]));
-    row[9 ^ sw] = make_double2(nan0(o.B[12]), nan0(o.B[13]));
-    row[10 ^ sw] = make_double2(nan0(o.B[14]), nan0(o.B[15]));
-    row[11 ^ sw] = make_double2(nan0(o.B[16]), nan0(o.B[17]));
-    __syncwarp();
+    double2 v[12];
+    v[0] = make_double2(nan0(o.A[0]), nan0(o.A[1]));
+    v[1] = make_double2(nan0(o.A[2]), nan0(o.B[0]));
+    v[2] = make_double2(nan0(o.B[1]), nan0(o.B[2]));
+    v[3] = make_double2(nan0(o.B[3]), nan0(o.B[4]));
+    v[4] = make_double2(nan0(o.B[5]), nan0(o.B[6]));
+    v[5] = make_double2(nan0(o.B[7]), nan0(o.B[8]));
+    v[6] = make_double2(nan0(o.A[3]), nan0(o.A[4]));
+    v[7] = make_double2(nan0(o.A[5]), nan0(o.B[9]));
+    v[8] = make_double2(nan0(o.B[10]), nan0(o.B[11]));
+    v[9] = make_double2(nan0(o.B[12]), nan0(o.B[13]));
+    v[10] = make_double2(nan0(o.B[14]), nan0(o.B[15]));
+    v[11] = make_double2(nan0(o.B[16]), nan0(o.B[17]));
     const int nval = (int)min((int64_t)32, nobs - wbase);
+    if (TMA && nval == 32) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const int q = 12 * lane + j, R = q >> 3, cc = q & 7;
+        st[R * 8 + (cc ^ (R & 7))] = v[j];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(st);
+        const int row0 = (int)(wbase / 32) * 48;  // 128-byte row of vals where this warp's 6144 bytes start
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&tmap),
+                     "r"(0), "r"(row0), "r"(sa)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile has been read: the CTA may retire
+      }
+      return;
+    }
+    // generic path: transpose through shared memory (rows padded to 13 words, or dense rows with an XOR swizzle of
+    // the 16-byte column index by ((row >> 1) & 3)) and write 6144 contiguous bytes with 16-byte stores
+    constexpr int SROW = TMA ? 12 : STAGE_ROW;
+    double2* row = st + lane * SROW;
+    const int sw = (!TMA && EVAL_SWIZZLE) ? (lane >> 1) & 3 : 0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) row[j ^ sw] = v[j];
+    __syncwarp();
     double2* dst = reinterpret_cast<double2*>(vals) + wbase * 12;
 #pragma unroll
     for (int m = 0; m < 12; ++m) {
       const int q = lane + 32 * m;
       const int r = q / 12, cidx = q - 12 * r;
-      if (r < nval) __stcs(dst + q, st[r * STAGE_ROW + (EVAL_SWIZZLE ? cidx ^ ((r >> 1) & 3) : cidx)]);
+      if (r < nval) __stcs(dst + q, st[r * SROW + ((!TMA && EVAL_SWIZZLE) ? cidx ^ ((r >> 1) & 3) : cidx)]);
+    }
+  }
+}
+
+// Persistent variant: every warp walks over tiles of 32 observations (grid-stride) and loads the indices and the
+// observed pixel of its NEXT tile before it evaluates the current one, so that the DRAM round trip of the index
+// stream (the head of the dependent chain index -> gathers -> ~250 FP64 instructions -> stores) overlaps the
+// arithmetic instead of being paid once per tile at 28 % occupancy.
+template <bool WCX, bool WVALS>
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MINBLOCKS)
+k_eval_persist(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pnt_idx,
+               const double2* __restrict__ pt2d, const double* __restrict__ xpts, const double* camtab,
+               double* __restrict__ cx, double* __restrict__ vals, int64_t nobs) {
+  constexpr int WROW = WVALS ? 32 * STAGE_ROW : 32 * CAM_ROW2;  // double2 per warp
+  __shared__ double2 stage[(EVAL_THREADS / 32) * WROW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ntiles = (nobs + 31) / 32, stride = (int64_t)gridDim.x * (EVAL_THREADS / 32);
+  int64_t tile = blockIdx.x * (int64_t)(EVAL_THREADS / 32) + warp;
+  if (tile >= ntiles) return;
+  double2* st = stage + warp * WROW;
+  int cn = 0, pn = 0;
+  double2 obn = make_double2(0.0, 0.0);
+  {
+    const int64_t k = tile * 32 + lane;
+    if (k < nobs) {
+      cn = __ldcs(cam_idx + k);
+      pn = __ldcs(pnt_idx + k);
+      obn = __ldcs(pt2d + k);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // camera records of k_cam_precompute (no-op without PDL)
+  for (; tile < ntiles; tile += stride) {
+    const int64_t wbase = tile * 32, k = wbase + lane;
+    const bool valid = k < nobs;
+    const int c = cn, p = pn;
+    const double2 ob = obn;
+    {
+      const int64_t k2 = (tile + stride) * 32 + lane;  // next tile of this warp
+      cn = 0; pn = 0;
+      if (k2 < nobs) {
+        cn = __ldcs(cam_idx + k2);
+        pn = __ldcs(pnt_idx + k2);
+        obn = __ldcs(pt2d + k2);
+      }
+    }
+    double X[3], cam[14];
+    const double* xp = xpts + (int64_t)p * 3;
+    X[0] = __ldg(xp);
+    X[1] = __ldg(xp + 1);
+    X[2] = __ldg(xp + 2);
+    warp_stage_cams<true>(camtab, c, lane, st);
+    read_staged_cam(st, lane, cam);
+    ObsBlock o;
+    if (WVALS) {
+      eval_block(X, cam, ob.x, ob.y, o);
+    } else {
+      eval_residual(X, cam, ob.x, ob.y, o.F);
+    }
+    if (WCX && valid) __stcs(reinterpret_cast<double2*>(cx) + k, make_double2(o.F[0], o.F[1]));
+    __syncwarp();  // every lane has its camera record in registers: the buffer can be reused
+    if (WVALS) {
+      double2* row = st + lane * STAGE_ROW;
+      row[0] = make_double2(nan0(o.A[0]), nan0(o.A[1]));
+      row[1] = make_double2(nan0(o.A[2]), nan0(o.B[0]));
+      row[2] = make_double2(nan0(o.B[1]), nan0(o.B[2]));
+      row[3] = make_double2(nan0(o.B[3]), nan0(o.B[4]));
+      row[4] = make_double2(nan0(o.B[5]), nan0(o.B[6]));
+      row[5] = make_double2(nan0(o.B[7]), nan0(o.B[8]));
+      row[6] = make_double2(nan0(o.A[3]), nan0(o.A[4]));
+      row[7] = make_double2(nan0(o.A[5]), nan0(o.B[9]));
+      row[8] = make_double2(nan0(o.B[10]), nan0(o.B[11]));
+      row[9] = make_double2(nan0(o.B[12]), nan0(o.B[13]));
+      row[10] = make_double2(nan0(o.B[14]), nan0(o.B[15]));
+      row[11] = make_double2(nan0(o.B[16]), nan0(o.B[17]));
+      __syncwarp();
+      const int nval = (int)min((int64_t)32, nobs - wbase);
+      double2* dst = reinterpret_cast<double2*>(vals) + wbase * 12;
+#pragma unroll
+      for (int m = 0; m < 12; ++m) {
+        const int q = lane + 32 * m;
+        const int r = q / 12, cidx = q - 12 * r;
+        if (r < nval) __stcs(dst + q, st[r * STAGE_ROW + cidx]);
+      }
+      __syncwarp();  // the tile has been read before the next camera staging overwrites it
     }
   }
 }
@@ -235,6 +350,36 @@ void launch_cam_precompute(const double* x, int64_t npnts, int64_t ncams, double
   k_cam_precompute<<<blocks, threads, 0, s>>>(x + 3 * npnts, ncams, camtab);
 }
 
+namespace {
+typedef CUresult (*fn_tmap_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// vals (24 nobs doubles) as a 2-D tensor of 128-byte rows; box = 48 rows (one warp's 32 observations), 128-byte
+// swizzle.  Only whole rows are described: the rows of every FULL warp lie inside (a partial last warp never
+// uses the map).  false: no encoder / unaligned pointer / switched off -> generic stores.
+bool eval_tmap(double* vals, int64_t nobs, CUtensorMap* out) {
+  // measured slower than the generic stores (profiles/r02_k_eval_ab.md): opt-in with BAGPU_EVAL_TMA=1
+  static const bool off = !(getenv("BAGPU_EVAL_TMA") && atoi(getenv("BAGPU_EVAL_TMA")) != 0);
+  static fn_tmap_encode enc = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<fn_tmap_encode>(f);
+  }();
+  const int64_t rows = (nobs / 32) * 48;  // rows covered by full warps
+  if (off || !enc || rows == 0 || (reinterpret_cast<uintptr_t>(vals) & 15)) return false;
+  const cuuint64_t gdim[2] = {16, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {16, 48}, estride[2] = {1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, vals, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
 void launch_eval(const ba_handle* h, const double* x, const double* camtab, double* cx, double* vals,
                  cudaStream_t s) {
   const int64_t n = h->nobs_l();
@@ -254,15 +399,35 @@ void launch_eval(const ba_handle* h, const double* x, const double* camtab, doub
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = h->profile ? 0 : 1;
-  if (cx && vals)
-    cudaLaunchKernelEx(&cfg, k_eval<true, true>, (const int32_t*)h->d_cam, (const int32_t*)h->d_pnt,
-                       (const double2*)h->d_pt2d, x, camtab, cx, vals, n);
-  else if (vals)
-    cudaLaunchKernelEx(&cfg, k_eval<false, true>, (const int32_t*)h->d_cam, (const int32_t*)h->d_pnt,
-                       (const double2*)h->d_pt2d, x, camtab, cx, vals, n);
-  else
-    cudaLaunchKernelEx(&cfg, k_eval<true, false>, (const int32_t*)h->d_cam, (const int32_t*)h->d_pnt,
-                       (const double2*)h->d_pt2d, x, camtab, cx, vals, n);
+  // bulk tensor store of the Jacobian tile (one per warp) when the driver provides the encoder and vals is 16-byte
+  // aligned; opt-in: BAGPU_EVAL_TMA=1 (A/B)
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
+  bool tma = false;
+  if (vals) tma = eval_tmap(vals, n, &tm);
+#define BA_EVAL_LAUNCH(WCX, WVALS, TMA)                                                                        \
+  cudaLaunchKernelEx(&cfg, k_eval<WCX, WVALS, TMA>, (const int32_t*)h->d_cam, (const int32_t*)h->d_pnt,       \
+                     (const double2*)h->d_pt2d, x, camtab, cx, vals, n, tm)
+  cudaError_t le;
+  static const int persist = getenv("BAGPU_EVAL_PERSIST") ? atoi(getenv("BAGPU_EVAL_PERSIST")) : 0;
+  if (persist > 0 && !tma) {  // grid-stride warps with index prefetch; `persist` resident-block multiples per SM
+    cudaLaunchConfig_t pc = cfg;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    pc.gridDim = dim3((unsigned)std::min<int64_t>(blocks, (int64_t)sms * EVAL_MINBLOCKS * persist));
+#define BA_EVAL_PLAUNCH(WCX, WVALS)                                                                           \
+  cudaLaunchKernelEx(&pc, k_eval_persist<WCX, WVALS>, (const int32_t*)h->d_cam, (const int32_t*)h->d_pnt,    \
+                     (const double2*)h->d_pt2d, x, camtab, cx, vals, n)
+    if (cx && vals) le = BA_EVAL_PLAUNCH(true, true);
+    else if (vals) le = BA_EVAL_PLAUNCH(false, true);
+    else le = BA_EVAL_PLAUNCH(true, false);
+#undef BA_EVAL_PLAUNCH
+  } else if (cx && vals) le = tma ? BA_EVAL_LAUNCH(true, true, true) : BA_EVAL_LAUNCH(true, true, false);
+  else if (vals) le = tma ? BA_EVAL_LAUNCH(false, true, true) : BA_EVAL_LAUNCH(false, true, false);
+  else le = BA_EVAL_LAUNCH(true, false, false);
+#undef BA_EVAL_LAUNCH
+  if (le != cudaSuccess) h->err = std::string("k_eval launch: ") + cudaGetErrorString(le);  // also left for cudaGetLastError
   if (h->profile && h->ev_eval1) cudaEventRecord(h->ev_eval1, s);
 }
 

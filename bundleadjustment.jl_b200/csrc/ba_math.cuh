@@ -275,7 +275,18 @@ __device__ __forceinline__ void warp_stage_cams(const double* camtab, int cam_of
     const int r = 4 * i + sub;
     const int c = __shfl_sync(0xffffffffu, cam_of_lane, r);
     const double2* src = reinterpret_cast<const double2*>(camtab + (int64_t)c * CAM_REC) + ch;
-    const double2 t = COHERENT ? __ldcg(src) : __ldg(src);
+    double2 t;
+    if (COHERENT) {
+#if !defined(EVAL_CAM_LDCA) || EVAL_CAM_LDCA  // default on: +1.5 % on Venice-1778 (profiles/r02_k_eval_ab.md)
+      // cached in L1 (popular cameras are re-read by many warps of an SM); a volatile asm with a memory clobber
+      // stays below the volatile griddepcontrol.wait, and L1 holds nothing of camtab from before the wait
+      asm volatile("ld.global.ca.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "l"(src) : "memory");
+#else
+      t = __ldcg(src);
+#endif
+    } else {
+      t = __ldg(src);
+    }
     rows[r * CAM_ROW2 + ch] = t;
   }
   __syncwarp();
