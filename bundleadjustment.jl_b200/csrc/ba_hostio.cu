@@ -7,6 +7,7 @@
 // may be freed while registered).  Instead: a ring of pinned chunks owned by the library; the GPU fills chunk i
 // (full PCIe rate) while a small pool of host threads copies the finished chunks i-1, i-2, ... into the caller's
 // array.  Buffers that already are page-locked (ba_alloc_pinned, cudaHostRegister by the caller) take one direct copy.
+#include <immintrin.h>
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
@@ -21,6 +22,34 @@ namespace {
 
 constexpr size_t CHUNK = (size_t)8 << 20;  // 8 MiB per pinned chunk
 constexpr int RING = 12;                   // chunks in flight (96 MiB of pinned memory per process and device)
+
+// pinned chunk -> caller's array with non-temporal stores: the destination is written once and not read here, so
+// skipping the read-for-ownership of its cache lines saves a quarter of the host-memory traffic of the staged path
+// (DMA write + copy read + RFO + write-back -> DMA write + copy read + streaming write)
+__attribute__((target("avx2"))) void stream_copy_avx2(char* dst, const char* src, size_t n) {
+  size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+  if (head > n) head = n;
+  memcpy(dst, src, head);
+  dst += head; src += head; n -= head;
+  const size_t body = n & ~(size_t)127;
+  for (size_t i = 0; i < body; i += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+  }
+  _mm_sfence();
+  memcpy(dst + body, src + body, n - body);
+}
+void stream_copy(void* dst, const void* src, size_t n) {
+  static const bool avx2 = __builtin_cpu_supports("avx2") && getenv("BAGPU_COPY_PLAIN") == nullptr;
+  if (avx2) stream_copy_avx2(static_cast<char*>(dst), static_cast<const char*>(src), n);
+  else memcpy(dst, src, n);
+}
 
 struct job {
   cudaEvent_t ev;
@@ -69,7 +98,7 @@ class copy_pool {
         dev = j.device;
       }
       cudaEventSynchronize(j.ev);  // the GPU has filled the chunk
-      memcpy(j.dst, j.src, j.bytes);
+      stream_copy(j.dst, j.src, j.bytes);
       j.slot_busy->store(0, std::memory_order_release);
     }
   }

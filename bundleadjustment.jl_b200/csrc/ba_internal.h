@@ -26,6 +26,7 @@ struct ba_group;  // ba_group.cu: the per-device sub-handles of a multi-GPU hand
 // Device-resident state of the LM solver (allocated on first use by ba::lm_prepare).
 struct ba_lm_state {
   bool ready = false;
+  void* d_slab = nullptr;  // the one device allocation behind every pointer lm_prepare hands out
   // ---- schedules built once per problem on the host -----------------------------------------
   int32_t* d_tstart = nullptr;   // point-major warp tasks: observation offsets, ntasks + 1
   int64_t ntasks = 0;

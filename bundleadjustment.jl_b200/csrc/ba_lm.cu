@@ -213,7 +213,14 @@ int lm_prepare(ba_handle* h) {
   int rc;
   const double t_host = ms_since(tp0);
   const auto tp1 = now();
-#define ALLOC(ptr, n) if ((rc = dmalloc(h, &(ptr), (size_t)(n)))) return rc
+  // one device allocation for the whole LM state of this handle (cudaMalloc is a synchronising driver call whose
+  // cost on a shared host varies from microseconds to tens of milliseconds: ~50 of them were a measurable part of the
+  // first Levenberg_Marquardt call): the requests are recorded, one slab is allocated, the pointers are carved out
+  struct slab_req { void** p; size_t bytes; };
+  std::vector<slab_req> reqs;
+#define ALLOC(ptr, n)                                                                                      \
+  reqs.push_back(slab_req{reinterpret_cast<void**>(&(ptr)),                                                \
+                          (std::max<size_t>((size_t)(n), 1) * sizeof(*(ptr)) + 255) & ~(size_t)255})
   ALLOC(S.d_tstart, tstart.size());
   ALLOC(S.d_pstart, pstart.size());
   ALLOC(S.d_cperm, nl);
@@ -277,11 +284,23 @@ int lm_prepare(ba_handle* h) {
   S.npart = 4 * (int64_t)std::max<int64_t>(nblk(std::max(nl, npl), PT_THREADS), 1024);
   ALLOC(S.d_part, S.npart + 16);  // + scratch for the four step norms
   ALLOC(S.d_scal, S_COUNT);
+  const auto tpw = now();
   if ((rc = lm_exact_workspace(h))) return rc;
+  const double t_work = ms_since(tpw);
   if (S.exact) {
     ALLOC(S.d_Yh, 27 * nl);
     ALLOC(S.d_cd, 9 * ncams);
     ALLOC(S.d_ex, 2 * S.cn);
+  }
+  {
+    size_t total = 0;
+    for (const slab_req& r : reqs) total += r.bytes;
+    BA_CUDA(cudaMalloc(&S.d_slab, total));
+    size_t off = 0;
+    for (const slab_req& r : reqs) {
+      *r.p = static_cast<char*>(S.d_slab) + off;
+      off += r.bytes;
+    }
   }
 #undef ALLOC
   // opt-in shared-memory sizes are per device: set them for this handle's device
@@ -308,8 +327,8 @@ int lm_prepare(ba_handle* h) {
   BA_CUDA(cudaMemsetAsync(S.d_delta, 0, sizeof(double) * (size_t)h->nvar(), h->stream));
   BA_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
   if (trace)
-    fprintf(stderr, "[bagpu] lm_prepare: schedules on the host %.1f ms, device allocations %.1f ms, uploads %.1f ms\n",
-            t_host, t_alloc, ms_since(tp2));
+    fprintf(stderr, "[bagpu] lm_prepare: schedules on the host %.1f ms, device allocations %.1f ms (of which exact-solve "
+            "workspace %.1f ms), uploads %.1f ms\n", t_host, t_alloc, t_work, ms_since(tp2));
   S.ready = true;
   return BA_OK;
 }
@@ -336,9 +355,8 @@ int lm_jtprod_cams(ba_handle* h, const double* x, const double* v, double* out) 
 
 void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
-  void* ptrs[] = {S.d_tstart, S.d_pstart, S.d_cperm, S.d_ctask_beg, S.d_ctask_end, S.d_cam_t0, S.d_ctask_cam, S.d_cam_cnt, S.d_empty_cams, S.d_Jp, S.d_F, S.d_pntc, S.d_x4,
-                  S.d_w, S.d_T, S.d_dr, S.d_V, S.d_gp, S.d_Vinv, S.d_wp, S.d_taskpart, S.d_Ug, S.d_Cr, S.d_H,
-                  S.d_Minv, S.d_pcg, S.d_pcgpart, S.d_Ac, S.d_Aci, S.d_yc, S.d_cpart, S.d_Acq, S.d_cdiag, S.d_Z, S.d_Zcand, S.d_harv, S.d_hcoef, S.d_zpart, S.d_dsmall, S.d_w4, S.d_q4, S.d_x, S.d_xt, S.d_delta, S.d_camt, S.d_part, S.d_scal, S.d_S, S.d_Sq, S.d_Yh, S.d_cd, S.d_ex};
+  // everything lm_prepare allocates lives in one slab; the rest are the buffers allocated on demand
+  void* ptrs[] = {S.d_slab, S.d_dr, S.d_harv, S.d_hcoef, S.d_dsmall, S.d_S, S.d_Sq};
   for (void* p : ptrs) cudaFree(p);
   chol_plan_release(S.chol);
   if (S.h_scal) cudaFreeHost(S.h_scal);
