@@ -415,9 +415,19 @@ def main():
               "warmup": lm_warm}
         if st.chol_count:
             fl = st.chol_n ** 3 / 3.0
+            tf = fl * st.chol_count / (st.timings_ms["cholesky"] * 1e-3) / 1e12
             lm["cholesky"] = {"n": st.chol_n, "count": st.chol_count, "ms_each": st.timings_ms["cholesky"] / st.chol_count,
-                              "TFLOPs": fl * st.chol_count / (st.timings_ms["cholesky"] * 1e-3) / 1e12,
-                              "schur_assembly_ms_each": st.timings_ms["schur_assembly"] / st.chol_count}
+                              "TFLOPs": tf, "schur_assembly_ms_each": st.timings_ms["schur_assembly"] / st.chol_count,
+                              "share_of_device_time": st.timings_ms["cholesky"] / st.timings_ms["device_total"]}
+            pk = C.c_double(0.0)
+            if L.ba_measure_fp64_mma_peak(local, C.byref(pk)) == 0 and pk.value > 0:
+                # dominant kernel of an LM iteration with the exact solver: the dense factorisation (k_chol_syrk, DMMA);
+                # aggregate over the ranks when the factorisation is distributed
+                lm["roofline"] = {"bound": "tensor", "kernel": "ba::k_chol_syrk (mma.sync.m8n8k4.f64)", "achieved": tf,
+                                  "peak": pk.value * world, "unit": "TFLOP/s", "frac": tf / (pk.value * world),
+                                  "flops_per_factorisation": fl,
+                                  "peak_source": "ba_measure_fp64_mma_peak on this GPU x %d rank(s) (MEASURED_PEAKS.json "
+                                                 "holds no FP64 figure)" % world}
         # a second, warm run on the same handle: the steady-state rate once the schedules exist
         barrier()
         t0 = time.perf_counter()
@@ -482,7 +492,7 @@ def main():
                                      "pinned ring by host threads (ba_hostio.cu)",
                     "first_pageable_call_s": first_pageable_s},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "ba::k_eval<true,true>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "ba::k_eval<true,true,false>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, world),
                          "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bpo * nl,

@@ -74,7 +74,7 @@ __device__ __forceinline__ bool wait_epoch(const unsigned long long* f, unsigned
 // epilogue, the fixed issue distance of dependent DMMAs) the other keeps the FP64 tensor pipe busy, and the
 // half-height tiles halve the tail of the last wave.
 __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t lda, const double* __restrict__ B,
-                                         int64_t ldb, double (&acc)[4][4][2], double* sm) {
+                                         int64_t ldb, double (&acc)[4][4][2], double* sm, int NK = CT / KC) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -97,7 +97,7 @@ __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t l
       cp_async16(Bs + row * LDSM + part * 2, B + (int64_t)row * ldb + kc * KC + part * 2);
     }
   };
-  constexpr int NK = CT / KC;  // 8
+  // NK k-chunks of 16: 8 for one 128-column panel, 16 for two adjacent panels
   load_stage(0, 0);
   cp_async_commit();
   load_stage(1, 1);
@@ -133,7 +133,8 @@ __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t l
 //                rank's tiles of panel k have landed in this rank's copy of the matrix (flags over NVLink)
 template <bool DIST>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, chol_peers P, int* __restrict__ info) {
+k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, chol_peers P, int* __restrict__ info,
+            int nk) {
   extern __shared__ __align__(16) double sm[];
   const int j = j0 + blockIdx.y, half = blockIdx.x & 1;
   const int i = DIST ? i0 + P.R * (int)(blockIdx.x >> 1) : j + (int)(blockIdx.x >> 1);
@@ -152,7 +153,7 @@ k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, c
   const double* Pi = A + ((int64_t)i * CT + half * TM) * ld + (int64_t)k * CT;
   const double* Pj = A + (int64_t)j * CT * ld + (int64_t)k * CT;
   double acc[4][4][2];
-  tile_abt(Pi, ld, Pj, ld, acc, sm);
+  tile_abt(Pi, ld, Pj, ld, acc, sm, nk);  // nk = 16: the panels k and k + 1 (adjacent columns) in one pass
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
   double* C = A + ((int64_t)i * CT + half * TM + wm * 32 + g) * ld + (int64_t)j * CT + wn * 32 + 2 * t;
@@ -622,25 +623,50 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
     if (!P.d_prof) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_prof), 8 * sizeof(long long)));
     prof = P.d_prof;
   }
-  k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, 0, P.d_Dinv, P.d_info, prof, solo);
-  if (nb > 1) k_chol_trsm<false><<<2 * (nb - 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, 0, P.d_Dinv, 0, solo, nullptr);
-  for (int k = 0; k + 1 < nb; ++k) {
-    // panel k is final in A[k+1:, k].  Column k+1 of the trailing matrix first ...
-    k_chol_syrk<false><<<dim3(2 * (nb - k - 1), 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 1, nb, 0, solo, nullptr);
-    const bool rest = k + 2 < nb;
-    if (rest && !no_lookahead) {
-      // ... then panel k+1 (potrf + trsm) on the side stream, under the rest of the update
+  // Two panels per trailing update: the rank-128 updates of panels k and k + 1 are applied together as ONE
+  // rank-256 update (the panels are adjacent columns), which halves the read-modify-write traffic of the trailing
+  // matrix, the per-tile prologue/epilogue and the number of partial last waves.  Per pair (k even):
+  //   panel k final -> column k + 1 updated with panel k (rank 128) -> potrf / trsm of panel k + 1
+  //   -> columns k + 2, k + 3 updated with both panels (rank 256) -> [side stream: the next pair's panel work]
+  //   || [main stream: the rest of the trailing matrix, rank 256]
+  static const bool single = getenv("BAGPU_CHOL_SINGLE_PANEL") != nullptr;  // A/B: one panel per update
+  const int step = (single || nb < 24) ? 1 : 2;  // small matrices are bound by the chain of diagonal blocks: no gain
+  auto potrf = [&](int k, cudaStream_t st, long long* pf) {
+    k_chol_potrf<<<1, PO_THREADS, PO_SMEM, st>>>(A, ld, k, P.d_Dinv, P.d_info, pf, solo);
+  };
+  auto trsm = [&](int k, cudaStream_t st) {
+    if (k + 1 < nb) k_chol_trsm<false><<<2 * (nb - k - 1), GEMM_THREADS, GEMM_SMEM, st>>>(A, ld, k, P.d_Dinv, 0, solo, nullptr);
+  };
+  // columns [j0, j0 + ncol) of the trailing matrix -= (panels k .. k + npan - 1) (...)'
+  auto update = [&](int k, int npan, int j0, int ncol, cudaStream_t st) {
+    if (j0 < nb && ncol > 0)
+      k_chol_syrk<false><<<dim3(2 * (nb - j0), std::min(ncol, nb - j0)), GEMM_THREADS, GEMM_SMEM, st>>>(
+          A, ld, k, j0, nb, 0, solo, nullptr, 8 * npan);
+  };
+  // the panel work of a pair starting at k (its first column is already up to date), on stream st
+  auto pair_panels = [&](int k, cudaStream_t st, long long* pf) {
+    potrf(k, st, pf);
+    trsm(k, st);
+    if (step == 2 && k + 1 < nb) {
+      update(k, 1, k + 1, 1, st);
+      potrf(k + 1, st, nullptr);
+      trsm(k + 1, st);
+    }
+  };
+  pair_panels(0, s, prof);
+  for (int k = 0; k + step < nb; k += step) {
+    const int npan = std::min(step, nb - k);
+    update(k, npan, k + step, step, s);  // the next pair's columns first
+    if (k + 2 * step < nb && !no_lookahead) {
       BA_CUDA(cudaEventRecord(P.ev_col, s));
       BA_CUDA(cudaStreamWaitEvent(P.side, P.ev_col, 0));
-      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv, P.d_info, nullptr, solo);
-      k_chol_trsm<false><<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, P.side>>>(A, ld, k + 1, P.d_Dinv, 0, solo, nullptr);
+      pair_panels(k + step, P.side, nullptr);
       BA_CUDA(cudaEventRecord(P.ev_panel, P.side));
-      k_chol_syrk<false><<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb, 0, solo, nullptr);
+      update(k, npan, k + 2 * step, nb, s);  // the rest of the trailing matrix under the panel work
       BA_CUDA(cudaStreamWaitEvent(s, P.ev_panel, 0));
     } else {
-      if (rest) k_chol_syrk<false><<<dim3(2 * (nb - k - 2), nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb, 0, solo, nullptr);
-      k_chol_potrf<<<1, PO_THREADS, PO_SMEM, s>>>(A, ld, k + 1, P.d_Dinv, P.d_info, nullptr, solo);
-      if (rest) k_chol_trsm<false><<<2 * (nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k + 1, P.d_Dinv, 0, solo, nullptr);
+      update(k, npan, k + 2 * step, nb, s);
+      pair_panels(k + step, s, nullptr);
     }
   }
   BA_CUDA(cudaGetLastError());
@@ -765,7 +791,7 @@ int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) {
     // the rest of this rank's trailing update
     const int nc = count_own(k + 1);
     if (nc > 0)
-      k_chol_syrk<true><<<dim3(2 * nc, 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 1, nb, first_own(k + 1), V, P.d_info);
+      k_chol_syrk<true><<<dim3(2 * nc, 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 1, nb, first_own(k + 1), V, P.d_info, 8);
     BA_CUDA(cudaEventRecord(P.ev_col, s));
     BA_CUDA(cudaStreamWaitEvent(P.side, P.ev_col, 0));
     panel(k + 1, P.side);
@@ -773,7 +799,7 @@ int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) {
     const int nr = count_own(k + 2);
     if (nr > 0 && k + 2 < nb)
       k_chol_syrk<true><<<dim3(2 * nr, nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb, first_own(k + 2), V,
-                                                                                P.d_info);
+                                                                                P.d_info, 8);
     BA_CUDA(cudaStreamWaitEvent(s, P.ev_panel, 0));
   }
   k_chol_wait_all<<<1, 256, 0, s>>>(nb, V, P.d_info);
