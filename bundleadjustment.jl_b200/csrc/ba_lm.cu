@@ -106,6 +106,9 @@ int lm_exact_workspace(ba_handle* h) {
     const int64_t nbt = S.cn / CHOL_TILE;
     if ((rc = dmalloc(h, &S.d_Sq, (size_t)(nbt * (nbt + 1) / 2 * CHOL_TILE * CHOL_TILE)))) return rc;
   }
+  if ((rc = dmalloc(h, &S.d_Yh, (size_t)(27 * h->nobs_l())))) return rc;
+  if ((rc = dmalloc(h, &S.d_cd, (size_t)(9 * ncams)))) return rc;
+  if ((rc = dmalloc(h, &S.d_ex, (size_t)(2 * S.cn)))) return rc;
   if ((rc = chol_plan_init(h, S.chol, S.cn))) return rc;
   // sharded: distribute the factorisation over the ranks (falls back to the replicated one without peer access)
   if (h->nranks > 1 && h->comm && (rc = chol_dist_setup(h, S.chol, S.d_S))) return rc;
@@ -284,14 +287,10 @@ int lm_prepare(ba_handle* h) {
   S.npart = 4 * (int64_t)std::max<int64_t>(nblk(std::max(nl, npl), PT_THREADS), 1024);
   ALLOC(S.d_part, S.npart + 16);  // + scratch for the four step norms
   ALLOC(S.d_scal, S_COUNT);
-  const auto tpw = now();
-  if ((rc = lm_exact_workspace(h))) return rc;
-  const double t_work = ms_since(tpw);
-  if (S.exact) {
-    ALLOC(S.d_Yh, 27 * nl);
-    ALLOC(S.d_cd, 9 * ncams);
-    ALLOC(S.d_ex, 2 * S.cn);
-  }
+  // (the exact solve's workspace -- the dense matrix, 2-3 GB on Venice -- is NOT part of this: it is allocated by
+  //  lm_exact_workspace when a damped solve is actually requested, so that ba_jtprod, which only needs the
+  //  camera-major schedules, stays light)
+  const double t_work = 0.0;
   {
     size_t total = 0;
     for (const slab_req& r : reqs) total += r.bytes;
@@ -327,8 +326,8 @@ int lm_prepare(ba_handle* h) {
   BA_CUDA(cudaMemsetAsync(S.d_delta, 0, sizeof(double) * (size_t)h->nvar(), h->stream));
   BA_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
   if (trace)
-    fprintf(stderr, "[bagpu] lm_prepare: schedules on the host %.1f ms, device allocations %.1f ms (of which exact-solve "
-            "workspace %.1f ms), uploads %.1f ms\n", t_host, t_alloc, t_work, ms_since(tp2));
+    fprintf(stderr, "[bagpu] lm_prepare: schedules on the host %.1f ms, device allocation %.1f ms, uploads %.1f ms\n",
+            t_host, t_alloc + t_work, ms_since(tp2));
   S.ready = true;
   return BA_OK;
 }
@@ -356,7 +355,7 @@ int lm_jtprod_cams(ba_handle* h, const double* x, const double* v, double* out) 
 void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   // everything lm_prepare allocates lives in one slab; the rest are the buffers allocated on demand
-  void* ptrs[] = {S.d_slab, S.d_dr, S.d_harv, S.d_hcoef, S.d_dsmall, S.d_S, S.d_Sq};
+  void* ptrs[] = {S.d_slab, S.d_dr, S.d_harv, S.d_hcoef, S.d_dsmall, S.d_S, S.d_Sq, S.d_Yh, S.d_cd, S.d_ex};
   for (void* p : ptrs) cudaFree(p);
   chol_plan_release(S.chol);
   if (S.h_scal) cudaFreeHost(S.h_scal);
@@ -933,6 +932,7 @@ int ba_lm_step(ba_handle* h, const double* x, double lambda, double pcg_tol, int
   if (h->group) return ba::group_lm_step(h, x, lambda, pcg_tol, pcg_max_iter, delta, dr2, obj, jtr, pcg_iters);
   int rc = ba::lm_prepare(h);
   if (rc) return rc;
+  if ((rc = ba::lm_exact_workspace(h))) return rc;
   BA_CUDA(cudaSetDevice(h->device));
   ba::Solver sv(h);
   ba_lm_state& S = h->lm;
@@ -982,15 +982,15 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
   const auto wall_prep = std::chrono::steady_clock::now();
   int rc;
   if (prm.solver != BA_SOLVER_AUTO && prm.solver != h->solver && (rc = ba_set_solver(h, prm.solver))) return rc;
-  const bool was_ready = h->lm.ready;
   if ((rc = lm_prepare(h))) return rc;
+  if ((rc = lm_exact_workspace(h))) return rc;
   BA_CUDA(cudaSetDevice(h->device));
   Solver sv(h);
   ba_lm_state& S = h->lm;
   const auto wall0 = std::chrono::steady_clock::now();
   if (trace)
     fprintf(stderr, "[bagpu] lm_prepare %.1f ms\n", std::chrono::duration<double>(wall0 - wall_prep).count() * 1e3);
-  const double t_prepare = was_ready ? 0.0 : std::chrono::duration<double>(wall0 - wall_prep).count() * 1e3;
+  const double t_prepare = std::chrono::duration<double>(wall0 - wall_prep).count() * 1e3;  // ~0 on a prepared handle
   double t_eval = 0, t_asm = 0, t_pcg = 0, t_back = 0, worst_rel = 0;
   S.t_schur_ms = S.t_chol_ms = 0.0;
   S.chol_count = 0;
