@@ -89,7 +89,8 @@ struct ba_lm_state {
   int64_t cn = 0;             // 9 ncams padded to a multiple of 128
   double* d_S = nullptr;      // cn x cn row-major: the scaled matrix, then its factor L
   long long* d_Sq = nullptr;  // packed lower-triangular tiles: fixed-point sums of the off-diagonal blocks
-  double* d_Yh = nullptr;     // 27 per local observation: D_c^-1 (B'A) L_p
+  double* d_Yh = nullptr;     // 27 per local observation: D_c^-1 (B'A) L_p (borrows d_S's storage when it fits)
+  bool yh_aliased = false;
   double* d_cd = nullptr;     // 9 ncams: sqrt(diag(U + lambda I)), the Jacobi scaling
   double* d_ex = nullptr;     // 2 vectors of cn: scaled right-hand side / residual, scaled solution
   ba::chol_plan chol;

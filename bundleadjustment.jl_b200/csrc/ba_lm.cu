@@ -106,7 +106,15 @@ int lm_exact_workspace(ba_handle* h) {
     const int64_t nbt = S.cn / CHOL_TILE;
     if ((rc = dmalloc(h, &S.d_Sq, (size_t)(nbt * (nbt + 1) / 2 * CHOL_TILE * CHOL_TILE)))) return rc;
   }
-  if ((rc = dmalloc(h, &S.d_Yh, (size_t)(27 * h->nobs_l())))) return rc;
+  // Yh (27 doubles per observation, 1.08 GB on Venice) is dead once k_exact_assemble has run, and the dense matrix is
+  // only written after that (k_exact_finish): when it fits, Yh borrows the storage of the matrix (one GB less to
+  // allocate; device allocations of this size cost tens of milliseconds each)
+  if (27 * h->nobs_l() <= S.cn * S.cn) {
+    S.d_Yh = S.d_S;
+    S.yh_aliased = true;
+  } else if ((rc = dmalloc(h, &S.d_Yh, (size_t)(27 * h->nobs_l())))) {
+    return rc;
+  }
   if ((rc = dmalloc(h, &S.d_cd, (size_t)(9 * ncams)))) return rc;
   if ((rc = dmalloc(h, &S.d_ex, (size_t)(2 * S.cn)))) return rc;
   if ((rc = chol_plan_init(h, S.chol, S.cn))) return rc;
@@ -355,7 +363,8 @@ int lm_jtprod_cams(ba_handle* h, const double* x, const double* v, double* out) 
 void lm_release(ba_handle* h) {
   ba_lm_state& S = h->lm;
   // everything lm_prepare allocates lives in one slab; the rest are the buffers allocated on demand
-  void* ptrs[] = {S.d_slab, S.d_dr, S.d_harv, S.d_hcoef, S.d_dsmall, S.d_S, S.d_Sq, S.d_Yh, S.d_cd, S.d_ex};
+  void* ptrs[] = {S.d_slab, S.d_dr, S.d_harv, S.d_hcoef, S.d_dsmall, S.d_S, S.d_Sq, S.yh_aliased ? nullptr : S.d_Yh,
+                  S.d_cd, S.d_ex};
   for (void* p : ptrs) cudaFree(p);
   chol_plan_release(S.chol);
   if (S.h_scal) cudaFreeHost(S.h_scal);
