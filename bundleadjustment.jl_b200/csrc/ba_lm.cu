@@ -119,7 +119,16 @@ int lm_exact_workspace(ba_handle* h) {
   if ((rc = dmalloc(h, &S.d_ex, (size_t)(2 * S.cn)))) return rc;
   if ((rc = chol_plan_init(h, S.chol, S.cn))) return rc;
   // sharded: distribute the factorisation over the ranks (falls back to the replicated one without peer access)
-  if (h->nranks > 1 && h->comm && (rc = chol_dist_setup(h, S.chol, S.d_S))) return rc;
+  if (h->nranks > 1 && h->comm) {
+    if ((rc = chol_dist_setup(h, S.chol, S.d_S))) return rc;
+    // NCCL sets up its channels for a message-size class inside the first collective of that class (tens of ms for the
+    // ~1 GB integer allreduce of the assembly): pay that here, with the communicator, not in the first LM iteration
+    const int64_t nbt = S.cn / CHOL_TILE, packed = nbt * (nbt + 1) / 2 * CHOL_TILE * CHOL_TILE;
+    BA_CUDA(cudaMemsetAsync(S.d_Sq, 0, sizeof(long long) * (size_t)packed, h->stream));
+    for (int rep = 0; rep < 2; ++rep)
+      if ((rc = allreduce_sum_i64(h, S.d_Sq, (size_t)packed))) return rc;
+    BA_CUDA(cudaStreamSynchronize(h->stream));
+  }
   return BA_OK;
 }
 
@@ -140,7 +149,7 @@ int lm_prepare(ba_handle* h) {
   const auto tp0 = now();
   // ---- point-major warp tasks: whole points, <= 32 observations; a longer point is a task of its own
   std::vector<int32_t> tstart, pstart((size_t)npl + 1, 0);
-  {
+  std::thread point_tasks([&] {  // (independent of the camera-major sort below: the two overlap)
     int64_t cur_start = 0, cur_len = 0, a = 0;
     int64_t next_point = 0;  // local points whose pstart is not set yet
     while (a < nl) {
@@ -168,7 +177,7 @@ int lm_prepare(ba_handle* h) {
     for (; next_point <= npl; ++next_point) pstart[(size_t)next_point] = (int32_t)nl;
     S.ntasks = (int64_t)tstart.size();
     tstart.push_back((int32_t)nl);
-  }
+  });
   // ---- camera-major order (stable counting sort) and tasks.  The sort runs on a few host threads: thread t
   // counts the cameras of its contiguous chunk of observations, the (camera, chunk) counts are turned into start
   // positions, and every thread scatters its own chunk -- stable, hence deterministic.
@@ -204,6 +213,7 @@ int lm_prepare(ba_handle* h) {
       for (int64_t k = r.first; k < r.second; ++k) cperm[(size_t)cur[h->h_cam[(size_t)k]]++] = (int32_t)k;
     });
   }
+  point_tasks.join();
   int tsz = 32;  // observations per camera task: enough tasks to fill 148 SMs, at most 256 per warp
   while (tsz < 256 && nl / tsz > 148 * 64) tsz *= 2;
   for (int64_t c = 0; c < ncams; ++c) {
