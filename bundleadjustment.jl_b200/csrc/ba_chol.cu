@@ -134,7 +134,7 @@ __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t l
 template <bool DIST>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, chol_peers P, int* __restrict__ info,
-            int nk) {
+            int nk, int kwait) {
   extern __shared__ __align__(16) double sm[];
   const int j = j0 + blockIdx.y, half = blockIdx.x & 1;
   const int i = DIST ? i0 + P.R * (int)(blockIdx.x >> 1) : j + (int)(blockIdx.x >> 1);
@@ -143,7 +143,8 @@ k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, c
     __shared__ int ok;
     if (threadIdx.x == 0) ok = 1;
     __syncthreads();
-    if ((int)threadIdx.x < P.R && !wait_epoch(P.ctl[P.q] + CHOL_NBMAX + 16 * k + threadIdx.x, P.epoch)) ok = 0;
+    // (a rank reports its panels in order, so the flag of the last panel used implies the earlier ones)
+    if ((int)threadIdx.x < P.R && !wait_epoch(P.ctl[P.q] + CHOL_NBMAX + 16 * kwait + threadIdx.x, P.epoch)) ok = 0;
     __syncthreads();
     if (!ok) {
       if (threadIdx.x == 0) atomicCAS(info, 0, -2);
@@ -641,7 +642,7 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
   auto update = [&](int k, int npan, int j0, int ncol, cudaStream_t st) {
     if (j0 < nb && ncol > 0)
       k_chol_syrk<false><<<dim3(2 * (nb - j0), std::min(ncol, nb - j0)), GEMM_THREADS, GEMM_SMEM, st>>>(
-          A, ld, k, j0, nb, 0, solo, nullptr, 8 * npan);
+          A, ld, k, j0, nb, 0, solo, nullptr, 8 * npan, 0);
   };
   // the panel work of a pair starting at k (its first column is already up to date), on stream st
   auto pair_panels = [&](int k, cudaStream_t st, long long* pf) {
@@ -785,21 +786,33 @@ int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) {
     if (n > 0) k_chol_trsm<true><<<2 * n, GEMM_THREADS, GEMM_SMEM, st>>>(A, ld, k, P.d_Dinv, first_own(k + 1), V, P.d_cnt);
     else k_chol_signal<<<1, 32, 0, st>>>(k, V);
   };
-  panel(0, s);
-  for (int k = 0; k + 1 < nb; ++k) {
-    // own tiles of column k + 1 first (they gate the next panel), then the next panel on the side stream under
-    // the rest of this rank's trailing update
-    const int nc = count_own(k + 1);
-    if (nc > 0)
-      k_chol_syrk<true><<<dim3(2 * nc, 1), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 1, nb, first_own(k + 1), V, P.d_info, 8);
+  // as in the single-GPU factorisation, two panels per trailing update (rank 256) above 24 tile rows
+  static const bool single = getenv("BAGPU_CHOL_SINGLE_PANEL") != nullptr;
+  const int step = (single || nb < 24) ? 1 : 2;
+  // this rank's tiles of the columns [j0, j0 + ncol) -= (panels k .. k + npan - 1) (...)'
+  auto update = [&](int k, int npan, int j0, int ncol, cudaStream_t st) {
+    if (j0 >= nb || ncol <= 0) return;
+    const int n = count_own(j0);
+    if (n > 0)
+      k_chol_syrk<true><<<dim3(2 * n, std::min(ncol, nb - j0)), GEMM_THREADS, GEMM_SMEM, st>>>(
+          A, ld, k, j0, nb, first_own(j0), V, P.d_info, 8 * npan, k + npan - 1);
+  };
+  auto pair_panels = [&](int k, cudaStream_t st) {
+    panel(k, st);
+    if (step == 2 && k + 1 < nb) {
+      update(k, 1, k + 1, 1, st);
+      panel(k + 1, st);
+    }
+  };
+  pair_panels(0, s);
+  for (int k = 0; k + step < nb; k += step) {
+    const int npan = std::min(step, nb - k);
+    update(k, npan, k + step, step, s);  // the next pair's columns first (they gate its panel work)
     BA_CUDA(cudaEventRecord(P.ev_col, s));
     BA_CUDA(cudaStreamWaitEvent(P.side, P.ev_col, 0));
-    panel(k + 1, P.side);
+    pair_panels(k + step, P.side);
     BA_CUDA(cudaEventRecord(P.ev_panel, P.side));
-    const int nr = count_own(k + 2);
-    if (nr > 0 && k + 2 < nb)
-      k_chol_syrk<true><<<dim3(2 * nr, nb - k - 2), GEMM_THREADS, GEMM_SMEM, s>>>(A, ld, k, k + 2, nb, first_own(k + 2), V,
-                                                                                P.d_info, 8);
+    update(k, npan, k + 2 * step, nb, s);  // the rest of this rank's trailing matrix under the panel work
     BA_CUDA(cudaStreamWaitEvent(s, P.ev_panel, 0));
   }
   k_chol_wait_all<<<1, 256, 0, s>>>(nb, V, P.d_info);
