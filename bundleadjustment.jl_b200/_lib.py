@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BAGPU_LIB", os.path.join(HERE, "libbagpu.so"))  # BAGPU_LIB: A/B builds
 
 BA_OK, BA_ERR_ARG, BA_ERR_CUDA, BA_ERR_UNSORTED, BA_ERR_COMM, BA_ERR_NUMERIC = range(6)
-SOLVERS = {"auto": 0, "pcg": 1, "exact": 2}  # BA_SOLVER_*
+SOLVERS = {"auto": 0, "pcg": 1, "exact": 2, "mixed": 3}  # BA_SOLVER_*
 SOLVER_NAMES = {v: k for k, v in SOLVERS.items()}
 _CODE = {1: "bad argument", 2: "CUDA failure", 3: "observations not point-major", 4: "NCCL failure",
          5: "numeric breakdown"}
@@ -44,7 +44,8 @@ class LMStats(C.Structure):
                 ("pcg_iters_total", C.c_int64), ("t_eval_ms", C.c_double), ("t_assemble_ms", C.c_double),
                 ("t_pcg_ms", C.c_double), ("t_backsub_ms", C.c_double), ("capped_solves", C.c_int64),
                 ("worst_solve_rel", C.c_double), ("t_prepare_ms", C.c_double), ("t_schur_ms", C.c_double),
-                ("t_chol_ms", C.c_double), ("chol_n", C.c_int64), ("chol_count", C.c_int64)]
+                ("t_chol_ms", C.c_double), ("chol_n", C.c_int64), ("chol_count", C.c_int64),
+                ("mixed_fallbacks", C.c_int64)]
 
 
 ITER_CB = C.CFUNCTYPE(None, C.POINTER(LMRow), C.c_void_p)
@@ -83,6 +84,7 @@ SYMBOLS = {
     "ba_set_solver": (C.c_int, [_vp, C.c_int]),
     "ba_last_solve_info": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_f64), C.POINTER(_i32)]),
     "ba_dbg_chol": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "ba_dbg_chol32": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ba_last_eval_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ba_lm_default_params": (None, [C.POINTER(LMParams)]),
     "ba_lm_step": (C.c_int, [_vp, _vp, _f64, _f64, _i32, _vp, C.POINTER(_f64), C.POINTER(_f64), _vp,

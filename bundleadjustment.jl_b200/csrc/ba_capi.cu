@@ -59,7 +59,9 @@ int create_impl(int64_t ncams, int64_t npnts, int64_t nobs, const int64_t* cam, 
   if (const char* e = getenv("BAGPU_COARSE")) h->coarse_clusters = atoi(e);
   if (const char* e = getenv("BAGPU_DEFLATE")) h->deflate = std::max(0, std::min(32, atoi(e)));
   if (const char* e = getenv("BAGPU_SOLVER"))
-    h->solver = !strcmp(e, "pcg") ? BA_SOLVER_PCG : (!strcmp(e, "exact") ? BA_SOLVER_EXACT : BA_SOLVER_AUTO);
+    h->solver = !strcmp(e, "pcg") ? BA_SOLVER_PCG : (!strcmp(e, "exact") ? BA_SOLVER_EXACT :
+                (!strcmp(e, "mixed") ? BA_SOLVER_MIXED : BA_SOLVER_AUTO));
+  if (const char* e = getenv("BAGPU_MIXED_MAX_CG")) h->mixed_max_cg = std::max(1, std::min(64, atoi(e)));
   if (const char* e = getenv("BAGPU_EXACT_REFINE")) h->exact_refine = std::max(0, std::min(8, atoi(e)));
   bool sorted = true;
   for (int64_t k = 0; k < nobs; ++k) {
@@ -140,9 +142,84 @@ __global__ void __launch_bounds__(256) k_fp64_mma(double* out, int iters, double
   for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
   out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
 }
+// legacy tensor path probes (mma.sync): TF32 m16n8k8 and BF16 m16n8k16, FP32 accumulate, 8 independent accumulators
+template <int KIND>
+__global__ void __launch_bounds__(256) k_mma_probe(float* out, int iters, unsigned a0, unsigned b0) {
+  float c[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[j][i] = (float)(threadIdx.x + j + i) * 1e-3f;
+  unsigned a[4] = {a0, a0 + 1, a0 + 2, a0 + 3}, b[2] = {b0, b0 + 1};
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (KIND == 0)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1] + c[j][2] + c[j][3];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
+// FP32 FMA probe
+__global__ void __launch_bounds__(256) k_fp32_fma(float* out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = (float)(threadIdx.x + j) * 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = fmaf(x[j], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += x[j];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
 }  // namespace
 
 extern "C" {
+
+// development probe: kind 0 = TF32 mma.sync m16n8k8, 1 = BF16 mma.sync m16n8k16, 2 = FP32 FMA; TFLOP/s
+__attribute__((visibility("default"))) int ba_dbg_probe_peak(int device, int kind, double* tflops) {
+  if (!tflops || kind < 0 || kind > 2) return BA_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return BA_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BA_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 4, iters = 1 << 14;
+  float* out = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(reinterpret_cast<void**>(&out), sizeof(float) * 256 * (size_t)blocks) != cudaSuccess) return BA_ERR_CUDA;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 0.f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, 0);
+    if (kind == 0) k_mma_probe<0><<<blocks, 256>>>(out, iters, 0x3f800000u, 0x3f000000u);
+    else if (kind == 1) k_mma_probe<1><<<blocks, 256>>>(out, iters, 0x3f803f80u, 0x3f003f00u);
+    else k_fp32_fma<<<blocks, 256>>>(out, iters, 0.999999f, 1e-9f);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+  }
+  const cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (err != cudaSuccess || !(best > 0.f)) return BA_ERR_CUDA;
+  const double per_warp_iter = kind == 0 ? 8.0 * 2 * 16 * 8 * 8 : (kind == 1 ? 8.0 * 2 * 16 * 8 * 16 : 16.0 * 2 * 32);
+  *tflops = per_warp_iter * iters * 8.0 * blocks / (best * 1e-3) / 1e12;
+  return BA_OK;
+}
 
 int ba_measure_fp64_mma_peak(int device, double* tflops) {
   if (!tflops) return BA_ERR_ARG;
@@ -318,7 +395,7 @@ int ba_set_deflation(ba_handle* h, int k) {
 }
 
 int ba_set_solver(ba_handle* h, int solver) {
-  if (!h || solver < BA_SOLVER_AUTO || solver > BA_SOLVER_EXACT) return fail(h, BA_ERR_ARG, "unknown solver");
+  if (!h || solver < BA_SOLVER_AUTO || solver > BA_SOLVER_MIXED) return fail(h, BA_ERR_ARG, "unknown solver");
   if (h->group) {
     h->solver = solver;
     return ba::group_apply(h, [solver](ba_handle* s) { return ba_set_solver(s, solver); });

@@ -27,16 +27,41 @@ namespace {
 
 constexpr int CT = CHOL_TILE;     // 128
 constexpr int TM = 64;            // rows of a CTA tile of the two products (columns: CT)
-constexpr int KC = 16;            // k per pipeline stage
-constexpr int LDSM = KC + 4;      // padded row stride (doubles): fragment loads are bank-conflict free
 constexpr int STAGES = 3;
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM = STAGES * (TM + CT) * LDSM * (int)sizeof(double);  // 92160 B: two CTAs per SM
+// Element type of the factorisation.  double: the exact solve (DMMA).  float: the mixed-precision factor
+// (src/lm.jl:92-98 facto_type below the model type) -- FP32 storage, products on the tensor cores as three TF32
+// MMAs per product (a = a_hi + a_lo split in registers: a_lo b_hi + a_hi b_lo + a_hi b_hi, FP32 accumulate),
+// i.e. FP32-level accuracy at the TF32 rate / 3; the factor then preconditions FP64 CG on the FP64 operator.
+template <typename T> struct mkt;
+template <> struct mkt<double> {
+  static constexpr int KC = 16;        // k per pipeline stage (128 bytes of a row)
+  static constexpr int LDSM = KC + 4;  // padded row stride: fragment loads are bank-conflict free
+  using T2 = double2;
+};
+template <> struct mkt<float> {
+  static constexpr int KC = 32;
+  static constexpr int LDSM = KC + 4;
+  using T2 = float2;
+};
+template <typename T>
+constexpr int gemm_smem() { return STAGES * (TM + CT) * mkt<T>::LDSM * (int)sizeof(T); }  // 92160 / 82944 B: two CTAs per SM
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// x = hi + lo + O(2^-23 |x|): hi = x rounded to TF32 (low 13 mantissa bits zero), lo = the remainder rounded to TF32
+// (the MMA would truncate it otherwise)
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(x - __uint_as_float(hi)));
 }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -56,9 +81,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ double2 ld_volatile_d2(const double2* p) {
-  double2 v;
-  asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_volatile_16(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 // bounded wait for a flag written by another rank (~2 s): false on time-out
@@ -68,36 +93,136 @@ __device__ __forceinline__ bool wait_epoch(const unsigned long long* f, unsigned
     if (clock64() - t0 > 4000000000ll) return false;
   return true;
 }
-// acc = A (64 x 128, rows lda apart) * B' (B: 128 x 128, rows ldb apart); accumulator fragment layout of
-// m8n8k4: warp (wm, wn) of 2 x 4 owns rows wm*32.., columns wn*32..; tile (mi, ni): lane holds row 8 mi + lane/4,
-// columns 8 ni + 2 (lane%4) + {0, 1}.  Two such CTAs share an SM (8 + 8 warps): while one waits (prologue loads,
-// epilogue, the fixed issue distance of dependent DMMAs) the other keeps the FP64 tensor pipe busy, and the
-// half-height tiles halve the tail of the last wave.
-__device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t lda, const double* __restrict__ B,
-                                         int64_t ldb, double (&acc)[4][4][2], double* sm, int NK = CT / KC) {
+// two adjacent elements as doubles (the sweeps compute in FP64 whatever the factor's storage type)
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double2 ld2(const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return make_double2((double)v.x, (double)v.y);
+}
+
+// Accumulators of one 64 x 128 CTA tile, 8 warps as 2 x 4, warp (wm, wn) owns rows wm*32.., columns wn*32...
+// each(f) visits them as pairs of adjacent columns: f(row, column, v0, v1), coordinates relative to the CTA tile.
+template <typename T> struct acc_frag;
+template <> struct acc_frag<double> {  // m8n8k4: tile (mi, ni): lane holds row 8 mi + lane/4, columns 8 ni + 2 (lane%4) + {0, 1}
+  double v[4][4][2];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) v[mi][ni][0] = v[mi][ni][1] = 0.0;
+  }
+  template <class F>
+  __device__ __forceinline__ void each(F f) const {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = (warp >> 2) * 32 + (lane >> 2), c0 = (warp & 3) * 32 + 2 * (lane & 3);
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) f(r0 + 8 * mi, c0 + 8 * ni, v[mi][ni][0], v[mi][ni][1]);
+  }
+};
+template <> struct acc_frag<float> {  // m16n8k8: tile (mi, ni): c0 c1 = row 16 mi + lane/4, c2 c3 = that row + 8
+  float v[2][4][4];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[mi][ni][e] = 0.f;
+  }
+  template <class F>
+  __device__ __forceinline__ void each(F f) const {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = (warp >> 2) * 32 + (lane >> 2), c0 = (warp & 3) * 32 + 2 * (lane & 3);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        f(r0 + 16 * mi, c0 + 8 * ni, v[mi][ni][0], v[mi][ni][1]);
+        f(r0 + 16 * mi + 8, c0 + 8 * ni, v[mi][ni][2], v[mi][ni][3]);
+      }
+  }
+};
+
+// one pipeline stage of MMAs from shared memory (As, Bs: this warp's / lane's fragment origin)
+__device__ __forceinline__ void mma_stage(const double* As, const double* Bs, acc_frag<double>& acc) {
+  constexpr int LD = mkt<double>::LDSM;
+#pragma unroll
+  for (int ks = 0; ks < mkt<double>::KC / 4; ++ks) {
+    double a[4], b[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * LD + ks * 4];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * LD + ks * 4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma8x8x4(acc.v[mi][ni][0], acc.v[mi][ni][1], a[mi], b[ni]);
+  }
+}
+__device__ __forceinline__ void mma_stage(const float* As, const float* Bs, acc_frag<float>& acc) {
+  constexpr int LD = mkt<float>::LDSM;
+#pragma unroll
+  for (int ks = 0; ks < mkt<float>::KC / 8; ++ks) {
+    unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const float* p = As + mi * 16 * LD + ks * 8;  // a0 (g, t)  a1 (g + 8, t)  a2 (g, t + 4)  a3 (g + 8, t + 4)
+      split_tf32(p[0], ah[mi][0], al[mi][0]);
+      split_tf32(p[8 * LD], ah[mi][1], al[mi][1]);
+      split_tf32(p[4], ah[mi][2], al[mi][2]);
+      split_tf32(p[8 * LD + 4], ah[mi][3], al[mi][3]);
+    }
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const float* p = Bs + ni * 8 * LD + ks * 8;   // b0 (k = t, n = g)  b1 (k = t + 4, n = g)
+      split_tf32(p[0], bh[ni][0], bl[ni][0]);
+      split_tf32(p[4], bh[ni][1], bl[ni][1]);
+    }
+    // small terms first; term by term over the eight tiles, so that dependent MMAs are eight issues apart
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) mma_tf32(acc.v[mi][ni], al[mi], bh[ni]);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) mma_tf32(acc.v[mi][ni], ah[mi], bl[ni]);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) mma_tf32(acc.v[mi][ni], ah[mi], bh[ni]);
+  }
+}
+
+// acc = A (64 x 128 k, rows lda apart) * B' (B: 128 x 128 k, rows ldb apart), both operands k-contiguous.
+// Two such CTAs share an SM (8 + 8 warps): while one waits (prologue loads, epilogue, the fixed issue distance of
+// dependent MMAs) the other keeps the tensor pipe busy, and the half-height tiles halve the tail of the last wave.
+// NK = number of k-chunks of KC: CT / KC for one 128-column panel, twice that for two adjacent panels.
+template <typename T>
+__device__ __forceinline__ void tile_abt(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb,
+                                         acc_frag<T>& acc, T* sm, int NK) {
+  constexpr int KC = mkt<T>::KC, LDSM = mkt<T>::LDSM, EPP = 16 / (int)sizeof(T);  // elements per 16-byte piece
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  acc.clear();
   auto load_stage = [&](int stage, int kc) {
-    double* As = sm + stage * ((TM + CT) * LDSM);
-    double* Bs = As + TM * LDSM;
+    T* As = sm + stage * ((TM + CT) * LDSM);
+    T* Bs = As + TM * LDSM;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int c = tid + i * GEMM_THREADS;  // 512 16-byte pieces of A
+      const int c = tid + i * GEMM_THREADS;  // 512 16-byte pieces of A (8 per row)
       const int row = c >> 3, part = c & 7;
-      cp_async16(As + row * LDSM + part * 2, A + (int64_t)row * lda + kc * KC + part * 2);
+      cp_async16(As + row * LDSM + part * EPP, A + (int64_t)row * lda + kc * KC + part * EPP);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = tid + i * GEMM_THREADS;  // 1024 pieces of B
       const int row = c >> 3, part = c & 7;
-      cp_async16(Bs + row * LDSM + part * 2, B + (int64_t)row * ldb + kc * KC + part * 2);
+      cp_async16(Bs + row * LDSM + part * EPP, B + (int64_t)row * ldb + kc * KC + part * EPP);
     }
   };
-  // NK k-chunks of 16: 8 for one 128-column panel, 16 for two adjacent panels
   load_stage(0, 0);
   cp_async_commit();
   load_stage(1, 1);
@@ -108,20 +233,9 @@ __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t l
     __syncthreads();  // stage kc has landed for everybody; everybody is done with stage kc - 1
     if (kc + STAGES - 1 < NK) load_stage((kc + STAGES - 1) % STAGES, kc + STAGES - 1);
     cp_async_commit();
-    const double* As = sm + (kc % STAGES) * ((TM + CT) * LDSM) + (wm * 32 + g) * LDSM + t;
-    const double* Bs = sm + (kc % STAGES) * ((TM + CT) * LDSM) + TM * LDSM + (wn * 32 + g) * LDSM + t;
-#pragma unroll
-    for (int ks = 0; ks < KC / 4; ++ks) {
-      double a[4], b[4];
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * LDSM + ks * 4];
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * LDSM + ks * 4];
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-    }
+    const T* As = sm + (kc % STAGES) * ((TM + CT) * LDSM) + (wm * 32 + g) * LDSM + t;
+    const T* Bs = sm + (kc % STAGES) * ((TM + CT) * LDSM) + TM * LDSM + (wn * 32 + g) * LDSM + t;
+    mma_stage(As, Bs, acc);
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -131,11 +245,12 @@ __device__ __forceinline__ void tile_abt(const double* __restrict__ A, int64_t l
 //   single GPU : i = j + blockIdx.x / 2
 //   DIST       : i = i0 + R (blockIdx.x / 2), the rank's own tile rows from i0 on; the CTA first waits until every
 //                rank's tiles of panel k have landed in this rank's copy of the matrix (flags over NVLink)
-template <bool DIST>
+template <typename T, bool DIST>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, chol_peers P, int* __restrict__ info,
+k_chol_syrk(T* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, chol_peers P, int* __restrict__ info,
             int nk, int kwait) {
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  T* sm = reinterpret_cast<T*>(sm_raw);
   const int j = j0 + blockIdx.y, half = blockIdx.x & 1;
   const int i = DIST ? i0 + P.R * (int)(blockIdx.x >> 1) : j + (int)(blockIdx.x >> 1);
   if (i >= nb || i < j) return;
@@ -151,23 +266,232 @@ k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, c
       return;
     }
   }
-  const double* Pi = A + ((int64_t)i * CT + half * TM) * ld + (int64_t)k * CT;
-  const double* Pj = A + (int64_t)j * CT * ld + (int64_t)k * CT;
-  double acc[4][4][2];
-  tile_abt(Pi, ld, Pj, ld, acc, sm, nk);  // nk = 16: the panels k and k + 1 (adjacent columns) in one pass
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
-  double* C = A + ((int64_t)i * CT + half * TM + wm * 32 + g) * ld + (int64_t)j * CT + wn * 32 + 2 * t;
+  const T* Pi = A + ((int64_t)i * CT + half * TM) * ld + (int64_t)k * CT;
+  const T* Pj = A + (int64_t)j * CT * ld + (int64_t)k * CT;
+  acc_frag<T> acc;
+  tile_abt<T>(Pi, ld, Pj, ld, acc, sm, nk);  // nk chunks: one panel, or the panels k and k + 1 (adjacent columns) in one pass
+  T* C = A + ((int64_t)i * CT + half * TM) * ld + (int64_t)j * CT;
+  using T2 = typename mkt<T>::T2;
+  acc.each([&](int r, int c, T v0, T v1) {
+    T2* p = reinterpret_cast<T2*>(C + (int64_t)r * ld + c);
+    T2 cv = *p;
+    cv.x -= v0;
+    cv.y -= v1;
+    *p = cv;
+  });
+}
+
+// ---- trailing update of the FP32 factorisation on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) ----
+// A_ij (128 x 128, FP32) -= P_i P_j' over nk chunks of 32 k, P = the panels k (and k + 1).  FP32-level accuracy from
+// TF32 MMAs by the three-term split p = hi + lo (both TF32): the CTA's threads load the FP32 operands, split them in
+// registers and store hi and lo into shared memory in the canonical K-major 128-byte-swizzled layout (row r at 128 r,
+// 16-byte piece c at position c ^ (r & 7)); one thread issues, per 8 k, lo*hi' + hi*lo' into one TMEM accumulator and
+// hi*hi' into another (tcgen05.mma kind::tf32, M = N = 128) -- two accumulators, so that the small cross terms are not
+// rounded at the magnitude of the large one.  tcgen05.commit on an mbarrier per stage tells the producers when the
+// stage may be overwritten; two stages, so the operand loads + splits of chunk c + 1 run under the MMAs of chunk c.
+// Epilogue: tcgen05.ld of both accumulators (warp w reads TMEM lanes 32 (w % 4) .., i.e. rows of the tile; warps w and
+// w + 4 share the rows and split the columns), sum, subtract from the tile in global memory.
+constexpr int TC_THREADS = 256;
+constexpr int TC_KC = 32;                            // floats per row of a stage = 128 bytes = one swizzle atom
+constexpr int TC_OPER = CT * 128;                    // bytes of one operand tile of a stage (128 rows x 128 B)
+constexpr int TC_STAGE = 4 * TC_OPER;                // A hi, A lo, B hi, B lo
+constexpr int TC_STAGES = 1;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE + 1024; // + slack to align the tiles to 1024 B (swizzle atom)
+constexpr unsigned TC_COLS = 256;                    // TMEM columns: accumulator of hi*hi' and of the cross terms
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100: version 1): start address, LBO 1, SBO 1024 B
+__device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned saddr) {
+  return (unsigned long long)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// D[tmem] (+)= A[smem] B[smem]', TF32 inputs, FP32 accumulate; issued by one thread for the CTA
+__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait (~1 s) on an mbarrier phase: false on time-out (a wrong descriptor must not hang the GPU)
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return true;
+    if (clock64() - t0 > 2000000000ll) return false;
+  }
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      double2* p = reinterpret_cast<double2*>(C + (int64_t)mi * 8 * ld + ni * 8);
-      double2 c = *p;
-      c.x -= acc[mi][ni][0];
-      c.y -= acc[mi][ni][1];
-      *p = c;
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <bool DIST>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_chol_syrk_tc(float* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, chol_peers P, int* __restrict__ info,
+               int nk, int kwait) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  __shared__ __align__(8) unsigned long long bar[TC_STAGES];
+  __shared__ unsigned tmem_base_sh;
+  __shared__ int ok_sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = j0 + blockIdx.y;
+  const int i = DIST ? i0 + P.R * (int)blockIdx.x : j + (int)blockIdx.x;
+  if (i >= nb || i < j) return;
+  if (tid == 0) ok_sh = *reinterpret_cast<volatile int*>(info) == 0 ? 1 : 0;  // an earlier failure (time-out, pivot): nothing to do
+  __syncthreads();
+  if (!ok_sh) return;
+  if (DIST) {
+    // (a rank reports its panels in order, so the flag of the last panel used implies the earlier ones)
+    if (tid < P.R && !wait_epoch(P.ctl[P.q] + CHOL_NBMAX + 16 * kwait + tid, P.epoch)) ok_sh = 0;
+    __syncthreads();
+    if (!ok_sh) {
+      if (tid == 0) atomicCAS(info, 0, -2);
+      return;
     }
+  }
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
+  if (warp == 0) {  // one warp allocates the tensor memory of the CTA (and frees it at the end)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(TC_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+#pragma unroll
+    for (int st = 0; st < TC_STAGES; ++st)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[st])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = tmem_base_sh;
+  const bool diag = (i == j);  // P_i = P_j: one operand pair serves both sides
+  const float* Pi = A + (int64_t)i * CT * ld + (int64_t)k * CT;
+  const float* Pj = A + (int64_t)j * CT * ld + (int64_t)k * CT;
+  // instruction descriptor: D FP32 (bits 4-5 = 1), A and B TF32 (bits 7-9, 10-12 = 2), both K-major, N / 8 at bit 17,
+  // M / 16 at bit 24
+  constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(CT >> 3) << 17) | ((unsigned)(CT >> 4) << 24);
+  // this thread's four 16-byte pieces of an operand tile: piece e = tid + 256 q -> row e / 8, piece e % 8 of the row.
+  // The FP32 data of chunk c + 1 is fetched into registers right after the MMAs of chunk c have been issued, so the
+  // global-load latency runs under those MMAs.
+  float4 va[4], vb[4];
+  auto fetch = [&](int c) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + TC_THREADS * q, row = e >> 3, pc = e & 7;
+      va[q] = *reinterpret_cast<const float4*>(Pi + (int64_t)row * ld + c * TC_KC + pc * 4);
+      if (!diag) vb[q] = *reinterpret_cast<const float4*>(Pj + (int64_t)row * ld + c * TC_KC + pc * 4);
+    }
+  };
+  auto put = [&](const float4 (&v)[4], unsigned char* hi) {
+    unsigned char* lo = hi + TC_OPER;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + TC_THREADS * q, row = e >> 3, pc = e & 7;
+      const int off = row * 128 + ((pc ^ (row & 7)) << 4);
+      uint4 h, l;
+      split_tf32(v[q].x, h.x, l.x);
+      split_tf32(v[q].y, h.y, l.y);
+      split_tf32(v[q].z, h.z, l.z);
+      split_tf32(v[q].w, h.w, l.w);
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    }
+  };
+  bool failed = false;
+  fetch(0);
+  for (int c = 0; c < nk; ++c) {
+    const int st = c % TC_STAGES;
+    unsigned char* base = tiles + st * TC_STAGE;
+    // the MMAs that read this stage two chunks ago are done (every thread decides the same way)
+    const int bad = (c >= TC_STAGES) ? !mbar_wait(&bar[st], (unsigned)((c / TC_STAGES - 1) & 1)) : 0;
+    if (__syncthreads_or(bad)) {
+      failed = true;
+      break;
+    }
+    put(va, base);
+    if (!diag) put(vb, base + 2 * TC_OPER);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy stores above -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned sa = smem_u32(base);
+      const unsigned long long ahi = umma_desc_sw128(sa), alo = umma_desc_sw128(sa + TC_OPER);
+      const unsigned long long bhi = diag ? ahi : umma_desc_sw128(sa + 2 * TC_OPER);
+      const unsigned long long blo = diag ? alo : umma_desc_sw128(sa + 3 * TC_OPER);
+#pragma unroll
+      for (int ks = 0; ks < TC_KC / 8; ++ks) {  // 8 k = 32 bytes further along the rows: + 2 in the address field
+        const unsigned acc = (c > 0 || ks > 0) ? 1u : 0u;
+        umma_tf32(tmem + CT, alo + 2 * ks, bhi + 2 * ks, IDESC, acc);
+        umma_tf32(tmem + CT, ahi + 2 * ks, blo + 2 * ks, IDESC, 1u);
+        umma_tf32(tmem, ahi + 2 * ks, bhi + 2 * ks, IDESC, acc);
+      }
+      umma_commit(&bar[st]);  // arrives once these (and all earlier) MMAs have completed
+    }
+    if (c + 1 < nk) fetch(c + 1);
+  }
+  if (!failed) {  // all MMAs done: the commit of the last chunk
+    const int c = nk - 1;
+    const int bad = !mbar_wait(&bar[c % TC_STAGES], (unsigned)((c / TC_STAGES) & 1));
+    failed = __syncthreads_or(bad) != 0;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!failed) {
+    const int q4 = warp & 3, hf = warp >> 2;  // TMEM lane quarter = tile rows 32 q4 ..; column half
+    const int row = 32 * q4 + lane;
+    float* C = A + ((int64_t)i * CT + row) * ld + (int64_t)j * CT + hf * 64;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      float d0[32], d1[32];
+      const unsigned ta = tmem + ((unsigned)(32 * q4) << 16) + (unsigned)(hf * 64 + cc * 32);
+      tmem_ld32(ta, d0);
+      tmem_ld32(ta + CT, d1);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4* p = reinterpret_cast<float4*>(C + cc * 32 + 4 * q);
+        float4 cv = *p;
+        cv.x -= d0[4 * q] + d1[4 * q];
+        cv.y -= d0[4 * q + 1] + d1[4 * q + 1];
+        cv.z -= d0[4 * q + 2] + d1[4 * q + 2];
+        cv.w -= d0[4 * q + 3] + d1[4 * q + 3];
+        *p = cv;
+      }
+    }
+  } else if (tid == 0) {
+    atomicCAS(info, 0, -3);  // an MMA completion never arrived
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_COLS) : "memory");
 }
 
 // panel solve: P_i[half] <- P_i[half] Linv_kk'.
@@ -175,44 +499,45 @@ k_chol_syrk(double* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, c
 //   DIST       : the rank's own row tiles i = i0 + R (blockIdx.x / 2); the result is stored into EVERY rank's copy of
 //                the matrix (peer-memory stores over NVLink fused into the epilogue: the all-gather of the panel),
 //                and the CTA that finishes last tells every rank that this rank's part of panel k is complete
-template <bool DIST>
+template <typename T, bool DIST>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-k_chol_trsm(double* __restrict__ A, int64_t ld, int k, const double* __restrict__ Dinv, int i0, chol_peers P,
+k_chol_trsm(T* __restrict__ A, int64_t ld, int k, const T* __restrict__ Dinv, int i0, chol_peers P,
             int* __restrict__ cnt) {
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  T* sm = reinterpret_cast<T*>(sm_raw);
   const int half = blockIdx.x & 1;
   const int i = DIST ? i0 + P.R * (int)(blockIdx.x >> 1) : k + 1 + (int)(blockIdx.x >> 1);
   const int64_t off = ((int64_t)i * CT + half * TM) * ld + (int64_t)k * CT;
-  double acc[4][4][2];
-  tile_abt(A + off, ld, Dinv + (int64_t)k * CT * CT, CT, acc, sm);  // (every read of these rows is complete on return)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
-  const int64_t o2 = off + (int64_t)(wm * 32 + g) * ld + wn * 32 + 2 * t;
-  if (!DIST) {
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni)
-        *reinterpret_cast<double2*>(A + o2 + (int64_t)mi * 8 * ld + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-    return;
-  }
-  for (int r = 0; r < P.R; ++r) {
-    double* C = P.S[r] + o2;
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni)
-        *reinterpret_cast<double2*>(C + (int64_t)mi * 8 * ld + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-  }
-  __threadfence_system();
-  __syncthreads();
-  __shared__ int last;
-  if (threadIdx.x == 0) last = (atomicAdd(cnt, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (last) {
+  acc_frag<T> acc;
+  tile_abt<T>(A + off, ld, Dinv + (int64_t)k * CT * CT, CT, acc, sm, CT / mkt<T>::KC);  // (every read of these rows is complete on return)
+  using T2 = typename mkt<T>::T2;
+  if constexpr (!DIST) {
+    acc.each([&](int r, int c, T v0, T v1) {
+      T2 o;
+      o.x = v0;
+      o.y = v1;
+      *reinterpret_cast<T2*>(A + off + (int64_t)r * ld + c) = o;
+    });
+  } else {
+    for (int q = 0; q < P.R; ++q) {
+      T* C = static_cast<T*>(P.S[q]) + off;
+      acc.each([&](int r, int c, T v0, T v1) {
+        T2 o;
+        o.x = v0;
+        o.y = v1;
+        *reinterpret_cast<T2*>(C + (int64_t)r * ld + c) = o;
+      });
+    }
     __threadfence_system();
-    if ((int)threadIdx.x < P.R) st_release_sys_u64(P.ctl[threadIdx.x] + CHOL_NBMAX + 16 * k + P.q, P.epoch);
-    if (threadIdx.x == 0) *cnt = 0;  // ready for the next panel (kernel boundaries order this)
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0) last = (atomicAdd(cnt, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+      __threadfence_system();
+      if ((int)threadIdx.x < P.R) st_release_sys_u64(P.ctl[threadIdx.x] + CHOL_NBMAX + 16 * k + P.q, P.epoch);
+      if (threadIdx.x == 0) *cnt = 0;  // ready for the next panel (kernel boundaries order this)
+    }
   }
 }
 
@@ -232,8 +557,10 @@ k_chol_wait_all(int nb, chol_peers P, int* __restrict__ info) {
 }
 
 // non-owners pull L_kk and Linv_kk from the owner of tile row k once its flag says they are complete
+// (16-byte pieces: PR of them per row of a block)
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_chol_fetch_diag(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Dinv, chol_peers P, int owner,
+k_chol_fetch_diag(T* __restrict__ A, int64_t ld, int k, T* __restrict__ Dinv, chol_peers P, int owner,
                   int* __restrict__ info) {
   __shared__ int ok;
   if (threadIdx.x == 0) ok = wait_epoch(P.ctl[P.q] + k, P.epoch) ? 1 : 0;
@@ -242,19 +569,19 @@ k_chol_fetch_diag(double* __restrict__ A, int64_t ld, int k, double* __restrict_
     if (threadIdx.x == 0) atomicCAS(info, 0, -2);
     return;
   }
+  constexpr int EPP = 16 / (int)sizeof(T), PR = CT / EPP;
   const int64_t base = (int64_t)k * CT * ld + (int64_t)k * CT;
-  const double* sL = P.S[owner] + base;
-  const double* sD = P.D[owner] + (int64_t)k * CT * CT;
-  double* dD = Dinv + (int64_t)k * CT * CT;
-  const int n2 = CT * CT / 2;  // double2 items per block
+  const T* sL = static_cast<const T*>(P.S[owner]) + base;
+  const T* sD = static_cast<const T*>(P.D[owner]) + (int64_t)k * CT * CT;
+  T* dD = Dinv + (int64_t)k * CT * CT;
+  const int n2 = CT * PR;  // pieces per block
   for (int e = blockIdx.x * 256 + threadIdx.x; e < 2 * n2; e += gridDim.x * 256) {
     if (e < n2) {
-      const int r = e >> 6, c2 = e & 63;
-      *reinterpret_cast<double2*>(A + base + (int64_t)r * ld + 2 * c2) =
-          ld_volatile_d2(reinterpret_cast<const double2*>(sL + (int64_t)r * ld + 2 * c2));
+      const int r = e / PR, c2 = e - r * PR;
+      *reinterpret_cast<uint4*>(A + base + (int64_t)r * ld + EPP * c2) = ld_volatile_16(sL + (int64_t)r * ld + EPP * c2);
     } else {
       const int f = e - n2;
-      *reinterpret_cast<double2*>(dD + 2 * f) = ld_volatile_d2(reinterpret_cast<const double2*>(sD + 2 * f));
+      *reinterpret_cast<uint4*>(dD + EPP * f) = ld_volatile_16(sD + EPP * f);
     }
   }
 }
@@ -290,8 +617,11 @@ __device__ __forceinline__ void po_mma(const double* __restrict__ A, int lda, co
 }
 
 // A_kk (lower) <- L_kk, Dinv[k] <- L_kk^-1.  info: first non-positive pivot (1-based global index), else untouched.
+// T: storage type of the matrix, of L and of Linv; the block itself is factorised and inverted in FP64 either way
+// (it is a latency-bound chain, not a throughput problem).
+template <typename T>
 __global__ void __launch_bounds__(PO_THREADS, 1)
-k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Dinv, int* __restrict__ info,
+k_chol_potrf(T* __restrict__ A, int64_t ld, int k, T* __restrict__ Dinv, int* __restrict__ info,
              long long* __restrict__ prof, chol_peers P) {
   extern __shared__ __align__(16) double smp[];
   long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = 0;  // phase cycle counts (BAGPU_POTRF_PROF; thread 0 only)
@@ -306,10 +636,10 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
   double* rinv = smp + CT * PO_LD;       // 128: reciprocals of the diagonal of L
   double* tmp = rinv + CT;               // 64 x 65 scratch of the doubling levels
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* Akk = A + (int64_t)k * CT * ld + (int64_t)k * CT;
+  T* Akk = A + (int64_t)k * CT * ld + (int64_t)k * CT;
   for (int e = tid; e < CT * CT; e += PO_THREADS) {
     const int r = e >> 7, c = e & 127;
-    a[r * PO_LD + c] = (c <= r) ? Akk[(int64_t)r * ld + c] : 0.0;
+    a[r * PO_LD + c] = (c <= r) ? (double)Akk[(int64_t)r * ld + c] : 0.0;
   }
   __syncthreads();
   PO_LAP(0)
@@ -393,7 +723,7 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
   }
   for (int e = tid; e < CT * CT; e += PO_THREADS) {
     const int r = e >> 7, c = e & 127;
-    if (c <= r) Akk[(int64_t)r * ld + c] = a[r * PO_LD + c];
+    if (c <= r) Akk[(int64_t)r * ld + c] = (T)a[r * PO_LD + c];
   }
   __syncthreads();  // the factor has been read out before its storage is reused
   PO_LAP(4)
@@ -444,10 +774,10 @@ k_chol_potrf(double* __restrict__ A, int64_t ld, int k, double* __restrict__ Din
     }
   }
   PO_LAP(6)
-  double* D = Dinv + (int64_t)k * CT * CT;
+  T* D = Dinv + (int64_t)k * CT * CT;
   for (int e = tid; e < CT * CT; e += PO_THREADS) {
     const int r = e >> 7, c = e & 127;
-    D[e] = (c <= r) ? a[r * PO_LD + c] : 0.0;
+    D[e] = (c <= r) ? (T)a[r * PO_LD + c] : (T)0;
   }
   PO_LAP(7)
   if (prof && threadIdx.x == 0)
@@ -467,25 +797,26 @@ constexpr int SV_THREADS = 512;
 
 // step k of L y = b: every CTA forms y_k = Linv_kk w_k; CTA 0 stores it, CTA c > 0 updates row tile i = k + c:
 // w_i -= L_ik y_k.  Warp w owns rows 8 w .. 8 w + 7; a lane holds columns 2 lane, 2 lane + 1, 64 + 2 lane, 65 + 2 lane.
+template <typename T>
 __global__ void __launch_bounds__(SV_THREADS)
-k_chol_fwd(const double* __restrict__ L, int64_t ld, const double* __restrict__ Dinv, double* __restrict__ w,
+k_chol_fwd(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, double* __restrict__ w,
            double* __restrict__ y, int k) {
   __shared__ double yk[CT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i = k + blockIdx.x;
-  const double* D = Dinv + (int64_t)k * CT * CT + (int64_t)(warp * 8) * CT + 2 * lane;
-  const double* T = L + ((int64_t)i * CT + warp * 8) * ld + (int64_t)k * CT + 2 * lane;
+  const T* D = Dinv + (int64_t)k * CT * CT + (int64_t)(warp * 8) * CT + 2 * lane;
+  const T* Tl = L + ((int64_t)i * CT + warp * 8) * ld + (int64_t)k * CT + 2 * lane;
   double2 d0[8], d1[8], t0[8], t1[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    d0[r] = *reinterpret_cast<const double2*>(D + r * CT);
-    d1[r] = *reinterpret_cast<const double2*>(D + r * CT + 64);
+    d0[r] = ld2(D + r * CT);
+    d1[r] = ld2(D + r * CT + 64);
   }
   if (blockIdx.x > 0) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      t0[r] = *reinterpret_cast<const double2*>(T + (int64_t)r * ld);
-      t1[r] = *reinterpret_cast<const double2*>(T + (int64_t)r * ld + 64);
+      t0[r] = ld2(Tl + (int64_t)r * ld);
+      t1[r] = ld2(Tl + (int64_t)r * ld + 64);
     }
   }
   const double2 w0 = *reinterpret_cast<const double2*>(w + (int64_t)k * CT + 2 * lane);
@@ -522,21 +853,22 @@ k_chol_fwd(const double* __restrict__ L, int64_t ld, const double* __restrict__ 
 
 // step i of L' x = y (i descending): every CTA forms x_i = Linv_ii' y_i; CTA i stores it, CTA kk < i updates
 // y_kk -= L_{i,kk}' x_i.  Thread (c, part): column c, rows 32 part .. 32 part + 31 (coalesced across c).
+template <typename T>
 __global__ void __launch_bounds__(SV_THREADS)
-k_chol_bwd(const double* __restrict__ L, int64_t ld, const double* __restrict__ Dinv, double* __restrict__ y,
+k_chol_bwd(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, double* __restrict__ y,
            double* __restrict__ x, int i) {
   __shared__ double yi[CT], xi[CT], part[3][CT];
   const int tid = threadIdx.x;
   const int c = tid & (CT - 1), h = tid >> 7;  // column, quarter of the rows
   const int kk = blockIdx.x;
-  const double* D = Dinv + (int64_t)i * CT * CT + (int64_t)(h * 32) * CT + c;
-  const double* T = L + ((int64_t)i * CT + h * 32) * ld + (int64_t)kk * CT + c;
+  const T* D = Dinv + (int64_t)i * CT * CT + (int64_t)(h * 32) * CT + c;
+  const T* Tl = L + ((int64_t)i * CT + h * 32) * ld + (int64_t)kk * CT + c;
   double dv[32], tv[32];
 #pragma unroll
-  for (int r = 0; r < 32; ++r) dv[r] = D[r * CT];
+  for (int r = 0; r < 32; ++r) dv[r] = (double)D[r * CT];
   if (kk != i) {
 #pragma unroll
-    for (int r = 0; r < 32; ++r) tv[r] = T[(int64_t)r * ld];
+    for (int r = 0; r < 32; ++r) tv[r] = (double)Tl[(int64_t)r * ld];
   }
   if (tid < CT) yi[tid] = y[(int64_t)i * CT + tid];
   __syncthreads();
@@ -557,6 +889,12 @@ k_chol_bwd(const double* __restrict__ L, int64_t ld, const double* __restrict__ 
   if (h > 0) part[h - 1][c] = s;
   __syncthreads();
   if (h == 0) y[(int64_t)kk * CT + c] -= ((s + part[0][c]) + part[1][c]) + part[2][c];
+}
+
+// BAGPU_CHOL_NO_TC=1: the FP32 trailing update on the legacy tensor path (mma.sync, three TF32 terms) -- the A/B switch
+inline bool tc_enabled() {
+  static const bool v = getenv("BAGPU_CHOL_NO_TC") == nullptr;
+  return v;
 }
 
 }  // namespace
@@ -580,18 +918,24 @@ int chol_plan_init(ba_handle* h, chol_plan& P, int64_t cn) {
   BA_CUDA(cudaEventCreateWithFlags(&P.ev_panel, cudaEventDisableTiming));
   BA_CUDA(cudaEventCreateWithFlags(&P.ev_join, cudaEventDisableTiming));
   // per device (a process may hold handles on several devices): set once per plan
-  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  BA_CUDA(cudaFuncSetAttribute(k_chol_trsm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  BA_CUDA(cudaFuncSetAttribute(k_chol_trsm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  BA_CUDA(cudaFuncSetAttribute(k_chol_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM));
+  BA_CUDA((cudaFuncSetAttribute(k_chol_syrk<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<double>())));
+  BA_CUDA((cudaFuncSetAttribute(k_chol_syrk<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<double>())));
+  BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<double>())));
+  BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<double>())));
+  BA_CUDA((cudaFuncSetAttribute(k_chol_syrk<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
+  BA_CUDA((cudaFuncSetAttribute(k_chol_syrk<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
+  BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
+  BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_potrf<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_potrf<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM));
   P.attrs_set = true;
   return BA_OK;
 }
 
 void chol_plan_release(chol_plan& P) {
   cudaFree(P.d_Dinv);
-  cudaFree(P.d_Dinv32);
   cudaFree(P.d_y);
   cudaFree(P.d_w);
   cudaFree(P.d_x);
@@ -611,8 +955,12 @@ void chol_plan_release(chol_plan& P) {
   P = chol_plan();
 }
 
-int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info_host) {
+namespace {
+template <typename T>
+int chol_factor_t(ba_handle* h, chol_plan& P, T* A, cudaStream_t s, int* info_host) {
   const int64_t cn = P.cn, ld = cn;
+  T* const Dinv = reinterpret_cast<T*>(P.d_Dinv);
+  constexpr int NKP = CT / mkt<T>::KC, GEMM_SMEM = gemm_smem<T>();
   const int nb = (int)(cn / CT);
   static const bool no_lookahead = getenv("BAGPU_CHOL_NO_LOOKAHEAD") != nullptr;
   chol_peers solo = {};
@@ -633,16 +981,23 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
   static const bool single = getenv("BAGPU_CHOL_SINGLE_PANEL") != nullptr;  // A/B: one panel per update
   const int step = (single || nb < 24) ? 1 : 2;  // small matrices are bound by the chain of diagonal blocks: no gain
   auto potrf = [&](int k, cudaStream_t st, long long* pf) {
-    k_chol_potrf<<<1, PO_THREADS, PO_SMEM, st>>>(A, ld, k, P.d_Dinv, P.d_info, pf, solo);
+    k_chol_potrf<T><<<1, PO_THREADS, PO_SMEM, st>>>(A, ld, k, Dinv, P.d_info, pf, solo);
   };
   auto trsm = [&](int k, cudaStream_t st) {
-    if (k + 1 < nb) k_chol_trsm<false><<<2 * (nb - k - 1), GEMM_THREADS, GEMM_SMEM, st>>>(A, ld, k, P.d_Dinv, 0, solo, nullptr);
+    if (k + 1 < nb) k_chol_trsm<T, false><<<2 * (nb - k - 1), GEMM_THREADS, GEMM_SMEM, st>>>(A, ld, k, Dinv, 0, solo, nullptr);
   };
   // columns [j0, j0 + ncol) of the trailing matrix -= (panels k .. k + npan - 1) (...)'
   auto update = [&](int k, int npan, int j0, int ncol, cudaStream_t st) {
-    if (j0 < nb && ncol > 0)
-      k_chol_syrk<false><<<dim3(2 * (nb - j0), std::min(ncol, nb - j0)), GEMM_THREADS, GEMM_SMEM, st>>>(
-          A, ld, k, j0, nb, 0, solo, nullptr, 8 * npan, 0);
+    if (j0 >= nb || ncol <= 0) return;
+    if constexpr (sizeof(T) == 4) {
+      if (tc_enabled()) {  // FP32: full 128 x 128 tiles on the tcgen05 tensor cores
+        k_chol_syrk_tc<false><<<dim3(nb - j0, std::min(ncol, nb - j0)), TC_THREADS, TC_SMEM, st>>>(
+            A, ld, k, j0, nb, 0, solo, P.d_info, (CT / TC_KC) * npan, 0);
+        return;
+      }
+    }
+    k_chol_syrk<T, false><<<dim3(2 * (nb - j0), std::min(ncol, nb - j0)), GEMM_THREADS, GEMM_SMEM, st>>>(
+        A, ld, k, j0, nb, 0, solo, nullptr, NKP * npan, 0);
   };
   // the panel work of a pair starting at k (its first column is already up to date), on stream st
   auto pair_panels = [&](int k, cudaStream_t st, long long* pf) {
@@ -688,6 +1043,14 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
   }
   return BA_OK;
 }
+}  // namespace
+
+int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info_host) {
+  return chol_factor_t<double>(h, P, A, s, info_host);
+}
+int chol_factor32(ba_handle* h, chol_plan& P, float* A32, cudaStream_t s, int* info_host) {
+  return chol_factor_t<float>(h, P, A32, s, info_host);
+}
 
 // ---- distributed factorisation ------------------------------------------------------------------------------
 namespace {
@@ -699,7 +1062,7 @@ struct peer_record {  // what the ranks exchange (NCCL all-gather of the raw byt
 };
 }  // namespace
 
-int chol_dist_setup(ba_handle* h, chol_plan& P, double* A) {
+int chol_dist_setup(ba_handle* h, chol_plan& P, void* A) {
   P.dist_ready = false;
   static const bool off = getenv("BAGPU_CHOL_REPLICATED") != nullptr || getenv("BAGPU_NO_P2P") != nullptr;
   const int R = h->nranks;
@@ -740,7 +1103,7 @@ int chol_dist_setup(ba_handle* h, chol_plan& P, double* A) {
         const cudaError_t e = cudaDeviceEnablePeerAccess(p.device, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; break; }
         cudaGetLastError();
-        V.S[r] = static_cast<double*>(p.S); V.D[r] = static_cast<double*>(p.D);
+        V.S[r] = p.S; V.D[r] = p.D;
         V.ctl[r] = static_cast<unsigned long long*>(p.ctl);
       } else {
         void *a = nullptr, *b = nullptr, *c = nullptr;
@@ -753,7 +1116,7 @@ int chol_dist_setup(ba_handle* h, chol_plan& P, double* A) {
         }
         P.peer_ipc[r] = true;
         P.peer_open[3 * r] = a; P.peer_open[3 * r + 1] = b; P.peer_open[3 * r + 2] = c;
-        V.S[r] = static_cast<double*>(a); V.D[r] = static_cast<double*>(b);
+        V.S[r] = a; V.D[r] = b;
         V.ctl[r] = static_cast<unsigned long long*>(c);
       }
     }
@@ -769,8 +1132,12 @@ int chol_dist_setup(ba_handle* h, chol_plan& P, double* A) {
   return BA_OK;
 }
 
-int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) {
+namespace {
+template <typename T>
+int chol_factor_dist_t(ba_handle* h, chol_plan& P, T* A, cudaStream_t s) {
   const int64_t cn = P.cn, ld = cn;
+  T* const Dinv = reinterpret_cast<T*>(P.d_Dinv);
+  constexpr int NKP = CT / mkt<T>::KC, GEMM_SMEM = gemm_smem<T>();
   const int nb = (int)(cn / CT);
   chol_peers& V = P.peers;
   const int R = V.R, q = V.q;
@@ -780,10 +1147,10 @@ int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) {
   BA_CUDA(cudaMemsetAsync(P.d_info, 0, sizeof(int), s));
   // diagonal block k and the panel below it, on stream st
   auto panel = [&](int k, cudaStream_t st) {
-    if (k % R == q) k_chol_potrf<<<1, PO_THREADS, PO_SMEM, st>>>(A, ld, k, P.d_Dinv, P.d_info, nullptr, V);
-    else k_chol_fetch_diag<<<16, 256, 0, st>>>(A, ld, k, P.d_Dinv, V, k % R, P.d_info);
+    if (k % R == q) k_chol_potrf<T><<<1, PO_THREADS, PO_SMEM, st>>>(A, ld, k, Dinv, P.d_info, nullptr, V);
+    else k_chol_fetch_diag<T><<<16, 256, 0, st>>>(A, ld, k, Dinv, V, k % R, P.d_info);
     const int n = count_own(k + 1);
-    if (n > 0) k_chol_trsm<true><<<2 * n, GEMM_THREADS, GEMM_SMEM, st>>>(A, ld, k, P.d_Dinv, first_own(k + 1), V, P.d_cnt);
+    if (n > 0) k_chol_trsm<T, true><<<2 * n, GEMM_THREADS, GEMM_SMEM, st>>>(A, ld, k, Dinv, first_own(k + 1), V, P.d_cnt);
     else k_chol_signal<<<1, 32, 0, st>>>(k, V);
   };
   // as in the single-GPU factorisation, two panels per trailing update (rank 256) above 24 tile rows
@@ -793,9 +1160,16 @@ int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) {
   auto update = [&](int k, int npan, int j0, int ncol, cudaStream_t st) {
     if (j0 >= nb || ncol <= 0) return;
     const int n = count_own(j0);
-    if (n > 0)
-      k_chol_syrk<true><<<dim3(2 * n, std::min(ncol, nb - j0)), GEMM_THREADS, GEMM_SMEM, st>>>(
-          A, ld, k, j0, nb, first_own(j0), V, P.d_info, 8 * npan, k + npan - 1);
+    if (n <= 0) return;
+    if constexpr (sizeof(T) == 4) {
+      if (tc_enabled()) {
+        k_chol_syrk_tc<true><<<dim3(n, std::min(ncol, nb - j0)), TC_THREADS, TC_SMEM, st>>>(
+            A, ld, k, j0, nb, first_own(j0), V, P.d_info, (CT / TC_KC) * npan, k + npan - 1);
+        return;
+      }
+    }
+    k_chol_syrk<T, true><<<dim3(2 * n, std::min(ncol, nb - j0)), GEMM_THREADS, GEMM_SMEM, st>>>(
+        A, ld, k, j0, nb, first_own(j0), V, P.d_info, NKP * npan, k + npan - 1);
   };
   auto pair_panels = [&](int k, cudaStream_t st) {
     panel(k, st);
@@ -820,18 +1194,21 @@ int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) {
   return BA_OK;
 }
 
-int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, double* x, cudaStream_t s) {
+template <typename T>
+int chol_solve_t(ba_handle* h, chol_plan& P, const T* L, const double* b, double* x, cudaStream_t s) {
   const int64_t cn = P.cn;
+  const T* const Dinv = reinterpret_cast<const T*>(P.d_Dinv);
+  constexpr bool is32 = sizeof(T) == 4;
   const int nb = (int)(cn / CT);
   static const bool no_graph = getenv("BAGPU_NO_GRAPH") != nullptr || getenv("BAGPU_DEBUG_SYNC") != nullptr;
   // the sweeps always run from P.d_w into P.d_x: fixed pointers, so the 2 nb launches are captured once per
   // (matrix, plan) and replayed as one graph launch
   BA_CUDA(cudaMemcpyAsync(P.d_w, b, sizeof(double) * (size_t)cn, cudaMemcpyDeviceToDevice, s));
   auto sweeps = [&]() {
-    for (int k = 0; k < nb; ++k) k_chol_fwd<<<nb - k, SV_THREADS, 0, s>>>(L, cn, P.d_Dinv, P.d_w, P.d_y, k);
-    for (int i = nb - 1; i >= 0; --i) k_chol_bwd<<<i + 1, SV_THREADS, 0, s>>>(L, cn, P.d_Dinv, P.d_y, P.d_x, i);
+    for (int k = 0; k < nb; ++k) k_chol_fwd<T><<<nb - k, SV_THREADS, 0, s>>>(L, cn, Dinv, P.d_w, P.d_y, k);
+    for (int i = nb - 1; i >= 0; --i) k_chol_bwd<T><<<i + 1, SV_THREADS, 0, s>>>(L, cn, Dinv, P.d_y, P.d_x, i);
   };
-  if (!no_graph && !P.graph_off && (!P.solve_graph || P.solve_graph_A != L)) {
+  if (!no_graph && !P.graph_off && (!P.solve_graph || P.solve_graph_A != L || P.solve_graph_32 != is32)) {
     if (P.solve_graph) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(P.solve_graph));
     P.solve_graph = nullptr;
     cudaGraph_t g = nullptr;
@@ -846,6 +1223,7 @@ int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, dou
       cudaGraphDestroy(g);
       P.solve_graph = ge;
       P.solve_graph_A = L;
+      P.solve_graph_32 = is32;
     }
   }
   if (P.solve_graph && !no_graph) BA_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(P.solve_graph), s));
@@ -854,19 +1232,32 @@ int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, dou
   BA_CUDA(cudaGetLastError());
   return BA_OK;
 }
+}  // namespace
+
+int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) { return chol_factor_dist_t<double>(h, P, A, s); }
+int chol_factor_dist32(ba_handle* h, chol_plan& P, float* A32, cudaStream_t s) { return chol_factor_dist_t<float>(h, P, A32, s); }
+int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, double* x, cudaStream_t s) {
+  return chol_solve_t<double>(h, P, L, b, x, s);
+}
+int chol_solve32(ba_handle* h, chol_plan& P, const float* L32, const double* b, double* x, cudaStream_t s) {
+  return chol_solve_t<float>(h, P, L32, b, x, s);
+}
 
 }  // namespace ba
 
 // ---- debug / benchmark entry: factor and solve a caller-supplied SPD matrix (tests, roofline of the factorisation) --
-extern "C" int ba_dbg_chol(int device, int64_t n, const double* A_rowmajor, const double* b, double* x, double* L_out,
-                           float* factor_ms, float* solve_ms) {
+namespace {
+template <typename T>
+int dbg_chol_t(int device, int64_t n, const double* A_rowmajor, const double* b, double* x, double* L_out,
+               float* factor_ms, float* solve_ms) {
   if (n < 1 || !A_rowmajor || !b || !x) return BA_ERR_ARG;
   ba_handle hh;
   ba_handle* h = &hh;
   if (cudaSetDevice(device) != cudaSuccess) return BA_ERR_CUDA;
   const int64_t cn = ba::chol_padded(n);
   ba::chol_plan P;
-  double *dA = nullptr, *db = nullptr;
+  T* dA = nullptr;
+  double* db = nullptr;
   cudaStream_t s = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   int rc = BA_OK, info = 0;
@@ -881,25 +1272,26 @@ extern "C" int ba_dbg_chol(int device, int64_t n, const double* A_rowmajor, cons
   };
   if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return done(BA_ERR_CUDA);
   cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-  if (cudaMalloc(reinterpret_cast<void**>(&dA), sizeof(double) * (size_t)(cn * cn)) != cudaSuccess) return done(BA_ERR_CUDA);
+  if (cudaMalloc(reinterpret_cast<void**>(&dA), sizeof(T) * (size_t)(cn * cn)) != cudaSuccess) return done(BA_ERR_CUDA);
   if (cudaMalloc(reinterpret_cast<void**>(&db), sizeof(double) * (size_t)cn) != cudaSuccess) return done(BA_ERR_CUDA);
   if ((rc = ba::chol_plan_init(h, P, cn))) return done(rc);
-  // pad with the identity
-  std::vector<double> pad((size_t)cn, 0.0);
-  cudaMemsetAsync(dA, 0, sizeof(double) * (size_t)(cn * cn), s);
-  cudaMemcpy2DAsync(dA, sizeof(double) * (size_t)cn, A_rowmajor, sizeof(double) * (size_t)n, sizeof(double) * (size_t)n,
-                    (size_t)n, cudaMemcpyHostToDevice, s);
-  for (int64_t r = n; r < cn; ++r) {
-    const double one = 1.0;
-    cudaMemcpyAsync(dA + r * cn + r, &one, sizeof(double), cudaMemcpyHostToDevice, s);
-  }
+  // padded with the identity, in the element type of the factorisation
+  std::vector<T> host((size_t)(cn * cn), (T)0);
+  for (int64_t r = 0; r < n; ++r)
+    for (int64_t c = 0; c < n; ++c) host[(size_t)(r * cn + c)] = (T)A_rowmajor[r * n + c];
+  for (int64_t r = n; r < cn; ++r) host[(size_t)(r * cn + r)] = (T)1;
+  cudaMemcpyAsync(dA, host.data(), sizeof(T) * host.size(), cudaMemcpyHostToDevice, s);
   cudaMemsetAsync(db, 0, sizeof(double) * (size_t)cn, s);
   cudaMemcpyAsync(db, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s);
   cudaStreamSynchronize(s);
   cudaEventRecord(e0, s);
-  rc = ba::chol_factor(h, P, dA, s, nullptr);
+  if (sizeof(T) == 8) rc = ba::chol_factor(h, P, reinterpret_cast<double*>(dA), s, nullptr);
+  else rc = ba::chol_factor32(h, P, reinterpret_cast<float*>(dA), s, nullptr);
   cudaEventRecord(e1, s);
-  if (!rc) rc = ba::chol_solve(h, P, dA, db, db, s);
+  if (!rc) {
+    if (sizeof(T) == 8) rc = ba::chol_solve(h, P, reinterpret_cast<double*>(dA), db, db, s);
+    else rc = ba::chol_solve32(h, P, reinterpret_cast<float*>(dA), db, db, s);
+  }
   cudaEventRecord(e2, s);
   if (rc) return done(rc);
   if (cudaStreamSynchronize(s) != cudaSuccess) return done(BA_ERR_CUDA);
@@ -907,9 +1299,22 @@ extern "C" int ba_dbg_chol(int device, int64_t n, const double* A_rowmajor, cons
   if (factor_ms) cudaEventElapsedTime(factor_ms, e0, e1);
   if (solve_ms) cudaEventElapsedTime(solve_ms, e1, e2);
   cudaMemcpy(x, db, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
-  if (L_out)
-    cudaMemcpy2D(L_out, sizeof(double) * (size_t)n, dA, sizeof(double) * (size_t)cn, sizeof(double) * (size_t)n, (size_t)n,
-                 cudaMemcpyDeviceToHost);
+  if (L_out) {
+    cudaMemcpy(host.data(), dA, sizeof(T) * host.size(), cudaMemcpyDeviceToHost);
+    for (int64_t r = 0; r < n; ++r)
+      for (int64_t c = 0; c < n; ++c) L_out[r * n + c] = (double)host[(size_t)(r * cn + c)];
+  }
   if (cudaGetLastError() != cudaSuccess) return done(BA_ERR_CUDA);
   return done(info ? BA_ERR_NUMERIC : BA_OK);
+}
+}  // namespace
+
+extern "C" int ba_dbg_chol(int device, int64_t n, const double* A_rowmajor, const double* b, double* x, double* L_out,
+                           float* factor_ms, float* solve_ms) {
+  return dbg_chol_t<double>(device, n, A_rowmajor, b, x, L_out, factor_ms, solve_ms);
+}
+// the mixed-precision factor: A rounded to FP32, FP32 factor (returned widened), x = (L32 L32')^-1 b with FP64 sweeps
+extern "C" int ba_dbg_chol32(int device, int64_t n, const double* A_rowmajor, const double* b, double* x, double* L_out,
+                             float* factor_ms, float* solve_ms) {
+  return dbg_chol_t<float>(device, n, A_rowmajor, b, x, L_out, factor_ms, solve_ms);
 }

@@ -23,8 +23,8 @@ constexpr int CHOL_RMAX = 16;     // ranks at most in the distributed factorisat
 // Control block of a rank (unsigned long long): [k] = epoch once Linv_kk / L_kk of step k may be fetched from the
 // owner of tile row k; [CHOL_NBMAX + 16 k + r] = epoch once rank r's tiles of panel k have landed in this rank's matrix.
 struct chol_peers {
-  double* S[CHOL_RMAX];
-  double* D[CHOL_RMAX];
+  void* S[CHOL_RMAX];   // the matrix (double, or float for the mixed-precision factor: same storage)
+  void* D[CHOL_RMAX];
   unsigned long long* ctl[CHOL_RMAX];
   int R, q;
   unsigned long long epoch;
@@ -34,7 +34,7 @@ struct chol_peers {
 struct chol_plan {
   int64_t cn = 0;            // padded order (multiple of CHOL_TILE)
   double* d_Dinv = nullptr;  // cn/128 blocks of 128 x 128: inverses of the diagonal blocks of L (lower, row-major)
-  float* d_Dinv32 = nullptr; // the same in FP32 (mixed-precision factor)
+                             // (the FP32 factorisation keeps its FP32 inverses in the same storage)
   double* d_y = nullptr;     // cn: forward-substitution result
   double* d_w = nullptr;     // cn: right-hand side being consumed
   double* d_x = nullptr;     // cn: solution of the sweeps
@@ -44,6 +44,7 @@ struct chol_plan {
   cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_join = nullptr;
   void* solve_graph = nullptr;   // cudaGraphExec_t of the 2 cn/128 substitution steps
   const void* solve_graph_A = nullptr;
+  bool solve_graph_32 = false;
   bool graph_off = false;        // capture not possible on the caller's stream
   bool attrs_set = false;
   // distributed factorisation over the ranks of a sharded handle (tile row i belongs to rank i mod R)
@@ -63,7 +64,7 @@ int chol_factor(ba_handle* h, chol_plan& P, double* A, cudaStream_t s, int* info
 // Collective over the ranks of a sharded handle (needs its NCCL communicator): exchange the addresses of A, the
 // diagonal-block inverses and the control blocks (CUDA IPC between processes, raw pointers + peer access inside one
 // process).  Leaves P.dist_ready false (replicated factorisation) when peer access is not available on every rank.
-int chol_dist_setup(ba_handle* h, chol_plan& P, double* A);
+int chol_dist_setup(ba_handle* h, chol_plan& P, void* A);
 // Right-looking factorisation distributed over the ranks: each rank updates its own tile rows; panels travel by
 // peer-memory stores fused into the panel-solve kernel, diagonal blocks are pulled from their owner; flags over
 // NVLink order the steps.  On return every rank holds the complete factor (the sweeps run replicated).
@@ -71,8 +72,11 @@ int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s);
 // x <- (L L')^-1 b for one right-hand side (b and x: cn doubles on the device, may alias).
 int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, double* x, cudaStream_t s);
 
-// FP32 factor of an FP64 matrix (mixed precision, src/lm.jl:92-98,165-173 facto_type): A32 (cn x cn) <- chol(float(A)).
+// Mixed precision (src/lm.jl:92-98,165-173: facto_type below the model type): the same factorisation with FP32 storage
+// and three-TF32-term tensor-core products (FP32-level accuracy); A32 is cn x cn floats, leading dimension cn.  The
+// sweeps read the FP32 factor and compute in FP64 (right-hand side and solution are doubles): a preconditioner.
 int chol_factor32(ba_handle* h, chol_plan& P, float* A32, cudaStream_t s, int* info_host);
+int chol_factor_dist32(ba_handle* h, chol_plan& P, float* A32, cudaStream_t s);
 int chol_solve32(ba_handle* h, chol_plan& P, const float* L32, const double* b, double* x, cudaStream_t s);
 
 }  // namespace ba

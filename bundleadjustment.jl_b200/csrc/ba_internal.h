@@ -86,6 +86,9 @@ struct ba_lm_state {
   int defl_iters_first = 0;     // PCG iterations of the solve the base vectors came from
   // ---- exact solve: explicit reduced camera system + dense Cholesky (ba_chol.cu) ---------------------
   bool exact = false;         // decided in lm_prepare from ba_handle::solver and the problem size
+  bool mixed = false;         // exact, with the FP32 tensor-core factor as preconditioner of FP64 CG (BA_SOLVER_MIXED)
+  bool factor64 = false;      // the current factor in d_S is the FP64 one (exact mode, or mixed after a fall-back)
+  int64_t mixed_fallbacks = 0;  // damped solves of this LM run that needed the FP64 factorisation after all
   int64_t cn = 0;             // 9 ncams padded to a multiple of 128
   double* d_S = nullptr;      // cn x cn row-major: the scaled matrix, then its factor L
   long long* d_Sq = nullptr;  // packed lower-triangular tiles: fixed-point sums of the off-diagonal blocks
@@ -156,6 +159,7 @@ struct ba_handle {
   int deflate = 32;          // PCG deflation: base Ritz vectors wanted (0 = off)
   int solver = BA_SOLVER_AUTO;  // damped solve: auto / PCG / exact (ba_set_solver)
   int exact_refine = 1;      // refinement steps of the exact solve (matrix-free FP64 residual)
+  int mixed_max_cg = 12;     // CG iterations of the mixed-precision solve before it falls back to the FP64 factor
   ba_lm_state lm;
   ncclComm* comm = nullptr;
   ba_p2p_state p2p;

@@ -90,14 +90,16 @@ int lm_exact_workspace(ba_handle* h) {
   BA_CUDA(cudaSetDevice(h->device));
   // auto = up to EXACT_AUTO_CAMS cameras (the factorisation is n^3/3 flops)
   S.exact = h->sorted && ncams > 0 &&
-            (h->solver == BA_SOLVER_EXACT || (h->solver == BA_SOLVER_AUTO && ncams <= exact_auto_cams()));
+            (h->solver == BA_SOLVER_EXACT || h->solver == BA_SOLVER_MIXED ||
+             (h->solver == BA_SOLVER_AUTO && ncams <= exact_auto_cams()));
+  S.mixed = S.exact && h->solver == BA_SOLVER_MIXED;
   S.cn = chol_padded(9 * ncams);
   if (S.exact && (double)S.cn * (double)S.cn * 8.0 > exact_max_bytes()) {
-    if (h->solver == BA_SOLVER_EXACT) {
-      h->err = "BA_SOLVER_EXACT: the dense reduced camera system does not fit (raise BAGPU_EXACT_MAX_GB or use PCG)";
+    if (h->solver == BA_SOLVER_EXACT || h->solver == BA_SOLVER_MIXED) {
+      h->err = "BA_SOLVER_EXACT / MIXED: the dense reduced camera system does not fit (raise BAGPU_EXACT_MAX_GB or use PCG)";
       return BA_ERR_ARG;
     }
-    S.exact = false;
+    S.exact = S.mixed = false;
   }
   if (!S.exact) return BA_OK;
   int rc;
@@ -481,14 +483,20 @@ struct Solver {
           S.d_pstart, h->d_pnt, h->pnt0, h->d_cam, nl, S.d_Yh, reinterpret_cast<unsigned long long*>(S.d_Sq));
     if ((rc = check())) return rc;
     if ((rc = allreduce_sum_i64(h, S.d_Sq, (size_t)packed))) return rc;
-    k_exact_finish<<<dim3(nblk(cn, 256), (unsigned)cn), 256, 0, s>>>(n9, cn, S.d_H, S.d_Cr, S.d_cd, S.d_Sq, S.d_S);
-    if ((rc = check())) return rc;
-    cudaEventRecord(S.ev[6], s);
     int info = 0;
-    if ((rc = S.chol.dist_ready ? chol_factor_dist(h, S.chol, S.d_S, s) : chol_factor(h, S.chol, S.d_S, s, nullptr))) return rc;
+    S.factor64 = !S.mixed;
+    if (S.mixed) {
+      // FP32 matrix (same storage), FP32 tensor-core factorisation: the preconditioner of the FP64 CG in mixed_solve
+      if ((rc = dense_factor<float>(&info))) return rc;
+      if (info > 0) {  // a non-positive pivot in FP32: the FP64 factorisation decides
+        if (tr) fprintf(stderr, "[bagpu] mixed solve: FP32 pivot %d not positive, FP64 factorisation instead\n", info);
+        S.mixed_fallbacks += 1;
+        S.factor64 = true;
+      }
+    }
+    if (S.factor64 && (rc = dense_factor<double>(&info))) return rc;
     cudaEventRecord(S.ev[7], s);
-    BA_CUDA(cudaMemcpyAsync(&info, S.chol.d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
-    if ((rc = read_scalars())) return rc;  // synchronises: pivot check + S_ERR
+    if ((rc = read_scalars())) return rc;  // S_ERR
     if (info == -2) {
       h->err = "distributed Cholesky: a peer's flag never arrived (a rank is missing or stalled)";
       return BA_ERR_COMM;
@@ -505,8 +513,8 @@ struct Solver {
     S.chol_count += 1;
     if (tr) {
       const double fl = (double)cn * cn * cn / 3.0;
-      fprintf(stderr, "[bagpu] exact factor: assembly of S (%lld x %lld) %.2f ms, Cholesky %.2f ms (%.1f TFLOP/s%s)\n",
-              (long long)cn, (long long)cn, ta, tc, fl / (tc * 1e-3) / 1e12,
+      fprintf(stderr, "[bagpu] exact factor: assembly of S (%lld x %lld) %.2f ms, Cholesky (%s) %.2f ms (%.1f TFLOP/s%s)\n",
+              (long long)cn, (long long)cn, ta, S.factor64 ? "FP64" : "FP32 storage, 3 x TF32", tc, fl / (tc * 1e-3) / 1e12,
               S.chol.dist_ready ? ", distributed over the ranks" : "");
     }
     if (S.h_scal[S_ERR] != 0.0) {
@@ -514,6 +522,86 @@ struct Solver {
       return BA_ERR_NUMERIC;
     }
     return BA_OK;
+  }
+  // the dense matrix from the fixed-point sums (the sums stay intact), in T, and its factorisation; synchronises
+  template <typename T>
+  int dense_factor(int* info) {
+    int rc;
+    const int64_t cn = S.cn;
+    T* A = reinterpret_cast<T*>(S.d_S);
+    k_exact_finish<T><<<dim3(nblk(cn, 256), (unsigned)cn), 256, 0, s>>>(n9, cn, S.d_H, S.d_Cr, S.d_cd, S.d_Sq, A);
+    if ((rc = check())) return rc;
+    cudaEventRecord(S.ev[6], s);  // the factorisation proper starts here
+    if constexpr (sizeof(T) == 8) rc = S.chol.dist_ready ? chol_factor_dist(h, S.chol, A, s) : chol_factor(h, S.chol, A, s, nullptr);
+    else rc = S.chol.dist_ready ? chol_factor_dist32(h, S.chol, A, s) : chol_factor32(h, S.chol, A, s, nullptr);
+    if (rc) return rc;
+    BA_CUDA(cudaMemcpyAsync(info, S.chol.d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+    return BA_OK;
+  }
+  // Mixed-precision solve: FP64 CG on S dc = b with the matrix-free FP64 product (the operator PCG applies),
+  // preconditioned by the FP32 factor: M^-1 r = D^-1 (L32 L32')^-1 D^-1 r.  M^-1 S = I + O(cond * 1e-7): a handful of
+  // iterations.  Stops at ||r|| / ||b|| <= tol, or when the residual stagnates below 1e-10 (its rounding floor); the
+  // TRUE residual ||b - S xc|| / ||b|| is then measured and reported like the exact solve's.  Returns 1 when the
+  // factor is no usable preconditioner (not positive definite in CG, or no convergence in mixed_max_cg iterations):
+  // the caller factorises in FP64.
+  int mixed_solve(double tol, int* iters) {
+    int rc;
+    const int64_t cn = S.cn;
+    double* rs = S.d_ex;        // r / cd, padded: right-hand side of the sweeps
+    double* xs = S.d_ex + cn;   // their result
+    const float* L32 = reinterpret_cast<const float*>(S.d_S);
+    const bool p2p = h->nranks > 1 && h->p2p.ready;
+    BA_CUDA(cudaMemsetAsync(S.d_scal + S_MBAD, 0, sizeof(double), s));
+    k_mixed_init<<<1, RED_THREADS, 0, s>>>(n9, cn, b, S.d_cd, xc, r, rs, S.d_scal);
+    double rel = 1.0, prev = 1.0;
+    int it = 0;
+    bool ok = false;
+    const int maxit = std::max(1, h->mixed_max_cg);
+    while (it < maxit) {
+      if ((rc = chol_solve32(h, S.chol, L32, rs, xs, s))) return rc;
+      k_mixed_dir<<<1, RED_THREADS, 0, s>>>(n9, xs, S.d_cd, r, p, S.d_scal, it == 0 ? 1 : 0);
+      BA_CUDA(cudaMemsetAsync(S.d_scal + S_DONE, 0, sizeof(double), s));  // the product kernels honour S_DONE
+      if ((rc = s_product(false))) return rc;
+      if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
+      k_mixed_update<<<1, RED_THREADS, 0, s>>>(n9, p, q, S.d_cd, xc, r, rs, S.d_scal);
+      ++it;
+      if ((rc = check())) return rc;
+      if (it < 2) continue;  // (never done after one iteration: save the round trip)
+      if ((rc = read_scalars())) return rc;
+      if (S.h_scal[S_ERR] != 0.0) break;
+      if (S.h_scal[S_MBAD] != 0.0) break;
+      prev = rel;
+      rel = S.h_scal[S_REL];
+      if (!std::isfinite(rel)) break;
+      if (rel <= tol || (rel <= 1e-10 && rel > 0.25 * prev)) {
+        ok = true;
+        break;
+      }
+    }
+    if (S.h_scal[S_ERR] == 3.0) {
+      h->err = "peer-memory exchange timed out (a rank is missing or stalled)";
+      return BA_ERR_COMM;
+    }
+    if (!ok) {
+      if (trace_on())
+        fprintf(stderr, "[bagpu] mixed solve: no convergence with the FP32 factor (%d iterations, residual %.2e%s)\n", it, rel,
+                S.h_scal[S_MBAD] != 0.0 ? ", non-positive curvature" : "");
+      BA_CUDA(cudaMemsetAsync(S.d_scal + S_MBAD, 0, sizeof(double), s));
+      return 1;
+    }
+    // the true residual of xc, matrix-free (the recursive one above drifts by rounding)
+    BA_CUDA(cudaMemcpyAsync(p, xc, sizeof(double) * (size_t)n9, cudaMemcpyDeviceToDevice, s));
+    BA_CUDA(cudaMemsetAsync(S.d_scal + S_DONE, 0, sizeof(double), s));
+    if ((rc = s_product(false))) return rc;
+    if (p2p) k_seq_inc<<<1, 1, 0, s>>>(h->p2p.d_seq);
+    k_exact_resid<<<1, RED_THREADS, 0, s>>>(n9, cn, b, q, S.d_cd, rs, S.d_scal, 1);
+    *iters = it;
+    S.last_solver = BA_SOLVER_MIXED;
+    S.last_converged = 1;
+    S.last_iters = it;
+    S.last_rel = -1.0;  // filled from S_REL at the next read of the scalars
+    return check();
   }
   // Exact solve, solve phase: xc = D^-1 (L L')^-1 D^-1 b, then `exact_refine` refinement steps with the FP64
   // residual b - S xc of the matrix-free product (the same operator PCG applies).  No host round trip: the
@@ -544,7 +632,33 @@ struct Solver {
     S.last_rel = -1.0;  // filled from S_REL at the next read of the scalars
     return check();
   }
-  int solve(double tol, int maxit, int* iters) { return S.exact ? exact_solve(iters) : pcg(tol, maxit, iters); }
+  int solve(double tol, int maxit, int* iters) {
+    if (!S.exact) return pcg(tol, maxit, iters);
+    if (!S.factor64) {
+      int rc = mixed_solve(tol, iters);
+      if (rc != 1) return rc;
+      // the FP32 factor did not do: the FP64 factorisation of the same sums, then the exact solve
+      S.mixed_fallbacks += 1;
+      S.factor64 = true;
+      int info = 0;
+      if ((rc = dense_factor<double>(&info))) return rc;
+      cudaEventRecord(S.ev[7], s);
+      BA_CUDA(cudaEventSynchronize(S.ev[7]));
+      float tc = 0;
+      cudaEventElapsedTime(&tc, S.ev[6], S.ev[7]);
+      S.t_chol_ms += tc;
+      S.chol_count += 1;
+      if (info == -2) {
+        h->err = "distributed Cholesky: a peer's flag never arrived (a rank is missing or stalled)";
+        return BA_ERR_COMM;
+      }
+      if (info != 0) {
+        h->err = "Cholesky of the reduced camera system: non-positive pivot";
+        return BA_ERR_NUMERIC;
+      }
+    }
+    return exact_solve(iters);
+  }
   // Ac = [P Z]' S [P Z], then Ac^-1.  P block: direct assembly in one pass over the points (k_coarse_assemble;
   // BAGPU_COARSE_PRODUCTS=1: column by column with CDOF ncl applications of S, the cross-check).  Z block
   // (deflation vectors, dense): one application of S per vector.
@@ -1013,6 +1127,7 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
   double t_eval = 0, t_asm = 0, t_pcg = 0, t_back = 0, worst_rel = 0;
   S.t_schur_ms = S.t_chol_ms = 0.0;
   S.chol_count = 0;
+  S.mixed_fallbacks = 0;
   int64_t pcg_total = 0, capped = 0;
   auto rec = [&](int i) { cudaEventRecord(S.ev[i], h->stream); };
   auto lap = [&](int a, int b) {
@@ -1169,6 +1284,7 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
     st->capped_solves = capped; st->worst_solve_rel = worst_rel; st->t_prepare_ms = t_prepare;
     st->t_schur_ms = S.t_schur_ms; st->t_chol_ms = S.t_chol_ms;
     st->chol_n = S.exact ? S.cn : 0; st->chol_count = S.chol_count;
+    st->mixed_fallbacks = S.mixed_fallbacks;
   }
   return BA_OK;
 }

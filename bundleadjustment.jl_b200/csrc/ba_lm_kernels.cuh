@@ -31,6 +31,9 @@ enum {
   S_ITK,      // S_ITERS as it was when the current PCG iteration started (read by every CTA of k_pcg_p)
   S_CBAD,     // the coarse matrix [P Z]'S[P Z] had a non-positive pivot: its inverse was replaced by zero, i.e. the
               // solves run with plain block-Jacobi (not an error: the preconditioner never changes the solution)
+  S_MBAD,     // mixed-precision solve: CG met a non-positive curvature (the FP32 factor is no usable preconditioner:
+              // the host falls back to the FP64 factorisation; not an error)
+  S_MRZ,      // mixed-precision solve: r.z of the current CG iteration (k_pcg_q, part of the product, rewrites S_RZ)
   S_COUNT = 32
 };
 
@@ -1621,15 +1624,16 @@ k_exact_assemble(const int32_t* __restrict__ pstart, const int32_t* __restrict__
 }
 
 // packed fixed point -> row-major double over the lower triangle, diagonal blocks added, identity on the padding
+template <typename T>  // T = double: the exact solve; float: the matrix of the mixed-precision factor
 __global__ void __launch_bounds__(256)
 k_exact_finish(int64_t n9, int64_t cn, const double* __restrict__ H, const double* __restrict__ Cr,
-               const double* __restrict__ cd, const long long* __restrict__ Sq, double* __restrict__ S) {
+               const double* __restrict__ cd, const long long* __restrict__ Sq, T* __restrict__ S) {
   const int64_t r = blockIdx.y;
   const int64_t c = blockIdx.x * (int64_t)256 + threadIdx.x;
   if (c > r || c >= cn) return;
-  double* sp = S + r * cn + c;
+  T* sp = S + r * cn + c;
   if (r >= n9) {
-    *sp = (r == c) ? 1.0 : 0.0;
+    *sp = (r == c) ? (T)1 : (T)0;
     return;
   }
   double v = -((double)Sq[ex_packed(r, c)] / EX_SCALE);
@@ -1638,7 +1642,7 @@ k_exact_finish(int64_t n9, int64_t cn, const double* __restrict__ H, const doubl
     const int i = (int)(r - 9 * br), j = (int)(c - 9 * bc);  // j <= i
     v += (H[br * 81 + i * 9 + j] - Cr[br * NV + sym9(j, i)]) / (cd[r] * cd[c]);
   }
-  *sp = v;
+  *sp = (T)v;
 }
 
 // out[i] = in[i] / cd[i] (i < n9), 0 on the padding
@@ -1681,6 +1685,77 @@ k_exact_resid(int64_t n9, int64_t cn, const double* __restrict__ b, const double
     scal[S_RZN] = r2;
     scal[S_RZ0] = b2;
     if (first) scal[S_REL] = sqrt(r2 / b2);  // residual of the direct solve, before any refinement
+  }
+}
+
+// ---- mixed-precision exact solve: FP64 CG on the matrix-free S, preconditioned by the FP32 factor of the assembled,
+// Jacobi-scaled S (M^-1 = D^-1 (L32 L32')^-1 D^-1).  The camera system has 9 ncams <= ~40 K rows here: the vector
+// work of an iteration is two single-CTA kernels with fixed-order sums (identical on every rank).
+// start: x = 0, r = b, rs = r / cd (zero on the padding); scal[S_RZ0] = b.b
+__global__ void __launch_bounds__(RED_THREADS)
+k_mixed_init(int64_t n9, int64_t cn, const double* __restrict__ b, const double* __restrict__ cd, double* __restrict__ x,
+             double* __restrict__ r, double* __restrict__ rs, double* __restrict__ scal) {
+  __shared__ double sh[RED_THREADS / 32];
+  double b2 = 0.0;
+  for (int64_t i = threadIdx.x; i < cn; i += RED_THREADS) {
+    double v = 0.0;
+    if (i < n9) {
+      v = b[i];
+      x[i] = 0.0;
+      r[i] = v;
+      b2 += v * v;
+      v /= cd[i];
+    }
+    rs[i] = v;
+  }
+  b2 = block_sum<RED_THREADS>(b2, sh);
+  if (threadIdx.x == 0) {
+    scal[S_RZ0] = b2;
+    scal[S_RZN] = b2;
+    scal[S_REL] = 1.0;
+    scal[S_ITERS] = 0.0;
+  }
+}
+// after the sweeps (xs = (L L')^-1 rs): z = xs / cd, rz' = r.z, beta = first ? 0 : rz' / rz, p = z + beta p
+__global__ void __launch_bounds__(RED_THREADS)
+k_mixed_dir(int64_t n9, const double* __restrict__ xs, const double* __restrict__ cd, const double* __restrict__ r,
+            double* __restrict__ p, double* __restrict__ scal, int first) {
+  __shared__ double sh[RED_THREADS / 32];
+  double rz = 0.0;
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) rz += r[i] * (xs[i] / cd[i]);
+  rz = block_sum<RED_THREADS>(rz, sh);
+  const double beta = first ? 0.0 : rz / scal[S_MRZ];
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) p[i] = xs[i] / cd[i] + (first ? 0.0 : beta * p[i]);
+  __syncthreads();  // everybody has read the old r.z
+  if (threadIdx.x == 0) {
+    scal[S_MRZ] = rz;
+    if (!(rz > 0.0) && scal[S_RZN] > 0.0) scal[S_MBAD] = 1.0;  // the preconditioner is not positive definite
+  }
+}
+// after q = S p: alpha = r.z / p.q, x += alpha p, r -= alpha q, rs = r / cd; scal[S_REL] = ||r|| / ||b||
+__global__ void __launch_bounds__(RED_THREADS)
+k_mixed_update(int64_t n9, const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ cd,
+               double* __restrict__ x, double* __restrict__ r, double* __restrict__ rs, double* __restrict__ scal) {
+  __shared__ double sh[RED_THREADS / 32];
+  double pq = 0.0;
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) pq += p[i] * q[i];
+  pq = block_sum<RED_THREADS>(pq, sh);
+  const double alpha = pq > 0.0 ? scal[S_MRZ] / pq : 0.0;
+  double r2 = 0.0;
+  for (int64_t i = threadIdx.x; i < n9; i += RED_THREADS) {
+    x[i] += alpha * p[i];
+    const double rv = r[i] - alpha * q[i];
+    r[i] = rv;
+    r2 += rv * rv;
+    rs[i] = rv / cd[i];
+  }
+  r2 = block_sum<RED_THREADS>(r2, sh);
+  if (threadIdx.x == 0) {
+    scal[S_PQ] = pq;
+    scal[S_RZN] = r2;
+    scal[S_REL] = sqrt(r2 / scal[S_RZ0]);
+    scal[S_ITERS] += 1.0;
+    if (!(pq > 0.0)) scal[S_MBAD] = 1.0;
   }
 }
 

@@ -132,9 +132,9 @@ function NLPModels.jtprod!(nlp::BALNLPModel, x::Vector{Float64}, v::Vector{Float
 end
 
 # knobs of the device solve (no counterpart in the reference; they never change the solution)
-set_solver!(nlp::BALNLPModel, s::Symbol) =                                     # :auto, :pcg, :exact
+set_solver!(nlp::BALNLPModel, s::Symbol) =                                     # :auto, :pcg, :exact, :mixed
   check(nlp, ccall((:ba_set_solver, libbagpu), Cint, (Ptr{Cvoid}, Cint), nlp.handle,
-                   Dict(:auto => 0, :pcg => 1, :exact => 2)[s]))
+                   Dict(:auto => 0, :pcg => 1, :exact => 2, :mixed => 3)[s]))
 set_coarse_clusters!(nlp::BALNLPModel, n::Integer) =
   check(nlp, ccall((:ba_set_coarse_clusters, libbagpu), Cint, (Ptr{Cvoid}, Cint), nlp.handle, n))
 set_deflation!(nlp::BALNLPModel, k::Integer) =

@@ -26,6 +26,7 @@ struct BALMStats
   t_eval_ms::Float64; t_assemble_ms::Float64; t_pcg_ms::Float64; t_backsub_ms::Float64
   capped_solves::Int64; worst_solve_rel::Float64; t_prepare_ms::Float64
   t_schur_ms::Float64; t_chol_ms::Float64; chol_n::Int64; chol_count::Int64
+  mixed_fallbacks::Int64
 end
 struct BALMRow
   iter::Int64; f::Float64; df::Float64; dfeas::Float64; lambda::Float64; delta_norm::Float64; rho::Float64
@@ -59,7 +60,7 @@ function Levenberg_Marquardt(model::FeasibilityResidual, facto::Symbol, perm::Sy
   nlp = model.nlp::BALNLPModel
   xs = Vector{Float64}(x)                                                 # x0 in, solution out
   prm = BALMParams(restol, satol, srtol, oatol, ortol, atol, rtol, νd, νm, λ, δd, ite_max, linesearch,
-                   pcg_max_iter, pcg_tol, Dict(:auto => 0, :pcg => 1, :exact => 2)[solver], 0)
+                   pcg_max_iter, pcg_tol, Dict(:auto => 0, :pcg => 1, :exact => 2, :mixed => 3)[solver], 0)
   st = Ref{BALMStats}()
   cb = @cfunction(lm_log_row, Cvoid, (Ptr{BALMRow}, Ptr{Cvoid}))
   @info log_header([:iter, :f, :df, :dfeas, :λ, :δ, :ρ, :status], [Int, Float64, Float64, Float64, Float64, Float64, Float64, String])

@@ -41,6 +41,7 @@ class GenericExecutionStats:
     worst_solve_rel: float = 0.0    # largest relative residual a damped solve stopped at
     chol_n: int = 0                 # exact solver: order of the dense factorisations (0: PCG) and how many ran
     chol_count: int = 0
+    mixed_fallbacks: int = 0        # mixed solver: damped solves that needed the FP64 factorisation after all
 
 
 def default_params(**kw) -> _lib.LMParams:
@@ -107,7 +108,7 @@ def Levenberg_Marquardt(model, facto="LDL", perm="AMD", normalize="None", linese
         timings_ms=dict(eval=st.t_eval_ms, assemble=st.t_assemble_ms, pcg=st.t_pcg_ms, backsub=st.t_backsub_ms,
                         device_total=st.elapsed_s * 1e3, prepare=st.t_prepare_ms, schur_assembly=st.t_schur_ms,
                         cholesky=st.t_chol_ms),
-        chol_n=int(st.chol_n), chol_count=int(st.chol_count),
+        chol_n=int(st.chol_n), chol_count=int(st.chol_count), mixed_fallbacks=int(st.mixed_fallbacks),
         capped_solves=int(st.capped_solves), worst_solve_rel=st.worst_solve_rel)
 
 
@@ -133,18 +134,19 @@ def last_solve_info(nlp: BALNLPModel) -> dict:
     return dict(solver=_lib.SOLVER_NAMES.get(sv.value, "?"), converged=bool(cv.value), rel=rel.value, iters=it.value)
 
 
-def dbg_chol(A, b, device=0, want_L=False):
-    """Factor and solve a dense SPD system with the library's device Cholesky (ba_dbg_chol).
-    Returns (x, L or None, factor_ms, solve_ms)."""
+def dbg_chol(A, b, device=0, want_L=False, fp32=False):
+    """Factor and solve a dense SPD system with the library's device Cholesky (ba_dbg_chol; fp32=True: the
+    mixed-precision factor, ba_dbg_chol32).  Returns (x, L or None, factor_ms, solve_ms)."""
     A = np.ascontiguousarray(A, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
     n = A.shape[0]
     x = np.empty(n)
     Lo = np.empty((n, n)) if want_L else None
     f, s = C.c_float(), C.c_float()
-    rc = _lib.lib().ba_dbg_chol(device, n, A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
-                                x.ctypes.data_as(C.c_void_p), None if Lo is None else Lo.ctypes.data_as(C.c_void_p),
-                                C.byref(f), C.byref(s))
+    fn = _lib.lib().ba_dbg_chol32 if fp32 else _lib.lib().ba_dbg_chol
+    rc = fn(device, n, A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+            x.ctypes.data_as(C.c_void_p), None if Lo is None else Lo.ctypes.data_as(C.c_void_p),
+            C.byref(f), C.byref(s))
     if rc:
         raise _lib.BAError(rc, "ba_dbg_chol")
     return x, Lo, f.value, s.value

@@ -45,8 +45,14 @@ enum {
  * BA_SOLVER_EXACT is their counterpart: the reduced camera system assembled explicitly and factorised by a dense
  * FP64 Cholesky (what ldl_factorize + ldl_solve!, src/ldl_aux.jl:122-201,4-42, amount to after the ordering has
  * eliminated residual rows and points) plus refinement steps with the matrix-free FP64 residual.  BA_SOLVER_PCG is
- * the matrix-free preconditioned CG (stopped at pcg_tol).  AUTO: exact up to 2048 cameras, PCG above. */
-enum { BA_SOLVER_AUTO = 0, BA_SOLVER_PCG = 1, BA_SOLVER_EXACT = 2 };
+ * the matrix-free preconditioned CG (stopped at pcg_tol).  AUTO: exact up to 2048 cameras, PCG above.
+ * BA_SOLVER_MIXED is the reference's mixed-precision mode (src/lm.jl:92-98,165-173: facto_type below the model type,
+ * "factorise in Float32, everything else in Float64"): the same explicit reduced camera
+ * system, factorised in FP32 storage on the tensor cores (three TF32 MMAs per product: FP32-level accuracy), and that
+ * factor preconditions FP64 CG on the FP64 matrix-free operator -- a handful of iterations to pcg_tol, so the step
+ * keeps the FP64 accuracy of the other solvers.  When the FP32 factor is no usable preconditioner (non-positive
+ * pivot, or no convergence in 12 iterations) the solve falls back to the FP64 factorisation (ba_lm_stats.mixed_fallbacks). */
+enum { BA_SOLVER_AUTO = 0, BA_SOLVER_PCG = 1, BA_SOLVER_EXACT = 2, BA_SOLVER_MIXED = 3 };
 
 /* ---- model lifetime: BALNLPModel(filename) ctor, src/BALNLPModels.jl:91-106 ---------------- */
 /* Copies indices and pt2d to the device (caller buffers are not retained).  device = CUDA
@@ -122,13 +128,14 @@ BA_API int ba_set_coarse_clusters(ba_handle* h, int n);
  * preconditioned reduced camera system come without extra products; ba_lm.cu).  Only used
  * for camera systems above the single-CTA threshold.  Changes the iteration count, not the solution. */
 BA_API int ba_set_deflation(ba_handle* h, int k);
-/* Choose the damped solve (BA_SOLVER_*); takes effect from the next LM call on.  Env BAGPU_SOLVER=pcg|exact
+/* Choose the damped solve (BA_SOLVER_*); takes effect from the next LM call on.  Env BAGPU_SOLVER=pcg|exact|mixed
  * sets the default of new handles. */
 BA_API int ba_set_solver(ba_handle* h, int solver);
-/* Outcome of the last damped solve on this handle: solver used (BA_SOLVER_PCG / BA_SOLVER_EXACT), whether it
- * converged (PCG: reached pcg_tol before pcg_max_iter; exact: factorisation succeeded), the relative residual
- * it stopped at (PCG: sqrt(r'M^-1 r / r0'M^-1 r0); exact: ||b - S x|| / ||b|| of the direct solve, measured
- * matrix-free before the refinement step) and its iteration count (PCG iterations / refinement steps). */
+/* Outcome of the last damped solve on this handle: solver used (BA_SOLVER_PCG / BA_SOLVER_EXACT / BA_SOLVER_MIXED;
+ * EXACT after a mixed solve fell back), whether it converged (PCG: reached pcg_tol before pcg_max_iter; exact:
+ * factorisation succeeded), the relative residual it stopped at (PCG: sqrt(r'M^-1 r / r0'M^-1 r0); exact:
+ * ||b - S x|| / ||b|| of the direct solve, measured matrix-free before the refinement step; mixed: the same true
+ * residual of the returned solution) and its iteration count (PCG / CG iterations, refinement steps). */
 BA_API int ba_last_solve_info(const ba_handle* h, int32_t* solver, int32_t* converged, double* rel, int32_t* iters);
 /* Profiling: with it on, the per-observation evaluation kernel (k_eval: cons!/jac_coord!/fused) is
  * bracketed by CUDA events on the handle's stream and ba_last_eval_ms returns its device time alone
@@ -176,6 +183,7 @@ typedef struct ba_lm_stats {
    * its dense Cholesky factorisations (chol_n^3 / 3 flops each, chol_count of them) */
   double t_schur_ms, t_chol_ms;
   int64_t chol_n, chol_count;
+  int64_t mixed_fallbacks; /* BA_SOLVER_MIXED: damped solves that needed the FP64 factorisation after all */
 } ba_lm_stats;
 
 typedef void (*ba_iter_cb)(const ba_lm_row* row, void* user);
@@ -213,6 +221,11 @@ BA_API int ba_comm_ipc_disable(ba_handle* h);
  * live) and the device times of the two phases.  Not part of the reference's surface. */
 BA_API int ba_dbg_chol(int device, int64_t n, const double* A_rowmajor, const double* b, double* x, double* L_out,
                        float* factor_ms, float* solve_ms);
+/* The same for the mixed-precision factor of BA_SOLVER_MIXED: A is rounded to FP32 and factorised in FP32 storage with
+ * three-TF32-term tensor-core products; x = (L32 L32')^-1 b by FP64 sweeps over the FP32 factor (a preconditioner
+ * application, accurate to about cond(A) * 1e-7); L_out receives the FP32 factor widened to doubles. */
+BA_API int ba_dbg_chol32(int device, int64_t n, const double* A_rowmajor, const double* b, double* x, double* L_out,
+                         float* factor_ms, float* solve_ms);
 
 /* ---- host-only helpers of the PCG deflation space (no GPU; exported so that they can be unit-tested) ------ */
 /* Eigenpairs of the Lanczos tridiagonal defined by the CG coefficients alpha[0..m), beta[0..m-1):

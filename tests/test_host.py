@@ -115,6 +115,7 @@ int main(void) {
   P(ba_lm_stats, status); P(ba_lm_stats, iter); P(ba_lm_stats, objective); P(ba_lm_stats, pcg_iters_total);
   P(ba_lm_stats, t_backsub_ms); P(ba_lm_stats, capped_solves); P(ba_lm_stats, worst_solve_rel);
   P(ba_lm_stats, t_prepare_ms); P(ba_lm_stats, t_chol_ms); P(ba_lm_stats, chol_count);
+  P(ba_lm_stats, mixed_fallbacks);
   return 0;
 }
 ''')
@@ -138,7 +139,8 @@ int main(void) {
                                                            "capped_solves": "capped_solves",
                                                            "worst_solve_rel": "worst_solve_rel",
                                                            "t_prepare_ms": "t_prepare_ms", "t_chol_ms": "t_chol_ms",
-                                                           "chol_count": "chol_count"})):
+                                                           "chol_count": "chol_count",
+                                                           "mixed_fallbacks": "mixed_fallbacks"})):
         for cf, pf in names.items():
             assert int(got["%s.%s" % (cname, cf)]) == getattr(cls, pf).offset, (cname, cf)
 
