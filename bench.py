@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--pcg-max-iter", type=int, default=None, help="cap PCG iterations per solve (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lm-reference", action="store_true", help="skip the LM legs on the small configs")
-    ap.add_argument("--solver", default="auto", choices=["auto", "pcg", "exact"], help="damped solve of the LM leg")
+    ap.add_argument("--solver", default="auto", choices=["auto", "pcg", "exact", "mixed"], help="damped solve of the LM leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -377,24 +377,24 @@ def main():
         ba.init_comm(mw)
         steps_w = {}
         try:
-            for sv in ("pcg", "exact"):
+            for sv in ("pcg", "exact", "mixed"):
                 ba.Levenberg_Marquardt(mw, "LDL", "AMD", "None", False, ite_max=2, solver=sv,
                                        pcg_max_iter=args.pcg_max_iter)
                 steps_w[sv] = ba.lm_step(mw, pw.x0, 30.0)[0]
         finally:
             mw.close()
-        lm_warm = ("3-iteration solves (PCG and exact) of a (160, 10000, 50000) synthetic problem, sharded over the "
+        lm_warm = ("3-iteration solves (PCG, exact and mixed) of a (160, 10000, 50000) synthetic problem, sharded over the "
                    "same %d rank(s), on its own handle" % world)
         if world > 1 and rank == 0:
             # driver-visible multi-GPU parity: the sharded damped solve against the same solve on one GPU
             m1 = ba.BALNLPModel(pw.cam_idx, pw.pnt_idx, pw.pt2d, pw.x0, pw.ncams, pw.npnts, pw.nobs, device=local)
             parity = {"problem": "(160, 10000, 50000), lambda 30", "ranks": world}
             try:
-                for sv in ("pcg", "exact"):
+                for sv in ("pcg", "exact", "mixed"):
                     m1.set_solver(sv)
                     d1 = ba.lm_step(m1, pw.x0, 30.0)[0]
                     parity[sv + "_rel_err_vs_1gpu"] = float(np.linalg.norm(steps_w[sv] - d1) / np.linalg.norm(d1))
-                parity["ok"] = bool(max(parity["pcg_rel_err_vs_1gpu"], parity["exact_rel_err_vs_1gpu"]) <= 1e-10)
+                parity["ok"] = bool(max(parity[sv + "_rel_err_vs_1gpu"] for sv in ("pcg", "exact", "mixed")) <= 1e-10)
             finally:
                 m1.close()
         barrier()
@@ -408,7 +408,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         lm = {"metric": "LM iters/s", "value": st.iter / float(t.item()), "iters": st.iter,
               "solver": st.rows[0]["solver"] if st.rows else None,
-              "pcg_iters": st.pcg_iters, "capped_solves": st.capped_solves, "worst_solve_rel": st.worst_solve_rel,
+              "solver_per_iteration": [r["solver"] for r in st.rows], "mixed_fallbacks": st.mixed_fallbacks,
+              "pcg_iters": st.pcg_iters, "solver_iters_per_iteration": [r["pcg_iters"] for r in st.rows],
+              "capped_solves": st.capped_solves, "worst_solve_rel": st.worst_solve_rel,
               "objective0": st.rows[0]["f"] if st.rows else None,
               "objective": st.objective, "status": st.status, "timings_ms": st.timings_ms,
               "e2e": "x0 host -> solution host through Levenberg_Marquardt(), schedules (lm_prepare) included",
@@ -420,7 +422,23 @@ def main():
                               "TFLOPs": tf, "schur_assembly_ms_each": st.timings_ms["schur_assembly"] / st.chol_count,
                               "share_of_device_time": st.timings_ms["cholesky"] / st.timings_ms["device_total"]}
             pk = C.c_double(0.0)
-            if L.ba_measure_fp64_mma_peak(local, C.byref(pk)) == 0 and pk.value > 0:
+            if lm["solver"] == "mixed" and st.mixed_fallbacks == 0:
+                # dominant kernel of the mixed solver: the FP32 factorisation's trailing update on tcgen05 (kind::tf32,
+                # three TF32 MMAs per FP32 product): executed TF32 flops against the TF32 tensor rate = half the
+                # measured dense bf16 rate of MEASURED_PEAKS.json
+                pkf = None
+                try:
+                    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                        pkf = float(json.load(f)["bf16_tflops"]) / 2.0
+                except Exception:
+                    pkf = 2250.0 / 2.0
+                lm["roofline"] = {"bound": "tensor", "kernel": "ba::k_chol_syrk_tc (tcgen05.mma kind::tf32, 3 terms)",
+                                  "achieved": 3.0 * tf, "peak": pkf * world, "unit": "TFLOP/s",
+                                  "frac": 3.0 * tf / (pkf * world), "flops_per_factorisation": 3.0 * fl,
+                                  "fp32_equivalent_TFLOPs": tf,
+                                  "peak_source": "TF32 dense = MEASURED_PEAKS.json bf16_tflops / 2 (nominal 1125 if absent) "
+                                                 "x %d rank(s)" % world}
+            elif L.ba_measure_fp64_mma_peak(local, C.byref(pk)) == 0 and pk.value > 0:
                 # dominant kernel of an LM iteration with the exact solver: the dense factorisation (k_chol_syrk, DMMA);
                 # aggregate over the ranks when the factorisation is distributed
                 lm["roofline"] = {"bound": "tensor", "kernel": "ba::k_chol_syrk (mma.sync.m8n8k4.f64)", "achieved": tf,
@@ -440,6 +458,25 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         lm["value_warm_handle"] = st2.iter / float(t.item())
         lm["objective_rerun_equal"] = bool(st2.objective == st.objective)
+        if lm["solver"] in ("exact", "mixed"):
+            # the other dense solver on the same (warm) handle: FP64 factorisation against FP32 factor + FP64 CG
+            other = "mixed" if lm["solver"] == "exact" else "exact"
+            for _rep in range(2):  # (the first call after a solver change rebuilds the LM state)
+                barrier()
+                t0 = time.perf_counter()
+                st3 = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=args.lm_iters - 1,
+                                             pcg_max_iter=args.pcg_max_iter, solver=other)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lm["other_dense_solver"] = {"solver": other, "value_warm_handle": st3.iter / float(t.item()),
+                                        "objective": st3.objective, "timings_ms": st3.timings_ms,
+                                        "solver_per_iteration": [r["solver"] for r in st3.rows],
+                                        "solver_iters_per_iteration": [r["pcg_iters"] for r in st3.rows],
+                                        "mixed_fallbacks": st3.mixed_fallbacks, "worst_solve_rel": st3.worst_solve_rel}
+            m.set_solver(args.solver)
         if world == 1 and not args.no_lm_reference:
             # the configs the reference arm times whole LM runs on (bench.py --impl reference, lm_configs)
             lm_configs = {}

@@ -159,7 +159,8 @@ struct ba_handle {
   int deflate = 32;          // PCG deflation: base Ritz vectors wanted (0 = off)
   int solver = BA_SOLVER_AUTO;  // damped solve: auto / PCG / exact (ba_set_solver)
   int exact_refine = 1;      // refinement steps of the exact solve (matrix-free FP64 residual)
-  int mixed_max_cg = 12;     // CG iterations of the mixed-precision solve before it falls back to the FP64 factor
+  int mixed_max_cg = 30;     // CG iterations of the mixed-precision solve before it falls back to the FP64 factor
+                             // (an FP64 factorisation costs about as much as 30 of them on Venice-1778)
   ba_lm_state lm;
   ncclComm* comm = nullptr;
   ba_p2p_state p2p;

@@ -159,7 +159,9 @@ class BALNLPModel:
 
     def set_solver(self, solver: str):
         """How the damped LM system is solved: "auto" (exact up to 2048 cameras, PCG above), "pcg" (matrix-free
-        preconditioned CG) or "exact" (explicit reduced camera system + dense FP64 Cholesky + refinement)."""
+        preconditioned CG), "exact" (explicit reduced camera system + dense FP64 Cholesky + refinement) or "mixed"
+        (the same system factorised in FP32 on the tensor cores, preconditioning FP64 CG on the FP64 operator:
+        the reference's facto_type < T mode, src/lm.jl:92-98)."""
         _lib.check(_lib.lib().ba_set_solver(self.handle, _lib.SOLVERS[solver]), self.handle)
 
     def set_deflation(self, k: int):

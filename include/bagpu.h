@@ -51,7 +51,7 @@ enum {
  * system, factorised in FP32 storage on the tensor cores (three TF32 MMAs per product: FP32-level accuracy), and that
  * factor preconditions FP64 CG on the FP64 matrix-free operator -- a handful of iterations to pcg_tol, so the step
  * keeps the FP64 accuracy of the other solvers.  When the FP32 factor is no usable preconditioner (non-positive
- * pivot, or no convergence in 12 iterations) the solve falls back to the FP64 factorisation (ba_lm_stats.mixed_fallbacks). */
+ * pivot, or no convergence in 30 iterations) the solve falls back to the FP64 factorisation (ba_lm_stats.mixed_fallbacks). */
 enum { BA_SOLVER_AUTO = 0, BA_SOLVER_PCG = 1, BA_SOLVER_EXACT = 2, BA_SOLVER_MIXED = 3 };
 
 /* ---- model lifetime: BALNLPModel(filename) ctor, src/BALNLPModels.jl:91-106 ---------------- */

@@ -29,6 +29,25 @@ def test_device_cholesky_matches_lapack(ba, n):
     assert eL <= 1e-12 and res <= 1e-11 and ex <= 1e-10
 
 
+@pytest.mark.parametrize("n", [1, 50, 129, 700, 2313, 3400])
+def test_device_fp32_cholesky_is_an_fp32_accurate_factor(ba, n):
+    """The mixed-precision factor (FP32 storage, three-TF32-term tensor-core products; n = 3400 takes the two-panel
+    updates): backward error and distance to LAPACK's spotrf at the FP32 level, and a preconditioner application."""
+    A = _spd(n, n)
+    A = 0.5 * (A + A.T)
+    b = np.random.default_rng(1).normal(size=n)
+    x, L, f_ms, s_ms = ba.lm.dbg_chol(A, b, want_L=True, fp32=True)
+    L = np.tril(L)
+    Lr = np.linalg.cholesky(A.astype(np.float32)).astype(np.float64)
+    back = np.linalg.norm(L @ L.T - A) / np.linalg.norm(A)
+    back_ref = np.linalg.norm(Lr @ Lr.T - A) / np.linalg.norm(A)
+    eL = np.linalg.norm(L - Lr) / np.linalg.norm(Lr)
+    res = np.linalg.norm(A @ x - b) / np.linalg.norm(b)
+    parity_report("device_fp32_cholesky_vs_spotrf", n=n, backward=back, backward_spotrf=back_ref, L=eL, residual=res,
+                  factor_ms=f_ms, solve_ms=s_ms)
+    assert back <= 2e-6 and eL <= 1e-4 and res <= 5e-3      # cond(A) = 1e4: residual ~ cond * 1e-7
+
+
 def test_device_cholesky_flags_a_non_positive_pivot(ba):
     A = _spd(300, 3)
     A[200, 200] = -1.0
@@ -57,6 +76,47 @@ def test_exact_and_pcg_solve_the_same_system(ba, shape, lam):
     assert e[0] <= (TOL if lam >= 1 else 1e-7)
     assert abs(dr1 - dr0) <= 1e-10 * dr0
     assert np.array_equal(d1, d2) and dr1 == dr2      # fixed-point assembly + ordered factorisation: bit-identical reruns
+
+
+@pytest.mark.parametrize("shape,lam", [((160, 10000, 50000), 30.0), ("trafalgar-257", 100.0), ("trafalgar-257", 1.0),
+                                        ("dubrovnik-356", 30.0)])
+def test_mixed_and_exact_solve_the_same_system(ba, shape, lam):
+    """BA_SOLVER_MIXED (FP32 tensor-core factor + FP64 CG on the FP64 operator, src/lm.jl:92-98 facto_type) returns
+    the FP64 step: same bar as the exact solver."""
+    p = ba.synth.make_problem(shape)
+    m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    m.set_solver("exact")
+    d0, dr0, _, _, _ = ba.lm_step(m, p.x0, lam)
+    m.set_solver("mixed")
+    d1, dr1, _, _, it1 = ba.lm_step(m, p.x0, lam)
+    i1 = ba.lm.last_solve_info(m)
+    d2, dr2, _, _, _ = ba.lm_step(m, p.x0, lam)
+    m.close()
+    e = rel_errors(d1, d0)
+    parity_report("mixed_vs_exact", shape=str(shape), lam=lam, norm=e[0], floor=e[1], entry=e[2], cg_iters=int(it1),
+                  true_residual=i1["rel"])
+    assert i1["solver"] == "mixed" and i1["converged"] and 1 <= it1 <= 30
+    assert e[0] <= TOL and abs(dr1 - dr0) <= 1e-10 * dr0 and i1["rel"] <= 1e-11
+    assert np.array_equal(d1, d2) and dr1 == dr2      # deterministic: fixed-point assembly, ordered sums
+
+
+def test_mixed_solver_falls_back_to_the_fp64_factorisation(ba, monkeypatch):
+    """When CG with the FP32 factor does not converge within its cap the solve is redone with the FP64 factorisation
+    (never an inexact step): forced here by a cap of one iteration."""
+    monkeypatch.setenv("BAGPU_MIXED_MAX_CG", "1")
+    p = ba.synth.make_problem((160, 10000, 50000))
+    m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    monkeypatch.delenv("BAGPU_MIXED_MAX_CG")
+    m.set_solver("exact")
+    d0, dr0, _, _, _ = ba.lm_step(m, p.x0, 30.0)
+    m.set_solver("mixed")
+    d1, dr1, _, _, _ = ba.lm_step(m, p.x0, 30.0)
+    info = ba.lm.last_solve_info(m)
+    assert info["solver"] == "exact" and info["converged"]
+    assert np.array_equal(d0, d1) and dr0 == dr1
+    st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=2, solver="mixed")
+    assert st.mixed_fallbacks == st.iter and all(r["solver"] == "exact" for r in st.rows)
+    m.close()
 
 
 def test_exact_solver_reports_indefinite_system_as_exception(ba):

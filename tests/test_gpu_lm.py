@@ -17,11 +17,13 @@ pytestmark = pytest.mark.gpu
 def _model(ba, p, solver=None, **kw):
     m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs, **kw)
     if solver is not None:
-        m.set_solver(solver)   # "pcg": matrix-free PCG; "exact": explicit Schur complement + dense Cholesky
+        # "pcg": matrix-free PCG; "exact": explicit Schur complement + dense FP64 Cholesky; "mixed": the same matrix
+        # factorised in FP32 on the tensor cores, preconditioning FP64 CG on the matrix-free operator
+        m.set_solver(solver)
     return m
 
 
-SOLVERS = ["pcg", "exact"]
+SOLVERS = ["pcg", "exact", "mixed"]
 
 
 def _rel(a, b):
