@@ -93,6 +93,16 @@ __device__ __forceinline__ bool wait_epoch(const unsigned long long* f, unsigned
     if (clock64() - t0 > 4000000000ll) return false;
   return true;
 }
+// the same at gpu scope (flags of the persistent sweep kernel; ~1 s)
+__device__ __forceinline__ bool wait_flag(const unsigned long long* f, unsigned long long epoch) {
+  const long long t0 = clock64();
+  unsigned long long v;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v >= epoch) return true;
+    if (clock64() - t0 > 2000000000ll) return false;
+  }
+}
 // two adjacent elements as doubles (the sweeps compute in FP64 whatever the factor's storage type)
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ double2 ld2(const float* p) {
@@ -891,6 +901,158 @@ k_chol_bwd(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, doub
   if (h == 0) y[(int64_t)kk * CT + c] -= ((s + part[0][c]) + part[1][c]) + part[2][c];
 }
 
+// ---- both sweeps as ONE persistent kernel ---------------------------------------------------------------------
+// CTA i owns tile row i of L (forward: y_i = Linv_ii (w_i - sum_{k<i} L_ik y_k)) and tile column i (backward:
+// x_i = Linv_ii' (y_i - sum_{k>i} L_ki' x_k)).  The CTAs are co-resident (cooperative launch, one per SM) and order
+// themselves with flags in global memory (release / acquire at gpu scope; epoch-valued, so they are never cleared):
+// the dependent chain is one flag hand-over + two 128 x 128 products per step instead of one kernel launch per step,
+// and everything off the chain (CTA i consuming y_k for k < i - 1) runs as early as its input exists.  The tile a CTA
+// will need next is in registers before it waits for the vector that goes with it; Linv_ii sits in shared memory.
+// Sums in FP64 whatever the storage type T of the factor.
+template <typename T> struct swt;
+template <> struct swt<float> { static constexpr int TPR = 2; };    // threads per row (forward) / per column (backward)
+template <> struct swt<double> { static constexpr int TPR = 4; };
+constexpr int SW_PAD = 4;
+template <typename T> constexpr int sweep_threads() { return CT * swt<T>::TPR; }
+template <typename T> constexpr int sweep_smem() { return CT * (CT + SW_PAD) * (int)sizeof(T); }
+
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT * swt<T>::TPR, 1)
+k_chol_sweep(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, const double* __restrict__ w,
+             double* y, double* x, int nb, unsigned long long* flags, unsigned long long epoch, int* __restrict__ info) {
+  constexpr int TPR = swt<T>::TPR, EPT = CT / TPR, NT = CT * TPR, LDS = CT + SW_PAD;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  T* Ds = reinterpret_cast<T*>(sm_raw);  // Linv_ii, rows LDS apart
+  __shared__ double vec[CT], mine[CT], part[TPR][CT];
+  __shared__ int ok_sh;
+  const int tid = threadIdx.x, i = blockIdx.x;
+  unsigned long long* ff = flags;               // forward: y_k complete
+  unsigned long long* fb = flags + CHOL_NBMAX;  // backward: x_k complete
+  if (tid == 0) ok_sh = 1;
+  {  // Linv_ii -> shared memory (off the dependent chain)
+    constexpr int EPP = 16 / (int)sizeof(T), PR = CT / EPP;
+    const T* D = Dinv + (int64_t)i * CT * CT;
+    for (int e = tid; e < CT * PR; e += NT) {
+      const int r = e / PR, c = (e - r * PR) * EPP;
+      cp_async16(Ds + r * LDS + c, D + r * CT + c);
+    }
+    cp_async_commit();
+  }
+  // wait for vector k of a sweep, bring it into vec[]
+  auto get_vec = [&](const unsigned long long* f, const double* v, int k) {
+    if (tid == 0 && !wait_flag(f + k, epoch)) ok_sh = 0;
+    __syncthreads();  // (also: everybody is done with the previous contents of vec)
+    if (tid < CT) vec[tid] = __ldcg(v + (int64_t)k * CT + tid);
+    __syncthreads();
+  };
+  // ---- forward: thread (r, pt) holds row r, columns pt * EPT ... of the current tile
+  {
+    const int r = tid / TPR, pt = tid - r * TPR;
+    T t[EPT];
+    auto load_tile = [&](int k) {
+      const T* src = L + ((int64_t)i * CT + r) * ld + (int64_t)k * CT + pt * EPT;
+#pragma unroll
+      for (int q = 0; q < EPT * (int)sizeof(T) / 16; ++q)
+        *reinterpret_cast<uint4*>(&t[q * (16 / (int)sizeof(T))]) = __ldg(reinterpret_cast<const uint4*>(src) + q);
+    };
+    double s = 0.0;
+    if (i > 0) load_tile(0);
+    for (int k = 0; k < i; ++k) {
+      get_vec(ff, y, k);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int c = 0; c < EPT; c += 4) {
+        a0 += (double)t[c] * vec[pt * EPT + c];
+        a1 += (double)t[c + 1] * vec[pt * EPT + c + 1];
+        a2 += (double)t[c + 2] * vec[pt * EPT + c + 2];
+        a3 += (double)t[c + 3] * vec[pt * EPT + c + 3];
+      }
+      s += (a0 + a1) + (a2 + a3);
+      if (k + 1 < i) load_tile(k + 1);  // in flight while the next vector is awaited
+    }
+#pragma unroll
+    for (int o = 1; o < TPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (pt == 0) mine[r] = w[(int64_t)i * CT + r] - s;
+    cp_async_wait<0>();
+    __syncthreads();
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < EPT; c += 2) {
+      a0 += (double)Ds[r * LDS + pt * EPT + c] * mine[pt * EPT + c];
+      a1 += (double)Ds[r * LDS + pt * EPT + c + 1] * mine[pt * EPT + c + 1];
+    }
+    double yv = a0 + a1;
+#pragma unroll
+    for (int o = 1; o < TPR; o <<= 1) yv += __shfl_xor_sync(0xffffffffu, yv, o);
+    __syncthreads();  // everybody has read mine[] (w_i') before it becomes y_i
+    if (pt == 0) {
+      mine[r] = yv;
+      __stcg(y + (int64_t)i * CT + r, yv);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_gpu_u64(ff + i, epoch);
+  }
+  // ---- backward: thread (c, g) holds column c, rows g * EPT ... of the current tile L_ki
+  {
+    const int c = tid % CT, g = tid / CT;
+    T t[EPT];
+    auto load_tile = [&](int k) {
+      const T* src = L + ((int64_t)k * CT + g * EPT) * ld + (int64_t)i * CT + c;
+#pragma unroll
+      for (int q = 0; q < EPT; ++q) t[q] = __ldg(src + (int64_t)q * ld);
+    };
+    double s = 0.0;
+    if (i + 1 < nb) load_tile(nb - 1);
+    for (int k = nb - 1; k > i; --k) {
+      get_vec(fb, x, k);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int q = 0; q < EPT; q += 4) {
+        a0 += (double)t[q] * vec[g * EPT + q];
+        a1 += (double)t[q + 1] * vec[g * EPT + q + 1];
+        a2 += (double)t[q + 2] * vec[g * EPT + q + 2];
+        a3 += (double)t[q + 3] * vec[g * EPT + q + 3];
+      }
+      s += (a0 + a1) + (a2 + a3);
+      if (k - 1 > i) load_tile(k - 1);
+    }
+    part[g][c] = s;
+    __syncthreads();
+    if (tid < CT) {
+      double tot = part[0][tid];
+#pragma unroll
+      for (int q = 1; q < TPR; ++q) tot += part[q][tid];
+      vec[tid] = mine[tid] - tot;  // y_i - sum_k L_ki' x_k
+    }
+    __syncthreads();
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < EPT; q += 2) {
+      a0 += (double)Ds[(g * EPT + q) * LDS + c] * vec[g * EPT + q];
+      a1 += (double)Ds[(g * EPT + q + 1) * LDS + c] * vec[g * EPT + q + 1];
+    }
+    part[g][c] = a0 + a1;
+    __syncthreads();
+    if (tid < CT) {
+      double tot = part[0][tid];
+#pragma unroll
+      for (int q = 1; q < TPR; ++q) tot += part[q][tid];
+      __stcg(x + (int64_t)i * CT + tid, tot);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      st_release_gpu_u64(fb + i, epoch);
+      if (!ok_sh) atomicCAS(info, 0, -4);  // a flag never arrived
+    }
+  }
+}
+
 // BAGPU_CHOL_NO_TC=1: the FP32 trailing update on the legacy tensor path (mma.sync, three TF32 terms) -- the A/B switch
 inline bool tc_enabled() {
   static const bool v = getenv("BAGPU_CHOL_NO_TC") == nullptr;
@@ -926,6 +1088,15 @@ int chol_plan_init(ba_handle* h, chol_plan& P, int64_t cn) {
   BA_CUDA((cudaFuncSetAttribute(k_chol_syrk<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
   BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
   BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_sweep<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem<float>()));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_sweep<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem<double>()));
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_sflags), 2 * CHOL_NBMAX * sizeof(unsigned long long)));
+  BA_CUDA(cudaMemset(P.d_sflags, 0, 2 * CHOL_NBMAX * sizeof(unsigned long long)));
+  {
+    int dev = 0;
+    BA_CUDA(cudaGetDevice(&dev));
+    BA_CUDA(cudaDeviceGetAttribute(&P.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
   BA_CUDA(cudaFuncSetAttribute(k_chol_syrk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   BA_CUDA(cudaFuncSetAttribute(k_chol_syrk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   BA_CUDA(cudaFuncSetAttribute(k_chol_potrf<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM));
@@ -943,6 +1114,7 @@ void chol_plan_release(chol_plan& P) {
   cudaFree(P.d_prof);
   cudaFree(P.d_ctl);
   cudaFree(P.d_cnt);
+  cudaFree(P.d_sflags);
   for (int r = 0; r < CHOL_RMAX; ++r)
     if (P.peer_ipc[r])
       for (int j = 0; j < 3; ++j)
@@ -1199,6 +1371,22 @@ int chol_solve_t(ba_handle* h, chol_plan& P, const T* L, const double* b, double
   const int64_t cn = P.cn;
   const T* const Dinv = reinterpret_cast<const T*>(P.d_Dinv);
   constexpr bool is32 = sizeof(T) == 4;
+  // one persistent kernel for both sweeps when its cn / 128 CTAs can be co-resident (one per SM); BAGPU_SWEEP_STEPS=1:
+  // the per-step kernels below (one launch per step, as a CUDA graph) -- the A/B switch and the route for larger systems
+  static const bool by_steps = getenv("BAGPU_SWEEP_STEPS") != nullptr;
+  if (!by_steps && !P.sweep_off && (int)(cn / CT) <= P.sm_count) {
+    int nbi = (int)(cn / CT);
+    int64_t ldv = cn;
+    unsigned long long ep = ++P.sweep_epoch;
+    double* yv = P.d_y;
+    void* args[] = {(void*)&L, (void*)&ldv, (void*)&Dinv, (void*)&b, (void*)&yv, (void*)&x, (void*)&nbi,
+                    (void*)&P.d_sflags, (void*)&ep, (void*)&P.d_info};
+    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_chol_sweep<T>), dim3((unsigned)nbi),
+                                                      dim3((unsigned)sweep_threads<T>()), args, (size_t)sweep_smem<T>(), s);
+    if (e == cudaSuccess) return BA_OK;
+    cudaGetLastError();   // e.g. the grid cannot be co-resident on this device / in this context: per-step kernels
+    P.sweep_off = true;
+  }
   const int nb = (int)(cn / CT);
   static const bool no_graph = getenv("BAGPU_NO_GRAPH") != nullptr || getenv("BAGPU_DEBUG_SYNC") != nullptr;
   // the sweeps always run from P.d_w into P.d_x: fixed pointers, so the 2 nb launches are captured once per

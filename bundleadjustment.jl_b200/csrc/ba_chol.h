@@ -47,6 +47,11 @@ struct chol_plan {
   bool solve_graph_32 = false;
   bool graph_off = false;        // capture not possible on the caller's stream
   bool attrs_set = false;
+  // persistent sweep kernel (both substitution sweeps in one cooperative launch): flags [2][CHOL_NBMAX], epoch-valued
+  unsigned long long* d_sflags = nullptr;
+  unsigned long long sweep_epoch = 0;
+  int sm_count = 0;
+  bool sweep_off = false;        // cooperative launch not possible here: per-step kernels
   // distributed factorisation over the ranks of a sharded handle (tile row i belongs to rank i mod R)
   bool dist_ready = false;
   chol_peers peers = {};
