@@ -292,22 +292,28 @@ k_chol_syrk(T* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, chol_p
 }
 
 // ---- trailing update of the FP32 factorisation on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) ----
-// A_ij (128 x 128, FP32) -= P_i P_j' over nk chunks of 32 k, P = the panels k (and k + 1).  FP32-level accuracy from
-// TF32 MMAs by the three-term split p = hi + lo (both TF32): the CTA's threads load the FP32 operands, split them in
-// registers and store hi and lo into shared memory in the canonical K-major 128-byte-swizzled layout (row r at 128 r,
-// 16-byte piece c at position c ^ (r & 7)); one thread issues, per 8 k, lo*hi' + hi*lo' into one TMEM accumulator and
-// hi*hi' into another (tcgen05.mma kind::tf32, M = N = 128) -- two accumulators, so that the small cross terms are not
-// rounded at the magnitude of the large one.  tcgen05.commit on an mbarrier per stage tells the producers when the
-// stage may be overwritten; two stages, so the operand loads + splits of chunk c + 1 run under the MMAs of chunk c.
-// Epilogue: tcgen05.ld of both accumulators (warp w reads TMEM lanes 32 (w % 4) .., i.e. rows of the tile; warps w and
-// w + 4 share the rows and split the columns), sum, subtract from the tile in global memory.
-constexpr int TC_THREADS = 256;
+// A_ij (128 x 128, FP32) -= P_i P_j' over nk chunks of 32 k, P = the panels k (and k + 1), for every tile (i >= j) of
+// the columns [j0, j0 + ncol): a PERSISTENT, warp-specialised kernel, one CTA per SM, tiles dealt round-robin.
+// FP32-level accuracy from TF32 MMAs by the three-term split p = hi + lo (both TF32).  Roles:
+//   * 8 producer warps: load the FP32 operand chunks (two chunks ahead, in registers), split them and store hi and lo
+//     into a 3-stage ring in shared memory, in the canonical K-major 128-byte-swizzled layout (row r at 128 r, 16-byte
+//     piece c at position c ^ (r & 7)); they run ahead across tile boundaries, so there is no pipeline drain per tile;
+//   * 1 MMA thread: per 8 k, lo*hi' + hi*lo' into one TMEM accumulator and hi*hi' into another (tcgen05.mma kind::tf32,
+//     M = N = 128) -- two accumulators, so that the small cross terms are not rounded at the magnitude of the large one;
+//     tcgen05.commit hands the stage back to the producers and, after the last chunk, the accumulators to the epilogue;
+//   * 4 epilogue warps: tcgen05.ld of both accumulators, sum, subtract from the tile in global memory, while the next
+//     tile is already being accumulated in the other half of the tensor memory (2 x 256 columns).
+// The MMA's M side (TMEM lanes) is P_j and its N side (TMEM columns) is P_i, i.e. the accumulator is the TRANSPOSED
+// update: an epilogue warp's 32 lanes then hold 32 consecutive columns of one row of A_ij -- coalesced 128-byte accesses.
+constexpr int TC_PROD_WARPS = 8, TC_EPI_WARPS = 4;
+constexpr int TC_PROD_THREADS = 32 * TC_PROD_WARPS;
+constexpr int TC_THREADS = 32 * (TC_PROD_WARPS + 1 + TC_EPI_WARPS);  // 416
 constexpr int TC_KC = 32;                            // floats per row of a stage = 128 bytes = one swizzle atom
 constexpr int TC_OPER = CT * 128;                    // bytes of one operand tile of a stage (128 rows x 128 B)
-constexpr int TC_STAGE = 4 * TC_OPER;                // A hi, A lo, B hi, B lo
-constexpr int TC_STAGES = 1;
+constexpr int TC_STAGE = 4 * TC_OPER;                // P_i hi, P_i lo, P_j hi, P_j lo
+constexpr int TC_STAGES = 3;
 constexpr int TC_SMEM = TC_STAGES * TC_STAGE + 1024; // + slack to align the tiles to 1024 B (swizzle atom)
-constexpr unsigned TC_COLS = 256;                    // TMEM columns: accumulator of hi*hi' and of the cross terms
+constexpr unsigned TC_COLS = 512;                    // TMEM columns: two buffers x (accumulator of hi*hi' + of the cross terms)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100: version 1): start address, LBO 1, SBO 1024 B
@@ -348,160 +354,209 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned pari
     if (clock64() - t0 > 2000000000ll) return false;
   }
 }
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-  unsigned r[32];
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+  unsigned r[16];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// x = hi + lo + O(2^-23 |x|) with hi and lo TF32 (13 low mantissa bits zero), round to nearest (ties away) by integer
+// arithmetic: five full-rate instructions per element (cvt.rna.tf32.f32 costs about four each, twice)
+__device__ __forceinline__ void split_tf32_fast(float x, unsigned& hi, unsigned& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
 }
 
-template <bool DIST>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-k_chol_syrk_tc(float* __restrict__ A, int64_t ld, int k, int j0, int nb, int i0, chol_peers P, int* __restrict__ info,
-               int nk, int kwait) {
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __maxnreg__(152)  // 416 threads: 152 registers each fit the SM's register file
+k_chol_syrk_tc(float* __restrict__ A, int64_t ld, int k, int j0, int ncol, int nb, int* __restrict__ info, int nk) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  __shared__ __align__(8) unsigned long long bar[TC_STAGES];
+  __shared__ __align__(8) unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
   __shared__ unsigned tmem_base_sh;
   __shared__ int ok_sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int j = j0 + blockIdx.y;
-  const int i = DIST ? i0 + P.R * (int)blockIdx.x : j + (int)blockIdx.x;
-  if (i >= nb || i < j) return;
   if (tid == 0) ok_sh = *reinterpret_cast<volatile int*>(info) == 0 ? 1 : 0;  // an earlier failure (time-out, pivot): nothing to do
   __syncthreads();
   if (!ok_sh) return;
-  if (DIST) {
-    // (a rank reports its panels in order, so the flag of the last panel used implies the earlier ones)
-    if (tid < P.R && !wait_epoch(P.ctl[P.q] + CHOL_NBMAX + 16 * kwait + tid, P.epoch)) ok_sh = 0;
-    __syncthreads();
-    if (!ok_sh) {
-      if (tid == 0) atomicCAS(info, 0, -2);
-      return;
-    }
-  }
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
-  if (warp == 0) {  // one warp allocates the tensor memory of the CTA (and frees it at the end)
+  if (warp == TC_PROD_WARPS) {  // the MMA warp allocates the tensor memory of the CTA (and frees it at the end)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(TC_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid == 32) {
-#pragma unroll
-    for (int st = 0; st < TC_STAGES; ++st)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[st])) : "memory");
+  if (tid == 0) {
+    for (int st = 0; st < TC_STAGES; ++st) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(TC_PROD_THREADS) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty[st])) : "memory");
+    }
+    for (int bf = 0; bf < 2; ++bf) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tfull[bf])) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&tempty[bf])), "r"(32 * TC_EPI_WARPS) : "memory");
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem = tmem_base_sh;
-  const bool diag = (i == j);  // P_i = P_j: one operand pair serves both sides
-  const float* Pi = A + (int64_t)i * CT * ld + (int64_t)k * CT;
-  const float* Pj = A + (int64_t)j * CT * ld + (int64_t)k * CT;
+  // tiles of this launch: columns j = j0 .. j0 + ncol - 1 (< nb), rows i = j .. nb - 1; tile t -> (j, i)
+  const int jend = min(j0 + ncol, nb);
+  int ntiles = 0;
+  for (int j = j0; j < jend; ++j) ntiles += nb - j;
+  // this CTA's tiles, t = blockIdx.x, + gridDim.x, ...: (column j, row j + rem), advanced incrementally
+  struct tile_iter {
+    int j, rem, nb;
+    __device__ __forceinline__ void advance(int by) {
+      rem += by;
+      while (j < nb && rem >= nb - j) {  // (j == nb: past the last tile)
+        rem -= nb - j;
+        ++j;
+      }
+    }
+    __device__ __forceinline__ int row() const { return j + rem; }
+  };
+  auto first_tile = [&]() {
+    tile_iter it = {j0, 0, nb};
+    it.advance((int)blockIdx.x);
+    return it;
+  };
   // instruction descriptor: D FP32 (bits 4-5 = 1), A and B TF32 (bits 7-9, 10-12 = 2), both K-major, N / 8 at bit 17,
   // M / 16 at bit 24
   constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(CT >> 3) << 17) | ((unsigned)(CT >> 4) << 24);
-  // this thread's four 16-byte pieces of an operand tile: piece e = tid + 256 q -> row e / 8, piece e % 8 of the row.
-  // The FP32 data of chunk c + 1 is fetched into registers right after the MMAs of chunk c have been issued, so the
-  // global-load latency runs under those MMAs.
-  float4 va[4], vb[4];
-  auto fetch = [&](int c) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = tid + TC_THREADS * q, row = e >> 3, pc = e & 7;
-      va[q] = *reinterpret_cast<const float4*>(Pi + (int64_t)row * ld + c * TC_KC + pc * 4);
-      if (!diag) vb[q] = *reinterpret_cast<const float4*>(Pj + (int64_t)row * ld + c * TC_KC + pc * 4);
-    }
-  };
-  auto put = [&](const float4 (&v)[4], unsigned char* hi) {
-    unsigned char* lo = hi + TC_OPER;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = tid + TC_THREADS * q, row = e >> 3, pc = e & 7;
-      const int off = row * 128 + ((pc ^ (row & 7)) << 4);
-      uint4 h, l;
-      split_tf32(v[q].x, h.x, l.x);
-      split_tf32(v[q].y, h.y, l.y);
-      split_tf32(v[q].z, h.z, l.z);
-      split_tf32(v[q].w, h.w, l.w);
-      *reinterpret_cast<uint4*>(hi + off) = h;
-      *reinterpret_cast<uint4*>(lo + off) = l;
-    }
-  };
   bool failed = false;
-  fetch(0);
-  for (int c = 0; c < nk; ++c) {
-    const int st = c % TC_STAGES;
-    unsigned char* base = tiles + st * TC_STAGE;
-    // the MMAs that read this stage two chunks ago are done (every thread decides the same way)
-    const int bad = (c >= TC_STAGES) ? !mbar_wait(&bar[st], (unsigned)((c / TC_STAGES - 1) & 1)) : 0;
-    if (__syncthreads_or(bad)) {
-      failed = true;
-      break;
+  if (warp < TC_PROD_WARPS) {
+    // ---- producers: chunk sequence g = 0, 1, ... over (tile, chunk); this thread's four 16-byte pieces of an operand
+    // tile: piece e = tid + 256 q -> row e / 8, piece e % 8 of the row
+    const int row0 = tid >> 3, pc = tid & 7;
+    const int soff = row0 * 128 + ((pc ^ (row0 & 7)) << 4);  // (row + 32 q) & 7 == row & 7
+    struct chunk_regs { float4 a[4], b[4]; };
+    const int nchunks = ((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * nk;  // of this CTA
+    tile_iter it = first_tile();
+    int cnext = 0;  // chunk of the tile `it` the next fetch brings
+    auto fetch = [&](chunk_regs& v) {
+      const int c = cnext, i = it.row(), j = it.j;
+      if (++cnext == nk) {
+        cnext = 0;
+        it.advance((int)gridDim.x);
+      }
+      const float* Pi = A + ((int64_t)i * CT + row0) * ld + (int64_t)k * CT + c * TC_KC + pc * 4;
+      const float* Pj = A + ((int64_t)j * CT + row0) * ld + (int64_t)k * CT + c * TC_KC + pc * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v.a[q] = *reinterpret_cast<const float4*>(Pi + (int64_t)(32 * q) * ld);
+      if (i != j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v.b[q] = *reinterpret_cast<const float4*>(Pj + (int64_t)(32 * q) * ld);
+      }
+      return i != j;
+    };
+    auto put1 = [&](const float4& v, unsigned char* hi, int off) {
+      uint4 h, l;
+      split_tf32_fast(v.x, h.x, l.x);
+      split_tf32_fast(v.y, h.y, l.y);
+      split_tf32_fast(v.z, h.z, l.z);
+      split_tf32_fast(v.w, h.w, l.w);
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(hi + TC_OPER + off) = l;
+    };
+    auto step = [&](int g, const chunk_regs& v, bool both) {
+      const int st = g % TC_STAGES;
+      unsigned char* base = tiles + st * TC_STAGE;
+      // the MMAs that read this stage TC_STAGES chunks ago are done
+      if (g >= TC_STAGES && !mbar_wait(&empty[st], (unsigned)((g / TC_STAGES - 1) & 1))) failed = true;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) put1(v.a[q], base, soff + q * 32 * 128);
+      if (both) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) put1(v.b[q], base + 2 * TC_OPER, soff + q * 32 * 128);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+      mbar_arrive(&full[st]);
+    };
+    chunk_regs v0, v1;
+    bool b0 = false, b1 = false;
+    if (nchunks > 0) b0 = fetch(v0);
+    if (nchunks > 1) b1 = fetch(v1);
+    for (int g = 0; g < nchunks && !failed; g += 2) {  // (nk is even, so nchunks is)
+      step(g, v0, b0);
+      if (g + 2 < nchunks) b0 = fetch(v0);
+      step(g + 1, v1, b1);
+      if (g + 3 < nchunks) b1 = fetch(v1);
     }
-    put(va, base);
-    if (!diag) put(vb, base + 2 * TC_OPER);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy stores above -> visible to the tensor core
-    __syncthreads();
-    if (tid == 0) {
+  } else if (warp == TC_PROD_WARPS) {
+    // ---- MMA issuer (one lane)
+    if (lane == 0) {
+      int g = 0, tc = 0;
+      tile_iter it = first_tile();
+      for (int t = blockIdx.x; t < ntiles && !failed; t += gridDim.x, ++tc, it.advance((int)gridDim.x)) {
+        const int i = it.row(), j = it.j;
+        const int bf = tc & 1;
+        // the epilogue has drained this accumulator buffer (two tiles ago)
+        if (tc >= 2 && !mbar_wait(&tempty[bf], (unsigned)((tc / 2 - 1) & 1))) failed = true;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned d = tmem + bf * 2 * CT;
+        for (int c = 0; c < nk && !failed; ++c, ++g) {
+          const int st = g % TC_STAGES;
+          if (!mbar_wait(&full[st], (unsigned)((g / TC_STAGES) & 1))) failed = true;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned sa = smem_u32(tiles + st * TC_STAGE);
+          // M side (TMEM lanes) = P_j, N side (TMEM columns) = P_i; on the diagonal P_j = P_i
+          const unsigned long long nhi = umma_desc_sw128(sa), nlo = umma_desc_sw128(sa + TC_OPER);
+          const unsigned long long mhi = (i == j) ? nhi : umma_desc_sw128(sa + 2 * TC_OPER);
+          const unsigned long long mlo = (i == j) ? nlo : umma_desc_sw128(sa + 3 * TC_OPER);
+#pragma unroll
+          for (int ks = 0; ks < TC_KC / 8; ++ks) {  // 8 k = 32 bytes further along the rows: + 2 in the address field
+            const unsigned acc = (c > 0 || ks > 0) ? 1u : 0u;
+            umma_tf32(d + CT, mlo + 2 * ks, nhi + 2 * ks, IDESC, acc);
+            umma_tf32(d + CT, mhi + 2 * ks, nlo + 2 * ks, IDESC, 1u);
+            umma_tf32(d, mhi + 2 * ks, nhi + 2 * ks, IDESC, acc);
+          }
+          umma_commit(&empty[st]);  // arrives once these (and all earlier) MMAs have completed
+        }
+        umma_commit(&tfull[bf]);
+      }
+    }
+  } else {
+    // ---- epilogue: warp e reads TMEM lanes 32 (warp % 4) .. = columns of the tile; TMEM column n = row n of the tile
+    const int q4 = warp & 3;
+    int tc = 0;
+    tile_iter it = first_tile();
+    for (int t = blockIdx.x; t < ntiles && !failed; t += gridDim.x, ++tc, it.advance((int)gridDim.x)) {
+      const int i = it.row(), j = it.j;
+      const int bf = tc & 1;
+      if (!__all_sync(0xffffffffu, mbar_wait(&tfull[bf], (unsigned)((tc / 2) & 1)))) {  // (warp-uniform: tcgen05.ld is .aligned)
+        failed = true;
+        break;
+      }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned sa = smem_u32(base);
-      const unsigned long long ahi = umma_desc_sw128(sa), alo = umma_desc_sw128(sa + TC_OPER);
-      const unsigned long long bhi = diag ? ahi : umma_desc_sw128(sa + 2 * TC_OPER);
-      const unsigned long long blo = diag ? alo : umma_desc_sw128(sa + 3 * TC_OPER);
+      float* C = A + (int64_t)i * CT * ld + (int64_t)j * CT + 32 * q4 + lane;
+      const unsigned ta = tmem + ((unsigned)(32 * q4) << 16) + (unsigned)(bf * 2 * CT);
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {  // 16 rows of the tile per pass: 16 coalesced loads in flight per lane
+        float d0[16], d1[16], cv[16];
 #pragma unroll
-      for (int ks = 0; ks < TC_KC / 8; ++ks) {  // 8 k = 32 bytes further along the rows: + 2 in the address field
-        const unsigned acc = (c > 0 || ks > 0) ? 1u : 0u;
-        umma_tf32(tmem + CT, alo + 2 * ks, bhi + 2 * ks, IDESC, acc);
-        umma_tf32(tmem + CT, ahi + 2 * ks, blo + 2 * ks, IDESC, 1u);
-        umma_tf32(tmem, ahi + 2 * ks, bhi + 2 * ks, IDESC, acc);
+        for (int n = 0; n < 16; ++n) cv[n] = C[(int64_t)(cc * 16 + n) * ld];
+        tmem_ld16(ta + cc * 16, d0);
+        tmem_ld16(ta + CT + cc * 16, d1);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) C[(int64_t)(cc * 16 + n) * ld] = cv[n] - (d0[n] + d1[n]);
       }
-      umma_commit(&bar[st]);  // arrives once these (and all earlier) MMAs have completed
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tempty[bf]);
     }
-    if (c + 1 < nk) fetch(c + 1);
   }
-  if (!failed) {  // all MMAs done: the commit of the last chunk
-    const int c = nk - 1;
-    const int bad = !mbar_wait(&bar[c % TC_STAGES], (unsigned)((c / TC_STAGES) & 1));
-    failed = __syncthreads_or(bad) != 0;
-  }
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (!failed) {
-    const int q4 = warp & 3, hf = warp >> 2;  // TMEM lane quarter = tile rows 32 q4 ..; column half
-    const int row = 32 * q4 + lane;
-    float* C = A + ((int64_t)i * CT + row) * ld + (int64_t)j * CT + hf * 64;
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      float d0[32], d1[32];
-      const unsigned ta = tmem + ((unsigned)(32 * q4) << 16) + (unsigned)(hf * 64 + cc * 32);
-      tmem_ld32(ta, d0);
-      tmem_ld32(ta + CT, d1);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4* p = reinterpret_cast<float4*>(C + cc * 32 + 4 * q);
-        float4 cv = *p;
-        cv.x -= d0[4 * q] + d1[4 * q];
-        cv.y -= d0[4 * q + 1] + d1[4 * q + 1];
-        cv.z -= d0[4 * q + 2] + d1[4 * q + 2];
-        cv.w -= d0[4 * q + 3] + d1[4 * q + 3];
-        *p = cv;
-      }
-    }
-  } else if (tid == 0) {
-    atomicCAS(info, 0, -3);  // an MMA completion never arrived
-  }
+  if (failed) atomicCAS(info, 0, -3);  // an mbarrier phase never completed
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_COLS) : "memory");
+  if (warp == TC_PROD_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_COLS) : "memory");
 }
 
 // panel solve: P_i[half] <- P_i[half] Linv_kk'.
@@ -1097,8 +1152,7 @@ int chol_plan_init(ba_handle* h, chol_plan& P, int64_t cn) {
     BA_CUDA(cudaGetDevice(&dev));
     BA_CUDA(cudaDeviceGetAttribute(&P.sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  BA_CUDA(cudaFuncSetAttribute(k_chol_syrk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   BA_CUDA(cudaFuncSetAttribute(k_chol_potrf<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM));
   BA_CUDA(cudaFuncSetAttribute(k_chol_potrf<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM));
   P.attrs_set = true;
@@ -1162,9 +1216,12 @@ int chol_factor_t(ba_handle* h, chol_plan& P, T* A, cudaStream_t s, int* info_ho
   auto update = [&](int k, int npan, int j0, int ncol, cudaStream_t st) {
     if (j0 >= nb || ncol <= 0) return;
     if constexpr (sizeof(T) == 4) {
-      if (tc_enabled()) {  // FP32: full 128 x 128 tiles on the tcgen05 tensor cores
-        k_chol_syrk_tc<false><<<dim3(nb - j0, std::min(ncol, nb - j0)), TC_THREADS, TC_SMEM, st>>>(
-            A, ld, k, j0, nb, 0, solo, P.d_info, (CT / TC_KC) * npan, 0);
+      if (tc_enabled()) {  // FP32: 128 x 128 tiles on the tcgen05 tensor cores, persistent CTAs (one per SM)
+        const int nc = std::min(ncol, nb - j0);
+        int64_t ntiles = 0;
+        for (int j = j0; j < j0 + nc; ++j) ntiles += nb - j;
+        k_chol_syrk_tc<<<(unsigned)std::min<int64_t>(ntiles, P.sm_count), TC_THREADS, TC_SMEM, st>>>(
+            A, ld, k, j0, nc, nb, P.d_info, (CT / TC_KC) * npan);
         return;
       }
     }
@@ -1333,13 +1390,6 @@ int chol_factor_dist_t(ba_handle* h, chol_plan& P, T* A, cudaStream_t s) {
     if (j0 >= nb || ncol <= 0) return;
     const int n = count_own(j0);
     if (n <= 0) return;
-    if constexpr (sizeof(T) == 4) {
-      if (tc_enabled()) {
-        k_chol_syrk_tc<true><<<dim3(n, std::min(ncol, nb - j0)), TC_THREADS, TC_SMEM, st>>>(
-            A, ld, k, j0, nb, first_own(j0), V, P.d_info, (CT / TC_KC) * npan, k + npan - 1);
-        return;
-      }
-    }
     k_chol_syrk<T, true><<<dim3(2 * n, std::min(ncol, nb - j0)), GEMM_THREADS, GEMM_SMEM, st>>>(
         A, ld, k, j0, nb, first_own(j0), V, P.d_info, NKP * npan, k + npan - 1);
   };

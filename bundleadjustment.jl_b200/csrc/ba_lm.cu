@@ -533,7 +533,8 @@ struct Solver {
     if ((rc = check())) return rc;
     cudaEventRecord(S.ev[6], s);  // the factorisation proper starts here
     if constexpr (sizeof(T) == 8) rc = S.chol.dist_ready ? chol_factor_dist(h, S.chol, A, s) : chol_factor(h, S.chol, A, s, nullptr);
-    else rc = S.chol.dist_ready ? chol_factor_dist32(h, S.chol, A, s) : chol_factor32(h, S.chol, A, s, nullptr);
+    else rc = chol_factor32(h, S.chol, A, s, nullptr);  // replicated on every rank: the tcgen05 factorisation of a single GPU
+                                                         // is faster than the distributed one's chain of diagonal blocks
     if (rc) return rc;
     BA_CUDA(cudaMemcpyAsync(info, S.chol.d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
     BA_CUDA(cudaStreamSynchronize(s));
