@@ -1220,7 +1220,11 @@ int chol_factor_t(ba_handle* h, chol_plan& P, T* A, cudaStream_t s, int* info_ho
         const int nc = std::min(ncol, nb - j0);
         int64_t ntiles = 0;
         for (int j = j0; j < j0 + nc; ++j) ntiles += nb - j;
-        k_chol_syrk_tc<<<(unsigned)std::min<int64_t>(ntiles, P.sm_count), TC_THREADS, TC_SMEM, st>>>(
+        // a few tiles per CTA (not the whole update): the high-priority panel kernels of the look-ahead get SMs as
+        // CTAs retire, while the operand ring still runs across the tile boundaries inside a CTA
+        static const int per_cta = getenv("BAGPU_TC_TILES_PER_CTA") ? std::max(1, atoi(getenv("BAGPU_TC_TILES_PER_CTA"))) : 8;
+        const int64_t grid = std::max<int64_t>(std::min<int64_t>(ntiles, P.sm_count), (ntiles + per_cta - 1) / per_cta);
+        k_chol_syrk_tc<<<(unsigned)grid, TC_THREADS, TC_SMEM, st>>>(
             A, ld, k, j0, nc, nb, P.d_info, (CT / TC_KC) * npan);
         return;
       }
@@ -1500,6 +1504,7 @@ int dbg_chol_t(int device, int64_t n, const double* A_rowmajor, const double* b,
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   int rc = BA_OK, info = 0;
   auto done = [&](int code) {
+    if (code == BA_ERR_CUDA && !hh.err.empty()) fprintf(stderr, "[bagpu] ba_dbg_chol: %s\n", hh.err.c_str());
     cudaFree(dA); cudaFree(db);
     ba::chol_plan_release(P);
     if (s) cudaStreamDestroy(s);
@@ -1532,7 +1537,13 @@ int dbg_chol_t(int device, int64_t n, const double* A_rowmajor, const double* b,
   }
   cudaEventRecord(e2, s);
   if (rc) return done(rc);
-  if (cudaStreamSynchronize(s) != cudaSuccess) return done(BA_ERR_CUDA);
+  {
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "[bagpu] ba_dbg_chol: %s\n", cudaGetErrorString(e));
+      return done(BA_ERR_CUDA);
+    }
+  }
   cudaMemcpy(&info, P.d_info, sizeof(int), cudaMemcpyDeviceToHost);
   if (factor_ms) cudaEventElapsedTime(factor_ms, e0, e1);
   if (solve_ms) cudaEventElapsedTime(solve_ms, e1, e2);

@@ -67,6 +67,13 @@ inline int64_t exact_auto_cams() {
   static const int64_t v = getenv("BAGPU_EXACT_AUTO_CAMS") ? atoll(getenv("BAGPU_EXACT_AUTO_CAMS")) : 2048;
   return v;
 }
+// AUTO: dense systems of at least this many rows are factorised in FP32 on the tensor cores (BA_SOLVER_MIXED), smaller
+// ones in FP64 (BA_SOLVER_EXACT): below ~1000 cameras the chain of diagonal blocks dominates both factorisations and
+// the extra CG iterations of the mixed solve cost more than the factorisation saves
+inline int64_t mixed_auto_rows() {
+  static const int64_t v = getenv("BAGPU_MIXED_AUTO_ROWS") ? atoll(getenv("BAGPU_MIXED_AUTO_ROWS")) : 8192;
+  return v;
+}
 inline double exact_max_bytes() {
   static const double v = (getenv("BAGPU_EXACT_MAX_GB") ? atof(getenv("BAGPU_EXACT_MAX_GB")) : 16.0) * 1e9;
   return v;
@@ -92,7 +99,7 @@ int lm_exact_workspace(ba_handle* h) {
   S.exact = h->sorted && ncams > 0 &&
             (h->solver == BA_SOLVER_EXACT || h->solver == BA_SOLVER_MIXED ||
              (h->solver == BA_SOLVER_AUTO && ncams <= exact_auto_cams()));
-  S.mixed = S.exact && h->solver == BA_SOLVER_MIXED;
+  S.mixed = S.exact && (h->solver == BA_SOLVER_MIXED || (h->solver == BA_SOLVER_AUTO && 9 * ncams >= mixed_auto_rows()));
   S.cn = chol_padded(9 * ncams);
   if (S.exact && (double)S.cn * (double)S.cn * 8.0 > exact_max_bytes()) {
     if (h->solver == BA_SOLVER_EXACT || h->solver == BA_SOLVER_MIXED) {

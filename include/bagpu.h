@@ -45,7 +45,8 @@ enum {
  * BA_SOLVER_EXACT is their counterpart: the reduced camera system assembled explicitly and factorised by a dense
  * FP64 Cholesky (what ldl_factorize + ldl_solve!, src/ldl_aux.jl:122-201,4-42, amount to after the ordering has
  * eliminated residual rows and points) plus refinement steps with the matrix-free FP64 residual.  BA_SOLVER_PCG is
- * the matrix-free preconditioned CG (stopped at pcg_tol).  AUTO: exact up to 2048 cameras, PCG above.
+ * the matrix-free preconditioned CG (stopped at pcg_tol).  AUTO: a dense solve up to 2048 cameras (MIXED from 8192
+ * camera unknowns on, EXACT below), PCG above.
  * BA_SOLVER_MIXED is the reference's mixed-precision mode (src/lm.jl:92-98,165-173: facto_type below the model type,
  * "factorise in Float32, everything else in Float64"): the same explicit reduced camera
  * system, factorised in FP32 storage on the tensor cores (three TF32 MMAs per product: FP32-level accuracy), and that

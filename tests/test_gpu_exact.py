@@ -136,6 +136,12 @@ def test_auto_picks_exact_for_small_camera_systems_and_pcg_for_large(ba):
     ba.lm_step(m, p.x0, 30.0)
     assert ba.lm.last_solve_info(m)["solver"] == "exact"
     m.close()
+    # dense systems from 8192 camera unknowns on: the FP32 tensor-core factor + FP64 CG
+    p = ba.synth.make_problem((920, 30000, 150000))
+    m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    ba.lm_step(m, p.x0, 30.0)
+    assert ba.lm.last_solve_info(m)["solver"] == "mixed"
+    m.close()
 
 
 def test_pcg_iteration_cap_is_reported(ba):

@@ -41,7 +41,7 @@ def _worker(rank, world, port, q, small_max, solver):
 
 # PCG with the fused single-CTA vector kernel / with the multi-CTA kernels; the exact solve (sharded assembly of the
 # reduced camera system, integer allreduce, replicated factorisation)
-@pytest.mark.parametrize("solver,small_max", [("pcg", None), ("pcg", "0"), ("exact", None)])
+@pytest.mark.parametrize("solver,small_max", [("pcg", None), ("pcg", "0"), ("exact", None), ("mixed", None)])
 def test_two_gpu_lm_matches_one_gpu(ba, small_max, solver):
     import torch
     if torch.cuda.device_count() < 2:
@@ -50,7 +50,7 @@ def test_two_gpu_lm_matches_one_gpu(ba, small_max, solver):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 1000)
-    port += (7 if small_max else 0) + (3 if solver == "exact" else 0)
+    port += (7 if small_max else 0) + (3 if solver == "exact" else 0) + (5 if solver == "mixed" else 0)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q, small_max, solver)) for r in range(2)]
     for pr in procs:
         pr.start()
@@ -149,7 +149,7 @@ def test_two_gpu_deflated_pcg_matches_one_gpu(ba):
     assert abs(got["objective"] - st.objective) <= 1e-8 * st.objective
 
 
-@pytest.mark.parametrize("solver", ["pcg", "exact"])
+@pytest.mark.parametrize("solver", ["pcg", "exact", "mixed"])
 def test_single_process_multi_gpu_handle_matches_one_gpu(ba, oracle, solver):
     """ba_create_multi: several GPUs behind one handle in one process (the mode the reference's single Julia
     process can reach).  Every host-pointer entry point must return the full-length arrays of the one-GPU handle."""
