@@ -93,16 +93,6 @@ __device__ __forceinline__ bool wait_epoch(const unsigned long long* f, unsigned
     if (clock64() - t0 > 4000000000ll) return false;
   return true;
 }
-// the same at gpu scope (flags of the persistent sweep kernel; ~1 s)
-__device__ __forceinline__ bool wait_flag(const unsigned long long* f, unsigned long long epoch) {
-  const long long t0 = clock64();
-  unsigned long long v;
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-    if (v >= epoch) return true;
-    if (clock64() - t0 > 2000000000ll) return false;
-  }
-}
 // two adjacent elements as doubles (the sweeps compute in FP64 whatever the factor's storage type)
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ double2 ld2(const float* p) {
@@ -958,10 +948,12 @@ k_chol_bwd(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, doub
 
 // ---- both sweeps as ONE persistent kernel ---------------------------------------------------------------------
 // CTA i owns tile row i of L (forward: y_i = Linv_ii (w_i - sum_{k<i} L_ik y_k)) and tile column i (backward:
-// x_i = Linv_ii' (y_i - sum_{k>i} L_ki' x_k)).  The CTAs are co-resident (cooperative launch, one per SM) and order
-// themselves with flags in global memory (release / acquire at gpu scope; epoch-valued, so they are never cleared):
-// the dependent chain is one flag hand-over + two 128 x 128 products per step instead of one kernel launch per step,
-// and everything off the chain (CTA i consuming y_k for k < i - 1) runs as early as its input exists.  The tile a CTA
+// x_i = Linv_ii' (y_i - sum_{k>i} L_ki' x_k)).  The CTAs are co-resident (cooperative launch, one per SM) and hand the
+// vectors over through global memory with the flag INSIDE the data: an element travels as one 16-byte store
+// {low word, flag, high word, flag} (flag = the launch's epoch, so nothing is ever cleared) and a consumer polls the
+// element itself until both flags match -- no fence, no separate flag store, no extra barrier on the dependent chain,
+// which is one such hand-over + two 128 x 128 products per step instead of one kernel launch per step;
+// everything off the chain (CTA i consuming y_k for k < i - 1) runs as early as its input exists.  The tile a CTA
 // will need next is in registers before it waits for the vector that goes with it; Linv_ii sits in shared memory.
 // Sums in FP64 whatever the storage type T of the factor.
 template <typename T> struct swt;
@@ -971,22 +963,39 @@ constexpr int SW_PAD = 4;
 template <typename T> constexpr int sweep_threads() { return CT * swt<T>::TPR; }
 template <typename T> constexpr int sweep_smem() { return CT * (CT + SW_PAD) * (int)sizeof(T); }
 
-__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// a double and its flag as ONE 16-byte store / load; each 8-byte half carries the flag, so a reader that sees both
+// flags has both words whatever the granularity at which the store became visible
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned flag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(flag),
+               "r"((unsigned)__double2hiint(v)), "r"(flag)
+               : "memory");
+}
+__device__ __forceinline__ bool ll_load(const uint4* p, unsigned flag, double& v) {  // bounded (~1 s)
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned a, fa, b, fb;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(p) : "memory");
+    if (fa == flag && fb == flag) {
+      v = __hiloint2double((int)b, (int)a);
+      return true;
+    }
+    if (clock64() - t0 > 2000000000ll) {
+      v = 0.0;
+      return false;
+    }
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(CT * swt<T>::TPR, 1)
 k_chol_sweep(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, const double* __restrict__ w,
-             double* y, double* x, int nb, unsigned long long* flags, unsigned long long epoch, int* __restrict__ info) {
+             uint4* yq, uint4* xq, double* x, int nb, unsigned flag, int* __restrict__ info) {
   constexpr int TPR = swt<T>::TPR, EPT = CT / TPR, NT = CT * TPR, LDS = CT + SW_PAD;
   extern __shared__ __align__(16) unsigned char sm_raw[];
   T* Ds = reinterpret_cast<T*>(sm_raw);  // Linv_ii, rows LDS apart
   __shared__ double vec[CT], mine[CT], part[TPR][CT];
   __shared__ int ok_sh;
   const int tid = threadIdx.x, i = blockIdx.x;
-  unsigned long long* ff = flags;               // forward: y_k complete
-  unsigned long long* fb = flags + CHOL_NBMAX;  // backward: x_k complete
   if (tid == 0) ok_sh = 1;
   {  // Linv_ii -> shared memory (off the dependent chain)
     constexpr int EPP = 16 / (int)sizeof(T), PR = CT / EPP;
@@ -997,11 +1006,14 @@ k_chol_sweep(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, co
     }
     cp_async_commit();
   }
-  // wait for vector k of a sweep, bring it into vec[]
-  auto get_vec = [&](const unsigned long long* f, const double* v, int k) {
-    if (tid == 0 && !wait_flag(f + k, epoch)) ok_sh = 0;
-    __syncthreads();  // (also: everybody is done with the previous contents of vec)
-    if (tid < CT) vec[tid] = __ldcg(v + (int64_t)k * CT + tid);
+  // wait for vector k of a sweep (each of 128 threads polls its own element), bring it into vec[]
+  auto get_vec = [&](const uint4* vq, int k) {
+    __syncthreads();  // everybody is done with the previous contents of vec
+    if (tid < CT) {
+      double v;
+      if (!ll_load(vq + (int64_t)k * CT + tid, flag, v)) ok_sh = 0;
+      vec[tid] = v;
+    }
     __syncthreads();
   };
   // ---- forward: thread (r, pt) holds row r, columns pt * EPT ... of the current tile
@@ -1017,7 +1029,7 @@ k_chol_sweep(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, co
     double s = 0.0;
     if (i > 0) load_tile(0);
     for (int k = 0; k < i; ++k) {
-      get_vec(ff, y, k);
+      get_vec(yq, k);
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
       for (int c = 0; c < EPT; c += 4) {
@@ -1046,11 +1058,9 @@ k_chol_sweep(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, co
     __syncthreads();  // everybody has read mine[] (w_i') before it becomes y_i
     if (pt == 0) {
       mine[r] = yv;
-      __stcg(y + (int64_t)i * CT + r, yv);
+      ll_store(yq + (int64_t)i * CT + r, yv, flag);
     }
-    __threadfence();
     __syncthreads();
-    if (tid == 0) st_release_gpu_u64(ff + i, epoch);
   }
   // ---- backward: thread (c, g) holds column c, rows g * EPT ... of the current tile L_ki
   {
@@ -1064,7 +1074,7 @@ k_chol_sweep(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, co
     double s = 0.0;
     if (i + 1 < nb) load_tile(nb - 1);
     for (int k = nb - 1; k > i; --k) {
-      get_vec(fb, x, k);
+      get_vec(xq, k);
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
       for (int q = 0; q < EPT; q += 4) {
@@ -1097,14 +1107,11 @@ k_chol_sweep(const T* __restrict__ L, int64_t ld, const T* __restrict__ Dinv, co
       double tot = part[0][tid];
 #pragma unroll
       for (int q = 1; q < TPR; ++q) tot += part[q][tid];
-      __stcg(x + (int64_t)i * CT + tid, tot);
+      ll_store(xq + (int64_t)i * CT + tid, tot, flag);
+      x[(int64_t)i * CT + tid] = tot;
     }
-    __threadfence();
     __syncthreads();
-    if (tid == 0) {
-      st_release_gpu_u64(fb + i, epoch);
-      if (!ok_sh) atomicCAS(info, 0, -4);  // a flag never arrived
-    }
+    if (tid == 0 && !ok_sh) atomicCAS(info, 0, -4);  // a vector never arrived
   }
 }
 
@@ -1145,8 +1152,8 @@ int chol_plan_init(ba_handle* h, chol_plan& P, int64_t cn) {
   BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
   BA_CUDA(cudaFuncSetAttribute(k_chol_sweep<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem<float>()));
   BA_CUDA(cudaFuncSetAttribute(k_chol_sweep<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem<double>()));
-  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&P.d_sflags), 2 * CHOL_NBMAX * sizeof(unsigned long long)));
-  BA_CUDA(cudaMemset(P.d_sflags, 0, 2 * CHOL_NBMAX * sizeof(unsigned long long)));
+  BA_CUDA(cudaMalloc(&P.d_vq, 2 * sizeof(uint4) * (size_t)cn));
+  BA_CUDA(cudaMemset(P.d_vq, 0, 2 * sizeof(uint4) * (size_t)cn));
   {
     int dev = 0;
     BA_CUDA(cudaGetDevice(&dev));
@@ -1168,7 +1175,7 @@ void chol_plan_release(chol_plan& P) {
   cudaFree(P.d_prof);
   cudaFree(P.d_ctl);
   cudaFree(P.d_cnt);
-  cudaFree(P.d_sflags);
+  cudaFree(P.d_vq);
   for (int r = 0; r < CHOL_RMAX; ++r)
     if (P.peer_ipc[r])
       for (int j = 0; j < 3; ++j)
@@ -1431,10 +1438,12 @@ int chol_solve_t(ba_handle* h, chol_plan& P, const T* L, const double* b, double
   if (!by_steps && !P.sweep_off && (int)(cn / CT) <= P.sm_count) {
     int nbi = (int)(cn / CT);
     int64_t ldv = cn;
-    unsigned long long ep = ++P.sweep_epoch;
-    double* yv = P.d_y;
-    void* args[] = {(void*)&L, (void*)&ldv, (void*)&Dinv, (void*)&b, (void*)&yv, (void*)&x, (void*)&nbi,
-                    (void*)&P.d_sflags, (void*)&ep, (void*)&P.d_info};
+    if (++P.sweep_epoch == 0) ++P.sweep_epoch;  // (0 is the flag of the freshly cleared buffers)
+    unsigned ep = P.sweep_epoch;
+    uint4* yq = reinterpret_cast<uint4*>(P.d_vq);
+    uint4* xq = yq + cn;
+    void* args[] = {(void*)&L, (void*)&ldv, (void*)&Dinv, (void*)&b, (void*)&yq, (void*)&xq, (void*)&x, (void*)&nbi,
+                    (void*)&ep, (void*)&P.d_info};
     const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_chol_sweep<T>), dim3((unsigned)nbi),
                                                       dim3((unsigned)sweep_threads<T>()), args, (size_t)sweep_smem<T>(), s);
     if (e == cudaSuccess) return BA_OK;

@@ -47,9 +47,10 @@ struct chol_plan {
   bool solve_graph_32 = false;
   bool graph_off = false;        // capture not possible on the caller's stream
   bool attrs_set = false;
-  // persistent sweep kernel (both substitution sweeps in one cooperative launch): flags [2][CHOL_NBMAX], epoch-valued
-  unsigned long long* d_sflags = nullptr;
-  unsigned long long sweep_epoch = 0;
+  // persistent sweep kernel (both substitution sweeps in one cooperative launch): y and x as {value, flag} elements
+  // of 16 bytes (2 x cn of them), the flag being the launch's epoch
+  void* d_vq = nullptr;
+  unsigned sweep_epoch = 0;
   int sm_count = 0;
   bool sweep_off = false;        // cooperative launch not possible here: per-step kernels
   // distributed factorisation over the ranks of a sharded handle (tile row i belongs to rank i mod R)

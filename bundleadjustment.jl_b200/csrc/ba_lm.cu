@@ -31,6 +31,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <thread>
 #include "ba_internal.h"
 #include "ba_math.cuh"
@@ -240,7 +241,6 @@ int lm_prepare(ba_handle* h) {
   S.nempty = (int64_t)empty_cams.size();
   S.nctasks = (int64_t)tb.size();
 
-  int rc;
   const double t_host = ms_since(tp0);
   const auto tp1 = now();
   // one device allocation for the whole LM state of this handle (cudaMalloc is a synchronising driver call whose
@@ -357,6 +357,21 @@ int lm_prepare(ba_handle* h) {
             t_host, t_alloc + t_work, ms_since(tp2));
   S.ready = true;
   return BA_OK;
+}
+
+// First LM call on a handle: the schedules (host work, then one slab allocation) and the dense workspace of the exact /
+// mixed solve (2-3 GB of device allocations: tens of milliseconds of driver time) are set up CONCURRENTLY, the latter
+// on a helper thread -- on one rank only: with a communicator the workspace setup is collective and was done with it.
+int lm_prepare_all(ba_handle* h) {
+  ba_lm_state& S = h->lm;
+  if (S.ready || S.d_S || h->nranks > 1) {
+    int rc = lm_prepare(h);
+    return rc ? rc : lm_exact_workspace(h);
+  }
+  std::future<int> ws = std::async(std::launch::async, [h] { return lm_exact_workspace(h); });
+  const int rc = lm_prepare(h);
+  const int rc2 = ws.get();
+  return rc ? rc : rc2;
 }
 
 int lm_jtprod_cams(ba_handle* h, const double* x, const double* v, double* out) {
@@ -1071,9 +1086,8 @@ int ba_lm_step(ba_handle* h, const double* x, double lambda, double pcg_tol, int
     return BA_ERR_ARG;
   }
   if (h->group) return ba::group_lm_step(h, x, lambda, pcg_tol, pcg_max_iter, delta, dr2, obj, jtr, pcg_iters);
-  int rc = ba::lm_prepare(h);
+  int rc = ba::lm_prepare_all(h);
   if (rc) return rc;
-  if ((rc = ba::lm_exact_workspace(h))) return rc;
   BA_CUDA(cudaSetDevice(h->device));
   ba::Solver sv(h);
   ba_lm_state& S = h->lm;
@@ -1123,8 +1137,7 @@ int ba_lm_solve(ba_handle* h, double* x_inout, const ba_lm_params* prm_in, ba_lm
   const auto wall_prep = std::chrono::steady_clock::now();
   int rc;
   if (prm.solver != BA_SOLVER_AUTO && prm.solver != h->solver && (rc = ba_set_solver(h, prm.solver))) return rc;
-  if ((rc = lm_prepare(h))) return rc;
-  if ((rc = lm_exact_workspace(h))) return rc;
+  if ((rc = lm_prepare_all(h))) return rc;
   BA_CUDA(cudaSetDevice(h->device));
   Solver sv(h);
   ba_lm_state& S = h->lm;
