@@ -1434,7 +1434,7 @@ int chol_solve_t(ba_handle* h, chol_plan& P, const T* L, const double* b, double
   constexpr bool is32 = sizeof(T) == 4;
   // one persistent kernel for both sweeps when its cn / 128 CTAs can be co-resident (one per SM); BAGPU_SWEEP_STEPS=1:
   // the per-step kernels below (one launch per step, as a CUDA graph) -- the A/B switch and the route for larger systems
-  static const bool by_steps = getenv("BAGPU_SWEEP_STEPS") != nullptr;
+  const bool by_steps = getenv("BAGPU_SWEEP_STEPS") != nullptr;  // (read per call: the tests switch it)
   if (!by_steps && !P.sweep_off && (int)(cn / CT) <= P.sm_count) {
     int nbi = (int)(cn / CT);
     int64_t ldv = cn;

@@ -48,6 +48,20 @@ def test_device_fp32_cholesky_is_an_fp32_accurate_factor(ba, n):
     assert back <= 2e-6 and eL <= 1e-4 and res <= 5e-3      # cond(A) = 1e4: residual ~ cond * 1e-7
 
 
+@pytest.mark.parametrize("fp32", [False, True])
+def test_persistent_sweep_kernel_matches_the_per_step_kernels(ba, monkeypatch, fp32):
+    """Both substitution sweeps as one cooperative kernel (k_chol_sweep) against the per-step kernels that remain the
+    route for systems of more than 148 tile rows: same solution up to the order of the FP64 sums."""
+    n = 1500
+    A = _spd(n, 7)
+    A = 0.5 * (A + A.T)
+    b = np.random.default_rng(2).normal(size=n)
+    x1 = ba.lm.dbg_chol(A, b, fp32=fp32)[0]
+    monkeypatch.setenv("BAGPU_SWEEP_STEPS", "1")
+    x2 = ba.lm.dbg_chol(A, b, fp32=fp32)[0]
+    assert np.linalg.norm(x1 - x2) <= 1e-11 * np.linalg.norm(x2)
+
+
 def test_device_cholesky_flags_a_non_positive_pivot(ba):
     A = _spd(300, 3)
     A[200, 200] = -1.0
@@ -117,6 +131,25 @@ def test_mixed_solver_falls_back_to_the_fp64_factorisation(ba, monkeypatch):
     st = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=2, solver="mixed")
     assert st.mixed_fallbacks == st.iter and all(r["solver"] == "exact" for r in st.rows)
     m.close()
+
+
+@pytest.mark.parametrize("lam", [1e-4, 1e-8])
+def test_mixed_solver_at_tiny_lambda_never_returns_an_inexact_step(ba, lam):
+    """Far below the dampings LM uses the FP32 factor degrades (many CG iterations) or fails (non-positive pivot):
+    whichever route the solve takes -- CG with the FP32 factor, or the FP64 fall-back -- the step is the exact
+    solver's up to the conditioning of the system."""
+    p = ba.synth.make_problem((160, 10000, 50000))
+    m = ba.BALNLPModel(p.cam_idx, p.pnt_idx, p.pt2d, p.x0, p.ncams, p.npnts, p.nobs)
+    m.set_solver("exact")
+    d0, dr0, _, _, _ = ba.lm_step(m, p.x0, lam)
+    m.set_solver("mixed")
+    d1, dr1, _, _, it = ba.lm_step(m, p.x0, lam)
+    info = ba.lm.last_solve_info(m)
+    m.close()
+    e = rel_errors(d1, d0)
+    parity_report("mixed_vs_exact_tiny_lambda", lam=lam, norm=e[0], solver=info["solver"], iters=int(it), rel=info["rel"])
+    assert info["solver"] in ("mixed", "exact") and info["converged"]
+    assert e[0] <= 1e-6 and abs(dr1 - dr0) <= 1e-9 * abs(dr0)
 
 
 def test_exact_solver_reports_indefinite_system_as_exception(ba):
