@@ -84,6 +84,7 @@ SYMBOLS = {
     "ba_set_solver": (C.c_int, [_vp, C.c_int]),
     "ba_last_solve_info": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_f64), C.POINTER(_i32)]),
     "ba_dbg_chol": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "ba_dbg_probe_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "ba_dbg_chol32": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ba_last_eval_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ba_lm_default_params": (None, [C.POINTER(LMParams)]),

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) k_fp32_fma(float* out, int iters, float a
 extern "C" {
 
 // development probe: kind 0 = TF32 mma.sync m16n8k8, 1 = BF16 mma.sync m16n8k16, 2 = FP32 FMA; TFLOP/s
-__attribute__((visibility("default"))) int ba_dbg_probe_peak(int device, int kind, double* tflops) {
+int ba_dbg_probe_peak(int device, int kind, double* tflops) {
   if (!tflops || kind < 0 || kind > 2) return BA_ERR_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return BA_ERR_CUDA;
   cudaDeviceProp prop;

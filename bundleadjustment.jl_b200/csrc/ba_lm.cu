@@ -131,6 +131,11 @@ int lm_exact_workspace(ba_handle* h) {
   // sharded: distribute the factorisation over the ranks (falls back to the replicated one without peer access)
   if (h->nranks > 1 && h->comm) {
     if ((rc = chol_dist_setup(h, S.chol, S.d_S))) return rc;
+    // AUTO on many ranks: the FP32 factorisation is replicated (17.5 ms on Venice whatever N), the FP64 one is
+    // distributed and overtakes it from 8 ranks on (8 GPUs: 34.7 against 31.3 LM iterations/s) -- every rank decides
+    // alike (dist_ready is agreed among the ranks)
+    static const int many = getenv("BAGPU_MIXED_AUTO_MAX_RANKS") ? atoi(getenv("BAGPU_MIXED_AUTO_MAX_RANKS")) : 8;
+    if (S.mixed && h->solver == BA_SOLVER_AUTO && h->nranks >= many && S.chol.dist_ready) S.mixed = false;
     // NCCL sets up its channels for a message-size class inside the first collective of that class (tens of ms for the
     // ~1 GB integer allreduce of the assembly): pay that here, with the communicator, not in the first LM iteration
     const int64_t nbt = S.cn / CHOL_TILE, packed = nbt * (nbt + 1) / 2 * CHOL_TILE * CHOL_TILE;

@@ -46,7 +46,8 @@ enum {
  * FP64 Cholesky (what ldl_factorize + ldl_solve!, src/ldl_aux.jl:122-201,4-42, amount to after the ordering has
  * eliminated residual rows and points) plus refinement steps with the matrix-free FP64 residual.  BA_SOLVER_PCG is
  * the matrix-free preconditioned CG (stopped at pcg_tol).  AUTO: a dense solve up to 2048 cameras (MIXED from 8192
- * camera unknowns on, EXACT below), PCG above.
+ * camera unknowns on -- except on 8 or more ranks with peer access, where the distributed FP64 factorisation of EXACT
+ * is the faster one -- EXACT below), PCG above.
  * BA_SOLVER_MIXED is the reference's mixed-precision mode (src/lm.jl:92-98,165-173: facto_type below the model type,
  * "factorise in Float32, everything else in Float64"): the same explicit reduced camera
  * system, factorised in FP32 storage on the tensor cores (three TF32 MMAs per product: FP32-level accuracy), and that
@@ -227,6 +228,10 @@ BA_API int ba_dbg_chol(int device, int64_t n, const double* A_rowmajor, const do
  * application, accurate to about cond(A) * 1e-7); L_out receives the FP32 factor widened to doubles. */
 BA_API int ba_dbg_chol32(int device, int64_t n, const double* A_rowmajor, const double* b, double* x, double* L_out,
                          float* factor_ms, float* solve_ms);
+
+/* Development probe of the tensor / FMA rates the mixed-precision factorisation could build on (kind 0: TF32
+ * mma.sync.m16n8k8, 1: BF16 mma.sync.m16n8k16, 2: FP32 FMA), TFLOP/s; scripts/probe_peaks.py. */
+BA_API int ba_dbg_probe_peak(int device, int kind, double* tflops);
 
 /* ---- host-only helpers of the PCG deflation space (no GPU; exported so that they can be unit-tested) ------ */
 /* Eigenpairs of the Lanczos tridiagonal defined by the CG coefficients alpha[0..m), beta[0..m-1):
