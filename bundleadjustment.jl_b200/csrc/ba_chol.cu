@@ -368,7 +368,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __maxnreg__(152)  // 416 threads: 152 registers each fit the SM's register file
+__global__ void __maxnreg__(128)  // 13 warps are allocated as 16 (granularity 4): 16 x 32 x 128 registers = the SM's file
 k_chol_syrk_tc(float* __restrict__ A, int64_t ld, int k, int j0, int ncol, int nb, int* __restrict__ info, int nk) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   __shared__ __align__(8) unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
@@ -1147,9 +1147,7 @@ int chol_plan_init(ba_handle* h, chol_plan& P, int64_t cn) {
   BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<double>())));
   BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<double>())));
   BA_CUDA((cudaFuncSetAttribute(k_chol_syrk<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
-  BA_CUDA((cudaFuncSetAttribute(k_chol_syrk<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
   BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
-  BA_CUDA((cudaFuncSetAttribute(k_chol_trsm<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<float>())));
   BA_CUDA(cudaFuncSetAttribute(k_chol_sweep<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem<float>()));
   BA_CUDA(cudaFuncSetAttribute(k_chol_sweep<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem<double>()));
   BA_CUDA(cudaMalloc(&P.d_vq, 2 * sizeof(uint4) * (size_t)cn));
@@ -1486,7 +1484,6 @@ int chol_solve_t(ba_handle* h, chol_plan& P, const T* L, const double* b, double
 }  // namespace
 
 int chol_factor_dist(ba_handle* h, chol_plan& P, double* A, cudaStream_t s) { return chol_factor_dist_t<double>(h, P, A, s); }
-int chol_factor_dist32(ba_handle* h, chol_plan& P, float* A32, cudaStream_t s) { return chol_factor_dist_t<float>(h, P, A32, s); }
 int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, double* x, cudaStream_t s) {
   return chol_solve_t<double>(h, P, L, b, x, s);
 }

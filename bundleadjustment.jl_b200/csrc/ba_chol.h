@@ -81,8 +81,8 @@ int chol_solve(ba_handle* h, chol_plan& P, const double* L, const double* b, dou
 // Mixed precision (src/lm.jl:92-98,165-173: facto_type below the model type): the same factorisation with FP32 storage
 // and three-TF32-term tensor-core products (FP32-level accuracy); A32 is cn x cn floats, leading dimension cn.  The
 // sweeps read the FP32 factor and compute in FP64 (right-hand side and solution are doubles): a preconditioner.
+// Replicated on every rank of a sharded handle (a distributed variant was measured slower).
 int chol_factor32(ba_handle* h, chol_plan& P, float* A32, cudaStream_t s, int* info_host);
-int chol_factor_dist32(ba_handle* h, chol_plan& P, float* A32, cudaStream_t s);
 int chol_solve32(ba_handle* h, chol_plan& P, const float* L32, const double* b, double* x, cudaStream_t s);
 
 }  // namespace ba
