@@ -245,6 +245,26 @@ def test_lm_warm_start_and_max_iter_status(ba):
     assert st2.objective <= st1.objective
 
 
+def test_two_stage_run_mixed_then_exact(ba):
+    """The reference's two-stage runs (src/benchmark_diffprec.jl:60-94: a first Levenberg_Marquardt with the
+    factorisation in Float32, a second one in Float64 started from its solution, `x = ...`): stage one with the mixed
+    solver, stage two with the exact one, started from stage one's solution."""
+    p = ba.synth.make_problem((40, 1500, 8000))
+    m = _model(ba, p)
+    one = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, solver="exact")
+    s1 = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, ite_max=3, solver="mixed")
+    assert s1.status == "max_iter" and {r["solver"] for r in s1.rows} <= {"mixed", "exact"}
+    s2 = ba.Levenberg_Marquardt(m, "LDL", "AMD", "None", False, x=s1.solution, solver="exact")
+    assert all(r["solver"] == "exact" for r in s2.rows)
+    assert s2.rows[0]["f"] == pytest.approx(s1.objective, rel=1e-12)
+    # (stage two restarts the damping at lambda = max(30, 1e10 / ||J'r||) and tests its steps against ITS starting point,
+    # src/lm.jl:59,391-405 -- near a solution that is a huge lambda and an early `small_step`, as in the reference: the
+    # pair need not end where the single run ends)
+    assert s2.status not in ("exception", "unknown") and s2.objective <= s1.objective
+    assert one.status not in ("exception", "unknown") and one.objective <= s1.objective
+    m.close()
+
+
 def test_lm_nan_start_reports_exception(ba):
     # theta == 0 on one camera -> NaN residuals -> NaN step -> status :exception (src/lm.jl:297-302,401)
     p = ba.synth.make_problem((9, 300, 1500))
