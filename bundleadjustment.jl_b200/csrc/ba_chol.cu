@@ -1,8 +1,10 @@
-// ba_chol.cu -- blocked FP64 Cholesky A = L L' of the (explicitly assembled, Jacobi-scaled) reduced camera
-// system, and the two triangular sweeps; hand-written for sm_100a.
+// ba_chol.cu -- blocked Cholesky A = L L' of the (explicitly assembled, Jacobi-scaled) reduced camera system, in FP64
+// (the exact solver) and in FP32 on the tcgen05 tensor cores (the mixed-precision solver), and the two triangular
+// sweeps; hand-written for sm_100a.
 //
 // Reference counterpart: the numeric factorisation and the L / D / L' sweeps of src/ldl_aux.jl:122-201,4-42 on
-// the camera block (after the ordering has eliminated residual rows and points), SURVEY.md section 8 row f2.
+// the camera block (after the ordering has eliminated residual rows and points); the
+// FP32 instantiation is the reference's facto_type < T mode (src/lm.jl:92-98,165-173), row f4.
 //
 // Layout: A is cn x cn row-major (cn a multiple of 128), lower triangle live.  Right-looking by 128-column panels:
 //   potrf  (1 CTA)        : the 128 x 128 diagonal block in shared memory (16-column sub-panels), plus its
@@ -16,6 +18,10 @@
 // the next panel's column is launched first, then the next potrf + trsm run on a side stream under the rest
 // of the trailing update.
 // Roofline: n^3/3 flops against the FP64 peak (ba_measure_fp64_peak; DMMA and DFMA peaks coincide on B200).
+// FP32 (templates instantiated for float): the same panels, look-ahead and diagonal blocks (still factorised in FP64:
+// a latency chain); the panel solve on the legacy tensor path (mma.sync TF32, three-term split); the trailing update --
+// the n^3/3 flops -- in k_chol_syrk_tc: persistent, warp-specialised, tcgen05.mma kind::tf32 with the accumulators in
+// tensor memory (see there).  Sweeps: k_chol_sweep, both of them as one persistent cooperative kernel.
 #include <unistd.h>
 #include <algorithm>
 #include <cstdlib>

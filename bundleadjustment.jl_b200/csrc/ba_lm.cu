@@ -1,6 +1,8 @@
-// ba_lm.cu -- device-resident Levenberg-Marquardt (K5-K8): block JtJ / Jtr assembly, Schur
-// complement onto the reduced camera system, PCG (block-Jacobi + a coarse level over camera clusters and
-// deflation vectors harvested from the PCG solves themselves), back-substitution, and the LM loop.
+// ba_lm.cu -- device-resident Levenberg-Marquardt (K5-K13): block JtJ / Jtr assembly, Schur
+// complement onto the reduced camera system, its solve -- PCG (block-Jacobi + a coarse level over camera clusters and
+// deflation vectors harvested from the PCG solves themselves), or the explicitly assembled system factorised by
+// ba_chol.cu: in FP64 (exact solver) or in FP32 on the tensor cores as the preconditioner of FP64 CG (mixed solver,
+// Solver::mixed_solve) -- back-substitution, and the LM loop.
 //
 // Reference semantics: src/lm.jl:15-418 (control flow, kept decision for decision) with the damped
 // solve  (J'J + lambda I) delta = -J'r  that src/lm.jl:61-100,138-152,175-229 obtains from
