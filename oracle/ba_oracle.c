@@ -9,12 +9,17 @@
  * The reference itself (Julia) cannot run in this container (no julia binary), so the
  * oracle is a restatement.  Pinning status:
  *   - residual path  : PINNED bit-exactly by the reference's own golden vector
- *                      (test/runtests.jl:15-27) and known-answer tests (:6-8);
- *                      see tests/test_oracle_golden.py.
+ *                      (test/runtests.jl:15-27) and known-answer tests (:6-8), and bit-exactly
+ *                      on 150 more observations by the reference's own Python model
+ *                      (src/SolverScipy.py:34-72 `fun`, imported in the build container:
+ *                      tests/golden/make_scipy_reference_golden.py); tests/test_oracle.py.
  *   - mul_sparse     : pinned by the property test of test/runtests.jl:91-108.
- *   - jac_structure, jac_coord, LDL solve, LM loop: PARITY UNPINNED by reference tests
- *     (the reference has no test for them).  They are anchored on the pinned residual
- *     (central finite differences), on a dense solve, and on the formulas cited below.
+ *   - jac_coord      : PINNED to 1.2e-12 (row-relative) by the Jacobian of the reference's Python
+ *                      `fun`, differentiated numerically in 80-bit arithmetic (same fixture):
+ *                      reference-held code, though not the reference's Julia Jacobian itself.
+ *   - jac_structure, LDL solve, LM loop: PARITY UNPINNED by reference tests (the reference has
+ *     no test for them).  They are anchored on the hand-checkable structure formula, on a
+ *     dense solve, on SuperLU / LAPACK, and on the formulas cited below.
  *
  * Every function cites the reference file:line it follows (paths relative to the
  * reference repository root).  Build: see oracle/Makefile (-O2 -ffp-contract=off).

@@ -108,6 +108,44 @@ def test_jac_coord_golden_point_fd(oracle, golden):
         assert np.all(np.abs(vals[k][:, :9] - J[:, :9]) <= 5e-6 * scale[:, :9])
 
 
+# ---- the reference's own Python model (src/SolverScipy.py:34-72), tests/golden/make_scipy_reference_golden.py ----
+@pytest.fixture(scope="module")
+def scipy_model_golden():
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "reference_scipy_model.json")) as f:
+        g = json.load(f)
+    return {k: (np.array(v) if isinstance(v, list) else v) for k, v in g.items()}
+
+
+def test_residuals_match_the_references_python_model(oracle, scipy_model_golden):
+    """cons! of the oracle against `fun` of the reference's Python implementation (an independent statement of the
+    same camera model by the reference's authors) on 150 observations, 6 cameras with rotations up to 1.3 rad."""
+    g = scipy_model_golden
+    npnts = int(g["shape"][1])
+    cx = oracle.cons(g["cam_idx"], g["pnt_idx"], g["pt2d"], g["x"], npnts)
+    ref = g["residuals"]
+    scale = np.abs(g["pt2d"]).max()       # the residual is a difference of pixel coordinates of this size
+    assert np.abs(cx - ref).max() <= 1e-12 * scale
+
+
+def test_hand_derived_jacobian_matches_the_references_python_model(oracle, scipy_model_golden):
+    """jac_coord! (the hand-derived blocks of src/JacobianByHand.jl as restated by the oracle) against the Jacobian of
+    the reference's Python `fun`, differentiated numerically in 80-bit arithmetic (accurate to ~1e-12): every one of
+    the 24 entries of every observation, relative to the largest entry of its row."""
+    g = scipy_model_golden
+    npnts = int(g["shape"][1])
+    vals = oracle.jac_coord(g["cam_idx"], g["pnt_idx"], g["x"], npnts).reshape(-1, 2, 12)
+    ref = g["jac_vals"].reshape(-1, 2, 12)
+    scale = np.abs(ref).max(axis=2, keepdims=True)
+    err = np.abs(vals - ref) / scale
+    assert err.max() <= 1e-10, err.max()
+    # and entry-wise for the entries that are not cancellation residues (>= 1e-6 of the row's largest)
+    big = np.abs(ref) >= 1e-6 * scale
+    assert (np.abs(vals - ref)[big] / np.abs(ref)[big]).max() <= 1e-6
+
+
 def test_jac_coord_thread_chunks_same_values(oracle, ba):
     p = small_problem(ba)
     a = oracle.jac_coord(p.cam_idx, p.pnt_idx, p.x0, p.npnts, nthreads=1)
