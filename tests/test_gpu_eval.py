@@ -28,6 +28,25 @@ def test_golden_residual_vector_on_gpu(ba, golden):
     assert fr.nls_meta.nequ == 10 and fr.nls_meta.nnzj == 120 and fr.meta.name.endswith("-feasres")
 
 
+# ---- the reference's own Python model (src/SolverScipy.py:34-72; tests/golden/make_scipy_reference_golden.py) -------
+def test_residuals_and_jacobian_match_the_references_python_model_on_gpu(ba):
+    """The CUDA path against reference-held code directly (no oracle in between): residuals of the reference's `fun`,
+    and its Jacobian differentiated numerically in 80-bit arithmetic (accurate to ~1e-12)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_scipy_model.json")) as f:
+        g = json.load(f)
+    ncams, npnts, nobs = g["shape"]
+    x = np.array(g["x"])
+    m = ba.BALNLPModel(np.array(g["cam_idx"]), np.array(g["pnt_idx"]), np.array(g["pt2d"]), x, ncams, npnts, nobs)
+    cx, vals = m.cons_jac_coord_(x)
+    m.close()
+    assert np.abs(cx - np.array(g["residuals"])).max() <= TOL * np.abs(g["pt2d"]).max()
+    ref = np.array(g["jac_vals"]).reshape(-1, 2, 12)
+    err = np.abs(vals.reshape(-1, 2, 12) - ref) / np.abs(ref).max(axis=2, keepdims=True)
+    assert err.max() <= TOL, err.max()
+
+
 @pytest.mark.parametrize("variant", ["plain", "stress", "big_rotations"])
 def test_residual_and_jacobian_match_oracle(ba, oracle, variant):
     p = small_problem(ba, shape=(9, 300, 1500), stress=variant == "stress", big_rotations=variant == "big_rotations")
