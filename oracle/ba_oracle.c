@@ -17,9 +17,12 @@
  *   - jac_coord      : PINNED to 1.2e-12 (row-relative) by the Jacobian of the reference's Python
  *                      `fun`, differentiated numerically in 80-bit arithmetic (same fixture):
  *                      reference-held code, though not the reference's Julia Jacobian itself.
- *   - jac_structure, LDL solve, LM loop: PARITY UNPINNED by reference tests (the reference has
- *     no test for them).  They are anchored on the hand-checkable structure formula, on a
- *     dense solve, on SuperLU / LAPACK, and on the formulas cited below.
+ *   - jac_structure  : the SET of (row, column) positions pinned by the reference's Python
+ *                      `bundle_adjustment_sparsity` (src/SolverScipy.py:75-88, same fixture); the
+ *                      ORDER of the entries (Julia's own) by the hand-checkable formula only.
+ *   - LDL solve, LM loop: PARITY UNPINNED by reference tests (the reference has no test for
+ *     them).  They are anchored on a dense solve, on SuperLU / LAPACK, on two elimination
+ *     orders agreeing with each other, and on the formulas cited below.
  *
  * Every function cites the reference file:line it follows (paths relative to the
  * reference repository root).  Build: see oracle/Makefile (-O2 -ffp-contract=off).

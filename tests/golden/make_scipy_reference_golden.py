@@ -9,6 +9,8 @@ reference file as they are (the file's benchmark script below them, which reads 
 
 What is generated, on a small deterministic BAL-shaped problem (bundleadjustment.jl_b200/synth.py, incl. large rotations):
  * `residuals`: `fun(params)` in float64 -- pins `cons!` beyond the five observations of test/runtests.jl;
+ * `jac_pattern_rows_cols_1based`: the sparsity pattern of `bundle_adjustment_sparsity` (src/SolverScipy.py:75-88) in the
+   Julia layout -- pins the SET of positions `jac_structure!` produces (their order is Julia's own);
  * `jac_vals`: the 2 x 12 Jacobian block of every observation in the layout of `jac_coord!` (row 1 then row 2; columns
    point x, y, z, then camera r, t, k1, k2, f -- src/BALNLPModels.jl:161-206), obtained from the reference's `fun` by
    central differences evaluated in 80-bit extended precision (numpy longdouble): truncation ~ h^2 and rounding
@@ -36,7 +38,7 @@ def reference_functions():
     head = text.split("\nimport time")[0]          # the function definitions; not the benchmark script below them
     ns = {}
     exec(compile(head, SRC, "exec"), ns)
-    return ns["fun"]
+    return ns["fun"], ns["bundle_adjustment_sparsity"]
 
 
 def to_reference_layout(p, x, dtype):
@@ -49,7 +51,7 @@ def to_reference_layout(p, x, dtype):
 
 def main():
     import bundleadjustment.jl_b200.synth as synth
-    fun = reference_functions()
+    fun, sparsity = reference_functions()
     p = synth.make_problem((6, 40, 150), big_rotations=True)
     ci, pi = p.cam_idx - 1, p.pnt_idx - 1
     pts2d = p.pt2d.reshape(-1, 2)
@@ -87,12 +89,26 @@ def main():
         cols = np.concatenate([pc, cc])
         vals[k, 0] = J1[2 * k, cols].astype(np.float64)
         vals[k, 1] = J1[2 * k + 1, cols].astype(np.float64)
+    # the sparsity pattern the reference's Python hands to scipy (src/SolverScipy.py:75-88), converted to the Julia
+    # layout (x = [points; cameras], camera columns r, t, k1, k2, f; 1-based rows and columns) as a sorted list of pairs
+    A = sparsity(p.ncams, p.npnts, ci, pi).tocoo()
+    inv_perm = {ref: jl for jl, ref in enumerate(cam_perm)}   # reference camera slot -> Julia camera slot
+    pairs = []
+    for r_, c_ in zip(A.row.tolist(), A.col.tolist()):
+        if c_ < 9 * p.ncams:
+            cam, slot = divmod(c_, 9)
+            col = 3 * p.npnts + 9 * cam + inv_perm[slot]
+        else:
+            col = c_ - 9 * p.ncams
+        pairs.append((r_ + 1, col + 1))
+    pairs.sort()
     fx = {
         "source": "src/SolverScipy.py:34-72 (rotate, project, fun), imported from /root/reference",
         "shape": [p.ncams, p.npnts, p.nobs], "synth": "make_problem((6, 40, 150), big_rotations=True)",
         "cam_idx": p.cam_idx.tolist(), "pnt_idx": p.pnt_idx.tolist(), "pt2d": p.pt2d.tolist(), "x": p.x0.tolist(),
         "residuals": np.asarray(res, dtype=np.float64).tolist(),
         "jac_vals": vals.reshape(-1).tolist(),
+        "jac_pattern_rows_cols_1based": pairs,
         "jac_how": "central differences of the reference's fun() in 80-bit extended precision, h = 1e-7 max(1, |x_j|); "
                    "h and h/2 agree to %.1e relative to the largest entry of a row" % agree,
     }

@@ -146,6 +146,19 @@ def test_hand_derived_jacobian_matches_the_references_python_model(oracle, scipy
     assert (np.abs(vals - ref)[big] / np.abs(ref)[big]).max() <= 1e-6
 
 
+def test_jac_structure_positions_match_the_references_python_sparsity(oracle, scipy_model_golden):
+    """The set of (row, column) positions of jac_structure! against `bundle_adjustment_sparsity` of the reference's
+    Python (src/SolverScipy.py:75-88), converted to the Julia layout; the ORDER of the entries is Julia's own and is
+    covered by the structure-formula tests above."""
+    g = scipy_model_golden
+    npnts, nobs = int(g["shape"][1]), int(g["shape"][2])
+    rows, cols = oracle.jac_structure(g["cam_idx"], g["pnt_idx"], npnts)
+    assert len(rows) == 24 * nobs
+    got = sorted(zip(rows.tolist(), cols.tolist()))
+    ref = [tuple(int(v) for v in rc) for rc in g["jac_pattern_rows_cols_1based"].tolist()]
+    assert got == ref
+
+
 def test_jac_coord_thread_chunks_same_values(oracle, ba):
     p = small_problem(ba)
     a = oracle.jac_coord(p.cam_idx, p.pnt_idx, p.x0, p.npnts, nthreads=1)
